@@ -1,0 +1,203 @@
+"""Pin oracle/ppst_oracle.py against outputs of the unmodified reference (tests/golden/*.npz,
+made by oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppst_oracle as O
+from golden_util import check_summary, sub_state_dict
+
+T = torch.from_numpy
+
+
+def test_upfirdn2d_all_cases(golden):
+    g = golden("ops")
+    for name in g["upfirdn2d/names"]:
+        up, down, p0, p1 = (int(v) for v in g["upfirdn2d/%s/cfg" % name])
+        y = O.upfirdn2d(T(g["upfirdn2d/%s/x" % name]), T(g["upfirdn2d/%s/k" % name]), up, down, (p0, p1))
+        want = g["upfirdn2d/%s/y" % name]
+        assert tuple(y.shape) == want.shape, name
+        assert np.abs(y.numpy() - want).max() <= 2e-6, name
+
+
+def test_upfirdn2d_hot_size(golden):
+    g = golden("ops")
+    y = O.upfirdn2d(T(g["upfirdn2d_hot/x"]), O.make_kernel([1, 2, 1]))
+    check_summary(g, "upfirdn2d_hot/y", y, atol=2e-6)
+
+
+def test_fused_leaky_relu_fwd_bwd(golden):
+    g = golden("ops")
+    for name in g["flrelu/names"]:
+        slope, scale = (float(v) for v in g["flrelu/%s/cfg" % name])
+        x, b = T(g["flrelu/%s/x" % name]), T(g["flrelu/%s/b" % name])
+        y = O.fused_leaky_relu(x, b, slope, scale)
+        assert np.array_equal(y.numpy(), g["flrelu/%s/y" % name]), name
+        gx, gb = O.fused_leaky_relu_backward(T(g["flrelu/%s/go" % name]), y, slope, scale)
+        assert np.abs(gx.numpy() - g["flrelu/%s/gx" % name]).max() <= 1e-6
+        assert np.abs(gb.numpy() - g["flrelu/%s/gb" % name]).max() <= 1e-4
+
+
+LAYER_TOL = 2e-5
+
+
+def _close(a, want, tol=LAYER_TOL):
+    assert tuple(a.shape) == want.shape
+    err = np.abs(a.numpy() - want).max()
+    assert err <= tol, err
+
+
+def test_conv_layers(golden):
+    g = golden("layers")
+    cases = {
+        "convlayer_1x1_act": dict(ksize=1),
+        "convlayer_3x3_reflect_in": dict(ksize=3, reflection_pad=True, norm="in"),
+        "convlayer_down_reflect": dict(ksize=3, downsample=True, blur_kernel=(1, 2, 1), reflection_pad=True),
+        "convlayer_skip_down": dict(ksize=1, downsample=True, blur_kernel=(1, 2, 1), activate=False, norm="in"),
+        "convlayer_1x1_bias_in_noact": dict(ksize=1, activate=False, norm="in"),
+        "convlayer_1x1_skip_plain": dict(ksize=1, activate=False),
+    }
+    for name, kw in cases.items():
+        sd = sub_state_dict(g, name)
+        y = O.conv_layer(sd, "", T(g[name + "/in0"]), **kw)
+        _close(y, g[name + "/out"])
+
+
+def test_res_blocks(golden):
+    g = golden("layers")
+    for name, norm in (("resblock_in", "in"), ("resblock_none", None)):
+        y = O.res_block(sub_state_dict(g, name), "", T(g[name + "/in0"]), norm=norm)
+        _close(y, g[name + "/out"])
+
+
+def test_styled_conv_and_torgb(golden):
+    g = golden("layers")
+    for name, ups in (("styled_plain", False), ("styled_up_small", True), ("styled_up_fused", True)):
+        sd = sub_state_dict(g, name)
+        y = O.styled_conv(sd, "", T(g[name + "/in0"]), T(g[name + "/in1"]), upsample=ups, noise=T(g[name + "/in2"]))
+        _close(y, g[name + "/out"])
+    sd = sub_state_dict(g, "torgb")
+    _close(O.to_rgb(sd, "", T(g["torgb/in0"]), T(g["torgb/in1"])), g["torgb/out"])
+
+
+def test_generator_blocks(golden):
+    g = golden("layers")
+    sd = sub_state_dict(g, "residual_block")
+    _close(O.residual_block(sd, "", T(g["residual_block/in0"])), g["residual_block/out"])
+    sd = sub_state_dict(g, "generator_modulation")
+    x, s = T(g["generator_modulation/in0"]), T(g["generator_modulation/in1"])
+    y = x * O.equal_linear(s, sd["scale.weight"], sd["scale.bias"])[:, :, None, None] \
+        + O.equal_linear(s, sd["bias.weight"], sd["bias.bias"])[:, :, None, None]
+    _close(y, g["generator_modulation/out"])
+    name = "respres_block"
+    sd = sub_state_dict(g, name)
+    x, s, n1, n2 = (T(g["%s/in%d" % (name, i)]) for i in range(4))
+    skip = O.conv_layer(sd, "skip.", x, 1, activate=False)
+    r = O.styled_conv(sd, "conv1.", x, s, noise=n1)
+    r = O.styled_conv(sd, "conv2.", r, s, noise=n2)
+    _close((skip + r) / O.SQRT2, g[name + "/out"])
+    for name in ("upres_block_small", "upres_block_fused"):
+        sd = sub_state_dict(g, name)
+        x, s, n1, n2 = (T(g["%s/in%d" % (name, i)]) for i in range(4))
+        skip = O.conv_layer(sd, "skip.", x, 1, activate=True)
+        skip = torch.nn.functional.interpolate(skip, scale_factor=2, mode="bilinear", align_corners=False)
+        r = O.styled_conv(sd, "conv1.", x, s, upsample=True, noise=n1)
+        r = O.styled_conv(sd, "conv2.", r, s, noise=n2)
+        _close((skip + r) / O.SQRT2, g[name + "/out"])
+
+
+def test_function_py(golden):
+    g = golden("function_py")
+    x = T(g["x"])
+    m, s = O.calc_mean_std(x)
+    _close(m, g["mean"], 1e-6)
+    _close(s, g["std"], 1e-6)
+    _close(O.nor_mean_std(x), g["nor_mean_std"], 1e-5)
+    _close(O.nor_mean(x)[0], g["nor_mean"], 1e-6)
+    _close(O.calc_cov(x), g["cov"], 1e-5)
+
+
+def test_mask_labels_bit_exact():
+    lab = O.make_label_map(2, 64, 48)
+    assert set(np.unique(lab.numpy())) <= {0, 1, 2}
+    oh = O.mask_labels(lab[0].numpy())
+    assert oh.shape == (3, 64, 48) and np.array_equal(oh.sum(0), np.ones((64, 48)))
+    for i in range(3):
+        assert np.array_equal(oh[i] == 1.0, lab[0].numpy() == i)
+    assert [O.aggregate_part_label(i) for i in range(18)].count(2) == 2
+
+
+@pytest.fixture(scope="module")
+def full_nets():
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    return O.make_networks(0)
+
+
+def test_full_networks_512(golden, full_nets):
+    """E1 / E2 (plain + corr-warp) / G (plain + extract) / Rselfcorr / corrm / warp at 512x512, B=1,
+    against the reference run with the same synthetic state_dict."""
+    g = golden("nets")
+    sdE1, sdE2, sdG = full_nets
+    c = O.make_portraits(1, 512, 512, seed=1234)
+    s = O.make_portraits(1, 512, 512, seed=4321, smooth=True)
+    noises = O.make_noises(1, 512, 512)
+    tol = 1e-4      # north_star fp32 tolerance: max-abs 1e-4 per layer
+    with torch.no_grad():
+        tE1, tG = {}, {}
+        sp_c = O.encoder_con(sdE1, c, taps=tE1)
+        check_summary(g, "E1/sp_c", sp_c, atol=tol, stats_tol=1e-4)
+        for k in ("FromRGB", "ResBlockDownBy1", "ResBlockDownBy2", "ResBlockDownBy4"):
+            key = "tap/E1/" + (k if k == "FromRGB" else "DownToSpatialCode." + k)
+            check_summary(g, key, tE1[k], atol=tol)
+        gl_c, _ = O.encoder_col(sdE2, c)
+        for i in range(4):
+            assert np.abs(gl_c[i].numpy() - g["E2/gl_c/%d" % i]).max() <= 1e-6
+        rgb, fea_c, fea_c1 = O.generator(sdG, sp_c, gl_c, extract_features=True, noises=noises, taps=tG)
+        for k in ["SpatialCodeModulation"] + ["HeadResnetBlock%d" % i for i in range(4)] + \
+                ["UpsamplingResBlock%d" % r for r in (16, 32, 64)]:
+            check_summary(g, "tap/G/" + k, tG[k], atol=tol)
+        check_summary(g, "G/rec_c", rgb, atol=tol, stats_tol=1e-4)
+        check_summary(g, "G/fea_c", fea_c, atol=tol)
+        check_summary(g, "G/fea_c1", fea_c1, atol=tol)
+        sp_s = O.encoder_con(sdE1, s)
+        gl_s, _ = O.encoder_col(sdE2, s)
+        _, fea_s, fea_s1 = O.generator(sdG, sp_s, gl_s, extract_features=True, noises=noises)
+        rs_c, rs_s = O.rselfcorr(fea_c1), O.rselfcorr(fea_s1)
+        check_summary(g, "Rselfcorr/c", rs_c, atol=tol)
+        fc, fs = torch.cat((fea_c, rs_c), 1), torch.cat((fea_s, rs_s), 1)
+        corr = O.corrm(fs, fc)
+        check_summary(g, "corrm/corr", corr, atol=2e-3)   # softmax at T=0.01 amplifies 1e-5 cosine noise
+        assert (corr.sum(-1) - 1).abs().max() < 1e-4
+        gl_s2, gl_w = O.encoder_col(sdE2, s, corrmatrix=[corr])      # list form, as the evaluator passes it
+        for i in range(4):
+            assert np.abs(gl_w[i].numpy() - g["E2/gl_w/%d" % i]).max() <= 2e-5
+            assert np.abs(gl_s2[i].numpy() - g["E2/gl_s/%d" % i]).max() <= 1e-6
+        check_summary(g, "G/swap", O.generator(sdG, sp_c, gl_w, noises=noises), atol=5e-4)
+        check_summary(g, "G/swap_alpha0.5", O.generator(sdG, sp_c, O.lerp(gl_c, gl_w, 0.5), noises=noises), atol=5e-4)
+        check_summary(g, "warp/full", O.model_warp(sp_s, corr), atol=1e-3)
+        check_summary(g, "warp/unfold", O.model_warp(torch.nn.functional.avg_pool2d(s, 2), corr), atol=1e-3)
+        # mask branch
+        x2 = torch.cat([c, s], 0)
+        lab = O.make_label_map(2, 512, 512)
+        assert int(lab.to(torch.int64).sum()) == int(g["labels/sum"][0])
+        onehot = torch.stack([torch.tensor(O.mask_labels(lab[b].numpy()), dtype=torch.float) for b in range(2)])
+        corr2 = torch.cat([corr, O.corrm(fc, fs)], 0)
+        v, pm, vw, pmw = O.encoder_col(sdE2, x2, mask=onehot, corrmatrix=corr2)
+        for i in range(4):
+            assert np.abs(v[i].numpy() - g["E2mask/v/%d" % i]).max() <= 1e-6
+            assert np.abs(vw[i].numpy() - g["E2mask/vw/%d" % i]).max() <= 2e-5
+        for i in range(12):
+            assert np.abs(pm[i].numpy() - g["E2mask/pm/%d" % i]).max() <= 1e-6
+            assert np.abs(pmw[i].numpy() - g["E2mask/pmw/%d" % i]).max() <= 2e-5
+
+
+def test_plain_path_non_square(golden, full_nets):
+    g = golden("nets")
+    sdE1, sdE2, sdG = full_nets
+    c2 = O.make_portraits(1, 256, 384, seed=5)
+    n2 = O.make_noises(1, 256, 384, seed=6)
+    with torch.no_grad():
+        sp2 = O.encoder_con(sdE1, c2)
+        gl2, _ = O.encoder_col(sdE2, c2)
+        check_summary(g, "plain256x384/sp", sp2, atol=1e-4)
+        check_summary(g, "plain256x384/rec", O.generator(sdG, sp2, gl2, noises=n2), atol=1e-4)
