@@ -1,0 +1,251 @@
+/* ppst_b200 -- C ABI of the B200-native (sm_100a) PPST swap / inference hot path.
+ *
+ * Plain pointers and sizes only: no torch / ATen / pybind types cross this boundary.
+ * Ownership: the caller allocates every buffer (inputs, outputs, scratch); kernels never allocate
+ * or free device memory.  Every entry point enqueues on `stream` (a cudaStream_t passed as void*,
+ * NULL = legacy default stream) and returns without synchronising.
+ * Return value: 0 on success, a negative PPST_ERR_* code otherwise; ppst_last_error() returns the
+ * text of the last error raised on the calling thread.  No C++ exception crosses the ABI.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference
+ * repository root, wangxb29/PPST).
+ */
+#ifndef PPST_B200_H_
+#define PPST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PPST_API __attribute__((visibility("default")))
+#else
+#define PPST_API
+#endif
+
+/* element types of activation buffers */
+enum { PPST_F32 = 0, PPST_F16 = 1, PPST_BF16 = 2 };
+
+/* error codes */
+enum {
+  PPST_OK = 0,
+  PPST_ERR_ARG = -1,        /* bad shape / null pointer / unsupported combination */
+  PPST_ERR_DTYPE = -2,      /* unsupported element type */
+  PPST_ERR_CUDA = -3,       /* a CUDA runtime / driver call failed (text in ppst_last_error) */
+  PPST_ERR_UNSUPPORTED = -4 /* configuration the kernels do not implement (the reference would return
+                               uninitialised memory here, upfirdn2d_kernel.cu:172-223; we refuse) */
+};
+
+/* activation selectors (fused_bias_act `act` argument, fused_bias_act_kernel.cu:37-46) */
+enum { PPST_ACT_LINEAR = 1, PPST_ACT_LRELU = 3 };
+
+PPST_API const char* ppst_last_error(void);
+PPST_API int ppst_version(void);
+/* number of kernels launched by this library on the calling process since load (for bench `gpu_launches`) */
+PPST_API long long ppst_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * stylegan2_op plugin operators
+ * ------------------------------------------------------------------------------------------- */
+
+/* Replaces the pybind entry `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ * (models/networks/stylegan2_op/fused_bias_act.cpp:11-20, kernel fused_bias_act_kernel.cu:19-49,
+ * host wrapper :52-99).
+ *   y[i] = f(x[i] + b[(i / step_b) % size_b]) * scale
+ *   act=3: grad=0 f(v)= v>0 ? v : v*alpha ; grad=1 f(v)= ref[i]>0 ? v : v*alpha ; grad=2 f=0
+ *   act=1: grad=0,1 f(v)=v ; grad=2 f=0
+ * `b` may be NULL (size_b = 0: no bias), `ref` may be NULL unless grad==1 with act==3.
+ * n = number of elements; step_b = prod(x.shape[2:]).  In-place (y == x) is allowed. */
+PPST_API int ppst_fused_bias_act(void* y, const void* x, const void* b, const void* ref, int64_t n, int64_t step_b,
+                        int64_t size_b, int act, int grad, float alpha, float scale, int dtype, void* stream);
+
+/* grad_bias[c] = sum over (batch, spatial) of g[n, c, :]  -- the reduction the reference does with
+ * `grad_input.sum(dim)` (stylegan2_op/fused_act.py:37-42).  g is [outer, size_b, step_b]; out is f32[size_b]. */
+PPST_API int ppst_bias_grad_reduce(float* out, const void* g, int64_t outer, int64_t size_b, int64_t step_b, int dtype,
+                          void* stream);
+
+/* Replaces `upfirdn2d_op.upfirdn2d(input[major,H,W,minor], kernel, up_x, up_y, down_x, down_y,
+ * pad_x0, pad_x1, pad_y0, pad_y1)` (stylegan2_op/upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu:53-137,140-272).
+ * Zero-insert upsample, pad (negative pads crop), FIR with the flipped `kernel` (f32 [kh,kw], device
+ * memory), decimate.  y is [major, out_h, out_w, minor] with
+ *   out = (in*up + pad0 + pad1 - k + down) / down      (upfirdn2d_kernel.cu:167-168).
+ * Any up/down >= 1 and kernel <= 32x32 is computed (tiled shared-memory path for the six reference modes,
+ * a generic path otherwise); nothing is ever left uninitialised. */
+PPST_API int ppst_upfirdn2d(void* y, const void* x, const float* kernel, int64_t major, int in_h, int in_w, int minor,
+                   int kh, int kw, int up_x, int up_y, int down_x, int down_y, int px0, int px1, int py0,
+                   int py1, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * segmented (per-sample, per-channel, optionally per-region) reductions
+ * Serves nn.InstanceNorm2d statistics (stylegan2_layers.py:421,527; generator.py:17,21),
+ * GAP / GMP (encoder_col.py:39-40,160-161), the masked GAP/GMP of the region branch
+ * (encoder_col.py:173-190,217-245) keyed by the integer label map (data/CelebAMask_dataset.py:54-60),
+ * and models/networks/function.py:3-35.
+ * ------------------------------------------------------------------------------------------- */
+
+/* x: activations, NCHW (channels_last = 0) or NHWC (channels_last = 1), n x c x hw.
+ * labels: NULL, or uint8 [n, hw]; n_regions >= 2 with labels, 1 without.
+ *   label_mode 0: the byte is the region index (membership: label == r)
+ *   label_mode 1: the byte is a membership bitmask (membership: (label >> r) & 1) -- what max-pooled
+ *                 one-hot masks become below full resolution (encoder_col.py:217, self.pool(mask))
+ * shift: NULL or f32 [n, c]: values are accumulated as (x - shift) (second pass of the exact variance).
+ * Outputs (f32, [n, n_regions, c]; any may be NULL):
+ *   sum   = sum over pixels of region r of (x - shift)
+ *   sumsq = sum over pixels of region r of (x - shift)^2
+ *   vmax  = max over ALL pixels of (x if pixel in region r else 0)   == amax(x * onehot_r)
+ *           (with n_regions == 1 and labels == NULL: plain max)
+ * scratch: f32 workspace of ppst_plane_reduce_scratch_elems(n, c, hw, n_regions) elements.
+ * Deterministic (no floating-point atomics). */
+PPST_API int64_t ppst_plane_reduce_scratch_elems(int64_t n, int64_t c, int64_t hw, int n_regions);
+PPST_API int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const void* x, const uint8_t* labels,
+                      const float* shift, float* scratch, int64_t n, int64_t c, int64_t hw, int n_regions,
+                      int label_mode, int channels_last, int dtype, void* stream);
+
+/* uint8 label map [n, hw] -> one-hot f32 [n, n_labels, hw]  (CelebAMaskDataset._mask_labels,
+ * data/CelebAMask_dataset.py:54-60; bit-exact membership test label == i). */
+PPST_API int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64_t n, int64_t hw, int n_labels, void* stream);
+
+/* Region membership bitmasks at reduced resolution: out[n, h/f, w/f] = OR over the f x f window of
+ * (in_mode 0: 1 << label, in_mode 1: the bitmask itself).  Equals MaxPool2d(f) of the one-hot mask
+ * (encoder_col.py:38,217).  f = 1 converts an index map into a bitmask map. */
+PPST_API int ppst_labels_pool_or(uint8_t* out, const uint8_t* in, int64_t n, int h, int w, int factor, int in_mode,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * layout
+ * ------------------------------------------------------------------------------------------- */
+/* NCHW (src_dtype) -> NHWC (dst_dtype), and back.  dst has channel stride dst_c >= c and the block is
+ * written at channel offset c_off (used to build concatenated feature maps, generator.py:272-278). */
+PPST_API int ppst_nchw_to_nhwc(void* dst, const void* src, int64_t n, int64_t c, int64_t hw, int64_t dst_c, int64_t c_off,
+                      int src_dtype, int dst_dtype, void* stream);
+PPST_API int ppst_nhwc_to_nchw(void* dst, const void* src, int64_t n, int64_t c, int64_t hw, int64_t src_c, int64_t c_off,
+                      int src_dtype, int dst_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * convolution (NHWC activations, weights packed [phase][cout][kh*kw*cin])
+ * Replaces the F.conv2d / F.conv_transpose2d calls of EqualConv2d (stylegan2_layers.py:188),
+ * EqualizedConv2d (:320,331,339-341), nn.Conv2d in generator.py:14-19,180-238, and the 1x1 heads.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  /* geometry */
+  int32_t n, in_h, in_w, cin;     /* input  [n, in_h, in_w, cin]  (already padded if the layer pre-pads) */
+  int32_t out_h, out_w, cout;     /* logical output grid of ONE phase */
+  int32_t kh, kw;                 /* taps of one phase */
+  int32_t stride;                 /* input stride (1 or 2) */
+  int32_t off_y, off_x;           /* input row/col of tap (0,0) for output (0,0); negative = zero padding */
+  /* output placement: out pixel (oy,ox) of phase p is stored at
+       (oy*out_sy + p_y, ox*out_sx + p_x) of a [n, full_h, full_w, cout_stride] tensor, channel offset c_off */
+  int32_t phases_y, phases_x;     /* 1,1 for a plain conv; 2,2 for the stride-2 transposed conv */
+  int32_t phase_off_dy, phase_off_dx; /* off_y/off_x increment per phase index (transposed conv: +1) */
+  int32_t full_h, full_w, cout_stride, c_off;
+  /* fused epilogue: v = acc + bias[co] + noise_w * noise[n, y, x];  v = v > 0 ? v : v*slope;  v *= gain */
+  int32_t has_act;                /* 0: linear (slope ignored, gain still applied) */
+  float slope, gain, noise_w;
+  int32_t in_dtype, out_dtype;    /* PPST_F32 / PPST_BF16 */
+  /* input addressing in ELEMENTS: pixel (y,x) of image i starts at i*in_img_pitch + y*in_row_pitch + x*cin.
+     0 = dense (in_w*cin, in_h*in_w*cin).  Lets a conv read the interior of a padded buffer. */
+  int64_t in_row_pitch, in_img_pitch;
+} ppst_conv_desc;
+
+/* CUDA-core implicit GEMM (fp32 accumulate; any channel counts).  fp32 mode and the thin layers
+ * (FromRGB 3->32, ToRGB 128->3).  weight: f32 [phases_y*phases_x][cout][kh*kw*cin]; bias f32[cout] or NULL;
+ * noise f32 [n, full_h, full_w] or NULL. */
+PPST_API int ppst_conv_simt(void* out, const void* in, const float* weight, const float* bias, const float* noise,
+                   const ppst_conv_desc* d, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit GEMM (bf16 in, fp32 accumulate in tensor memory, bf16 out).
+ * Requires cin % 64 == 0, cout % 16 == 0, stride == 1.  weight: bf16, same packing as above.
+ * stats (optional, f32 [n_tiles][2][cout_stride]... see ppst_conv_tc_stats_elems): per-tile partial sum / sum of
+ * squares of the stored (rounded) outputs, reduced later by ppst_in_coeffs -- the instance-norm statistics
+ * of LayerEpilogue (stylegan2_layers.py:414-437) come for free with the convolution. */
+PPST_API int64_t ppst_conv_tc_stats_elems(const ppst_conv_desc* d);
+PPST_API int ppst_conv_tc(void* out, const void* in, const void* weight, const float* bias, const float* noise,
+                 float* stats, const ppst_conv_desc* d, void* stream);
+/* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
+PPST_API int ppst_conv_tc_available(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * normalisation / modulation epilogues (NHWC)
+ * ------------------------------------------------------------------------------------------- */
+/* Per-(n,c) affine coefficients from reduced statistics:
+ *   mean = sum/count (+ shift), var = sumsq/count - (sum/count)^2  (biased, nn.InstanceNorm2d), rstd = rsqrt(var+eps)
+ *   a = rstd * (1 + style[n, c]) ; b = -mean * a + style[n, C + c] + bias[c]
+ * i.e. InstanceNorm followed by StyleMod `x * (s + 1) + b` (stylegan2_layers.py:361-374) and/or a
+ * per-channel bias (FusedLeakyReLU bias after IN in ConvLayer, :527-531).  style (f32 [n, 2c]) / bias /
+ * shift may be NULL.  If use_norm == 0: a = 1 + style, b = style_shift + bias.
+ * partials: if n_partials > 0, sum/sumsq are [n][n_partials][c] tile partials (from ppst_conv_tc) and are
+ * reduced here in a fixed order. */
+PPST_API int ppst_in_coeffs(float* a, float* b, const float* sum, const float* sumsq, const float* shift,
+                   const float* style, const float* bias, int64_t n, int64_t c, int64_t n_partials,
+                   double count, float eps, int use_norm, void* stream);
+
+typedef struct {
+  int32_t n, h, w, c;             /* logical input grid (x is [n, h, w, c]) */
+  int32_t up;                     /* 1, or 2 = nearest x2 (Upscale2d, stylegan2_layers.py:88-105) */
+  int32_t pad_t, pad_b, pad_l, pad_r;
+  int32_t pad_mode;               /* 0 zero, 1 reflect (nn.ReflectionPad2d), 2 replicate (nn.ReplicationPad2d) */
+  /* y = post( pre(x*a + b) * pre_gain + R ) * post_gain
+     pre/post(v) = v >= 0 ? v : v*slope  (slope = 1: identity)
+     R = 0 | res*ra + rb | bilinear_x2(res)*ra + rb  (F.interpolate(scale_factor=2, align_corners=False),
+     generator.py:75) */
+  float pre_slope, pre_gain, post_slope, post_gain;
+  int32_t res_mode;               /* 0 none, 1 same size, 2 bilinear x2 from [n, h/2, w/2, c] */
+  int32_t x_dtype, res_dtype, out_dtype;
+  int32_t out_c_stride, out_c_off; /* destination channel stride / offset (concat) */
+} ppst_apply_desc;
+
+/* out: [n, h*up + pad_t + pad_b, w*up + pad_l + pad_r, out_c_stride]; a,b,ra,rb: f32 [n, c] or NULL (1 / 0). */
+PPST_API int ppst_affine_apply(void* out, const void* x, const float* a, const float* b, const void* res,
+                      const float* ra, const float* rb, const ppst_apply_desc* d, void* stream);
+
+/* Resampling into a channel slice of an NHWC tensor.
+ * mode 0: bilinear, align_corners=False (F.interpolate, generator.py:274,277; encoder_col.py:130)
+ * mode 1: adaptive average pool with integer window (nn.AdaptiveAvgPool2d, generator.py:257,276;
+ *         F.adaptive_avg_pool2d encoder_col.py:119-122) -- requires in % out == 0 */
+PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
+                  int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * small dense layers and vector normalisation (f32)
+ * ------------------------------------------------------------------------------------------- */
+/* y[m, n] = act_in(x)[m, :] . w[n, :] * w_scale + b[n] * b_scale ; relu_in applies ReLU to x first
+ * (projector MLPs, encoder_col.py:50-86; EqualLinear / EqualizedLinear, stylegan2_layers.py:205-273).
+ * x: [m, k] row stride ldx; w: [n, k] f32; b NULL or [n]. */
+PPST_API int ppst_linear(float* y, const float* x, const float* w, const float* b, int64_t m, int64_t n, int64_t k,
+                int64_t ldx, float w_scale, float b_scale, int relu_in, void* stream);
+
+/* mode 0: y = v * rsqrt(sum v^2 + eps)        (util.normalize, util/util.py:18-22, eps = 1e-8)
+ * mode 1: y = v / max(||v||, eps)              (F.normalize, encoder_col.py:166, eps = 1e-12) */
+PPST_API int ppst_l2_normalize(float* y, const float* x, int64_t rows, int64_t cols, float eps, int mode, void* stream);
+
+/* y = a*(1-r) + b*r  (util.lerp, util/util.py:32-35) */
+PPST_API int ppst_lerp(float* y, const float* a, const float* b, float r, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * correlation swap (models/ppst_model.py:330-387)
+ * ------------------------------------------------------------------------------------------- */
+/* PPSTModel.Rselfcorr (:330-339): fea NHWC [n, 256, 256, 64] -> out NHWC slice [n, 64, 64, 256] written at
+ * channel offset c_off of a tensor with channel stride out_c_stride. */
+PPST_API int ppst_rselfcorr(void* out, const void* fea, int64_t n, int h, int w, int c, int out_c_stride, int c_off,
+                   int in_dtype, int out_dtype, void* stream);
+
+/* corrm preparation (:349-361): per pixel, centre the first `c_center` channels over the channel dim, then
+ * L2-normalise all c channels (+ DBL_EPSILON).  in: NHWC [rows, c]; out f32 [rows, c]. */
+PPST_API int ppst_corr_prepare(float* out, const void* in, int64_t rows, int c, int c_center, int in_dtype, void* stream);
+
+/* Batched f32 GEMM  C[b] = alpha * A[b] (m x k, row-major, lda) * B[b]  with B either k x n row-major
+ * (trans_b = 0) or n x k row-major (trans_b = 1); 3-term bf16 split on tcgen05 is a later round -- this is
+ * the exact-f32 CUDA-core path (corrm logits, :363; warp corr @ feat, encoder_col.py:124,133). */
+PPST_API int ppst_gemm_f32(float* c, const float* a, const float* b, int64_t batch, int64_t m, int64_t n, int64_t k,
+                  int64_t lda, int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t stride_c,
+                  int trans_b, float alpha, void* stream);
+
+/* in-place row softmax of (x / divisor), f32 [rows, cols]  (F.softmax(logits / 0.01, dim=-1), ppst_model.py:363) */
+PPST_API int ppst_softmax_rows(float* x, int64_t rows, int64_t cols, float divisor, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPST_B200_H_ */

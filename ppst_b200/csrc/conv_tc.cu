@@ -1,0 +1,581 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate, bf16 out).
+//
+// GEMM view (per phase): M = output pixels, N = cout, K = taps * cin.
+//   * M tile  = 128 output pixels = a TH x TW spatial patch of ONE image.  For tap (ky,kx) the A operand is that
+//     patch shifted by the tap offset: ONE 4-D TMA box {BKC channels, TW, TH, 1} over the NHWC tensor.  Out-of-bounds
+//     coordinates are zero-filled by the TMA unit, which IS the zero padding of the convolution; stride-2 convs use
+//     the tensor map's element strides.  No im2col buffer ever exists.
+//   * The box lands in shared memory as 128 rows (pixels) x BKC*2 bytes, 128B/64B-swizzled = the canonical K-major
+//     UMMA operand layout, so tcgen05.mma consumes it directly.  B = packed weights [phase*cout][taps*cin], K-major.
+//   * Accumulators live in tensor memory (2 stages x BN columns): the epilogue of tile i overlaps the MMAs of
+//     tile i+1.  Epilogue: tcgen05.ld -> + bias + noise -> leaky-ReLU * gain -> bf16 -> 16-byte global stores, plus
+//     per-channel partial sum / sum-of-squares of the stored values (instance-norm statistics for free).
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+//     warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).  Persistent grid: one CTA per SM, static tile striding.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ppst {
+
+int validate_conv_desc(const ppst_conv_desc& d, const char* who);
+
+namespace tc {
+
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;            // first epilogue warp
+constexpr int BM = 128;
+
+struct Params {
+  // geometry
+  int n, out_h, out_w, cout, cin;
+  int kh, kw, stride;
+  int off_y, off_x, phases_y, phases_x, phase_off_dy, phase_off_dx;
+  int full_h, full_w, cout_stride, c_off;
+  int th, tw, tiles_y, tiles_x;         // spatial tile and tile counts per image
+  int n_tiles_n;                        // cout / BN
+  int num_tiles;                        // total work items
+  int kblocks_per_tap;                  // cin / BKC
+  int has_act;
+  float slope, gain, noise_w;
+  int stats_partials;                   // partial slots per image = tiles_y*tiles_x*phases
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (sm_100 "version 1"): rows of BKC*2 bytes, 8-row swizzle atoms.
+template <int BKC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t layout = (BKC == 64) ? 2ull /*SWIZZLE_128B*/ : 4ull /*SWIZZLE_64B*/;
+  constexpr uint64_t sbo = (uint64_t)(8 * BKC * 2) >> 4;      // byte distance between 8-row groups
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                    // start address, 14 bits
+  d |= (uint64_t)1 << 16;                                     // leading byte offset (unused for swizzled K-major)
+  d |= sbo << 32;                                             // stride byte offset
+  d |= (uint64_t)1 << 46;                                     // descriptor version
+  d |= layout << 61;
+  return d;
+}
+
+template <int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+  // kind::f16: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// warp-level transposing reduction: on entry lane L holds v[c] for columns c = 0..31 of ITS row;
+// on exit v[0] of lane L = sum over the 32 lanes (rows) of column L.  31 shuffles.
+__device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int BKC, int STAGES>
+struct Smem {
+  static constexpr int kABytes = BM * BKC * 2;
+  static constexpr int kBBytes = BN * BKC * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStatsBytes = 2 /*buf*/ * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
+  static constexpr int kBarOffset = STAGES * kStageBytes + kStatsBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+template <int BN, int BKC, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ noise,
+               float* __restrict__ stats_sum, float* __restrict__ stats_sq, const Params p) {
+  using S = Smem<BN, BKC, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * S::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);              // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.kh * p.kw;
+  const int kblocks = taps * p.kblocks_per_tap;
+  const int n_phases = p.phases_y * p.phases_x;
+
+  // work item -> (n-tile, phase, spatial tile, image); n-tile fastest so that neighbouring CTAs share A in L2
+  auto decode = [&](int tile, int& nt, int& ph, int& tx, int& ty, int& img) {
+    nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+    ph = tile % n_phases; tile /= n_phases;
+    tx = tile % p.tiles_x; tile /= p.tiles_x;
+    ty = tile % p.tiles_y; img = tile / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nt, ph, tx, ty, img;
+        decode(tile, nt, ph, tx, ty, img);
+        const int py = ph / p.phases_x, px = ph % p.phases_x;
+        const int iy0 = ty * p.th * p.stride + p.off_y + py * p.phase_off_dy;
+        const int ix0 = tx * p.tw * p.stride + p.off_x + px * p.phase_off_dx;
+        const int brow = ph * p.cout + nt * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / p.kblocks_per_tap, cb = kb - tap * p.kblocks_per_tap;
+          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::kStageBytes;
+          uint8_t* sb = sa + S::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+          tma_load_4d(sa, &map_a, &full_bar[stage], cb * BKC, ix0 + kx, iy0 + ky, img);
+          tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.cin + cb * BKC, brow);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc<BN>();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);          // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
+          const uint64_t da = make_smem_desc<BKC>(sa);
+          const uint64_t db = make_smem_desc<BKC>(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < BKC / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte address field
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);                      // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                              // TMEM lane quadrant
+    const int row = q * 32 + lane;                       // row of the 128-pixel tile
+    const int ety = row / p.tw, etx = row - ety * p.tw;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int nt, ph, tx, ty, img;
+      decode(tile, nt, ph, tx, ty, img);
+      const int py = ph / p.phases_x, px = ph % p.phases_x;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int oy = ty * p.th + ety, ox = tx * p.tw + etx;
+      const bool valid = (oy < p.out_h) && (ox < p.out_w);
+      const int64_t pix = ((int64_t)img * p.full_h + (oy * p.phases_y + py)) * p.full_w + (ox * p.phases_x + px);
+      const float nz = (noise != nullptr && valid) ? p.noise_w * noise[pix] : 0.0f;
+      __nv_bfloat16* orow = out + pix * p.cout_stride + p.c_off + nt * BN;
+      float* st_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN + q * BN;
+      float* st_sq = s_stats + (size_t)(as * 2 + 1) * 4 * BN + q * BN;
+
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(r[j]) + (bias ? __ldg(bias + nt * BN + c0 + j) : 0.0f) + nz;
+          if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
+          v[j] = a * p.gain;
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (stats_sum != nullptr) {
+          // statistics of the values as stored (bf16-rounded), fp32 accumulate
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+            const float2 f = __bfloat1622float2(h);
+            s1[2 * j] = valid ? f.x : 0.0f;
+            s1[2 * j + 1] = valid ? f.y : 0.0f;
+            s2[2 * j] = s1[2 * j] * s1[2 * j];
+            s2[2 * j + 1] = s1[2 * j + 1] * s1[2 * j + 1];
+          }
+          const float cs = warp_col_reduce(s1, lane);
+          const float cq = warp_col_reduce(s2, lane);
+          st_sum[c0 + lane] = cs;
+          st_sq[c0 + lane] = cq;
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+
+      if (stats_sum != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps
+        const int e = threadIdx.x - kEpiWarp0 * 32;
+        const float* b_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN;
+        const float* b_sq = s_stats + (size_t)(as * 2 + 1) * 4 * BN;
+        const int slot = ((ty * p.tiles_x + tx) * n_phases + ph);
+        for (int c = e; c < BN; c += 128) {
+          const float s = (b_sum[c] + b_sum[BN + c]) + (b_sum[2 * BN + c] + b_sum[3 * BN + c]);
+          const float qv = (b_sq[c] + b_sq[BN + c]) + (b_sq[2 * BN + c] + b_sq[3 * BN + c]);
+          const int64_t o = ((int64_t)img * p.stats_partials + slot) * p.cout + nt * BN + c;
+          stats_sum[o] = s;
+          stats_sq[o] = qv;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  uint64_t v[12];
+  bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+static int encode_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box, const uint32_t* estr, int bkc) {
+  MapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.v[0] = (uint64_t)base;
+  key.v[1] = (uint64_t)rank | ((uint64_t)bkc << 8);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[6 + i] = ((uint64_t)box[i] << 32) | estr[i];
+  }
+  key.v[10] = strides_b[0];
+  key.v[11] = rank > 2 ? (strides_b[1] ^ (strides_b[2] << 1)) : 0;
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return 0; }
+  }
+  EncodeTiledFn enc = get_encode();
+  PPST_REQUIRE(enc != nullptr, PPST_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t gbox[4], gest[4];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; gbox[i] = box[i]; gest[i] = estr[i]; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_b[i];
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                         gbox, gest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PPST_REQUIRE(r == CUDA_SUCCESS, PPST_ERR_CUDA, "conv_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[key] = *out;
+  return 0;
+}
+
+static void pick_tile(int out_h, int out_w, int& th, int& tw) {
+  // 128 pixels; prefer a squarish patch (halo reuse in L2), shrink TW for narrow outputs
+  tw = 16;
+  while (tw > out_w && tw > 1) tw >>= 1;
+  if (out_w >= 128 && out_h < 8) tw = 128;
+  th = BM / tw;
+}
+
+static int g_num_sms = 0;
+
+template <int BN, int BKC, int STAGES>
+static int launch(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
+                  const float* noise, float* stats, cudaStream_t st) {
+  using S = Smem<BN, BKC, STAGES>;
+  Params p;
+  p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
+  p.kh = d.kh; p.kw = d.kw; p.stride = d.stride;
+  p.off_y = d.off_y; p.off_x = d.off_x; p.phases_y = d.phases_y; p.phases_x = d.phases_x;
+  p.phase_off_dy = d.phase_off_dy; p.phase_off_dx = d.phase_off_dx;
+  p.full_h = d.full_h; p.full_w = d.full_w; p.cout_stride = d.cout_stride; p.c_off = d.c_off;
+  pick_tile(d.out_h, d.out_w, p.th, p.tw);
+  p.tiles_y = ceil_div(d.out_h, p.th); p.tiles_x = ceil_div(d.out_w, p.tw);
+  p.n_tiles_n = d.cout / BN;
+  const int n_phases = d.phases_y * d.phases_x;
+  const int64_t tiles = (int64_t)d.n * p.tiles_y * p.tiles_x * n_phases * p.n_tiles_n;
+  PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_tc: too many tiles");
+  p.num_tiles = (int)tiles;
+  p.kblocks_per_tap = d.cin / BKC;
+  p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
+  p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
+
+  CUtensorMap map_a, map_b;
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)d.n};
+    const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
+    const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
+    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)(p.tw * d.stride), (uint32_t)(p.th * d.stride), 1};
+    const uint32_t est[4] = {1, (uint32_t)d.stride, (uint32_t)d.stride, 1};
+    int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
+    const uint64_t dims[2] = {K, (uint64_t)d.cout * n_phases};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)BN};
+    const uint32_t est[2] = {1, 1};
+    int rc = encode_map(&map_b, weight, 2, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  auto kern = conv_tc_kernel<BN, BKC, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+                        "cudaFuncSetAttribute(conv_tc)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  float* ssum = stats;
+  float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
+  kern<<<grid, kThreads, S::kTotal, st>>>(map_a, map_b, (__nv_bfloat16*)out, bias, noise, ssum, ssq, p);
+  PPST_LAUNCH_CHECK("conv_tc_kernel");
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace ppst
+
+extern "C" int ppst_conv_tc_available(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return (major == 10 && ppst::tc::get_encode() != nullptr) ? 1 : 0;
+}
+
+extern "C" int64_t ppst_conv_tc_stats_elems(const ppst_conv_desc* d) {
+  if (!d) return 0;
+  int th, tw;
+  ppst::tc::pick_tile(d->out_h, d->out_w, th, tw);
+  const int64_t partials = (int64_t)ppst::ceil_div(d->out_h, th) * ppst::ceil_div(d->out_w, tw) * d->phases_y * d->phases_x;
+  return 2 * (int64_t)d->n * partials * d->cout;
+}
+
+extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const float* bias, const float* noise,
+                            float* stats, const ppst_conv_desc* dp, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && in && weight && dp, PPST_ERR_ARG, "conv_tc: null argument");
+  const ppst_conv_desc d = *dp;
+  int rc = validate_conv_desc(d, "conv_tc");
+  if (rc) return rc;
+  PPST_REQUIRE(d.in_dtype == PPST_BF16 && d.out_dtype == PPST_BF16, PPST_ERR_DTYPE, "conv_tc: bf16 in / bf16 out only");
+  PPST_REQUIRE(d.cin % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cin=%d must be a multiple of 32", d.cin);
+  PPST_REQUIRE(d.cout % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cout=%d must be a multiple of 32", d.cout);
+  PPST_REQUIRE(d.stride == 1 || d.stride == 2, PPST_ERR_UNSUPPORTED, "conv_tc: stride %d", d.stride);
+  PPST_REQUIRE(d.in_row_pitch % 8 == 0 && d.in_img_pitch % 8 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: input pitches must be 16-byte multiples");
+  PPST_REQUIRE(d.cout_stride % 8 == 0 && d.c_off % 8 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: output channel slice must be 16-byte aligned");
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               PPST_ERR_ARG, "conv_tc: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool k64 = (d.cin % 64 == 0);
+#define PPST_TC(BN_, BKC_, ST_) return tc::launch<BN_, BKC_, ST_>(d, out, in, weight, bias, noise, stats, st)
+  if (k64) {
+    if (d.cout % 256 == 0) PPST_TC(256, 64, 4);
+    if (d.cout % 128 == 0) PPST_TC(128, 64, 6);
+    if (d.cout % 64 == 0) PPST_TC(64, 64, 8);
+    PPST_TC(32, 64, 8);
+  } else {
+    if (d.cout % 64 == 0) PPST_TC(64, 32, 8);
+    PPST_TC(32, 32, 8);
+  }
+#undef PPST_TC
+}

@@ -1,0 +1,322 @@
+// Normalisation / modulation epilogues on NHWC activations.
+//
+//  ppst_in_coeffs    : reduced statistics (+ style vector, + bias) -> per-(n,c) scale/shift, so that
+//                      InstanceNorm -> StyleMod (stylegan2_layers.py:414-437,361-374) or InstanceNorm ->
+//                      FusedLeakyReLU bias (:527-531) collapse into ONE affine per element.
+//  ppst_affine_apply : y = post(pre(x*a+b)*g1 + R)*g2, optionally nearest-x2 upsampled, written into a padded
+//                      (zero / reflect / replicate) destination, R optionally a bilinear-x2 upsampled skip.
+//                      One read of x (+ one of R) and one write per element: the 6-7 full-tensor passes the
+//                      reference spends per StyledConv become one.
+//  ppst_resample     : bilinear (align_corners=False) / adaptive-average resampling into a channel slice.
+#include "common.cuh"
+
+namespace ppst {
+
+__global__ void in_coeffs_kernel(float* __restrict__ a, float* __restrict__ b, const float* __restrict__ sum,
+                                 const float* __restrict__ sumsq, const float* __restrict__ shift,
+                                 const float* __restrict__ style, const float* __restrict__ bias, int64_t n, int64_t c,
+                                 int64_t n_partials, double count, float eps, int use_norm) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  const int64_t ni = t / c, ch = t % c;
+  double scale = 1.0, off = 0.0;
+  if (use_norm) {
+    double s = 0.0, q = 0.0;
+    if (n_partials > 0) {
+      for (int64_t p = 0; p < n_partials; ++p) {          // fixed order -> deterministic
+        s += (double)sum[(ni * n_partials + p) * c + ch];
+        q += (double)sumsq[(ni * n_partials + p) * c + ch];
+      }
+    } else {
+      s = sum[t];
+      q = sumsq[t];
+    }
+    const double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const double mean = m + (shift ? (double)shift[t] : 0.0);
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    scale = rstd;
+    off = -mean * rstd;
+  }
+  if (style) {
+    const double s1 = 1.0 + (double)style[ni * 2 * c + ch];
+    scale *= s1;
+    off = off * s1 + (double)style[ni * 2 * c + c + ch];
+  }
+  if (bias) off += (double)bias[ch];
+  a[t] = (float)scale;
+  b[t] = (float)off;
+}
+
+__device__ __forceinline__ float lrelu_slope(float v, float slope) { return v >= 0.0f ? v : v * slope; }
+
+__device__ __forceinline__ int map_pad(int u, int size, int mode, bool& zero) {
+  if (u >= 0 && u < size) return u;
+  if (mode == 0) { zero = true; return 0; }
+  if (mode == 1) {                       // reflect (no edge repeat): -1 -> 1, size -> size-2
+    if (u < 0) u = -u;
+    if (u >= size) u = 2 * (size - 1) - u;
+    return min(max(u, 0), size - 1);
+  }
+  return min(max(u, 0), size - 1);       // replicate
+}
+
+struct Bilin2 {
+  int i0, i1;
+  float l0, l1;
+};
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False): src = max(0, 0.5*(dst+0.5)-0.5)
+__device__ __forceinline__ Bilin2 bilin_x2(int dst, int in_size) {
+  float src = 0.5f * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.0f) src = 0.0f;
+  Bilin2 r;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + ((r.i0 < in_size - 1) ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.0f - r.l1;
+  return r;
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void load_ch(float (&v)[V], const T* p) {
+  if (V == 1) {
+    v[0] = Cvt<T>::to_f(p[0]);
+  } else if (sizeof(T) == 4) {
+#pragma unroll
+    for (int h = 0; h < V / 4; ++h) {
+      const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + 4 * h);
+      v[4 * h + 0] = f.x; v[4 * h + 1] = f.y; v[4 * h + 2] = f.z; v[4 * h + 3] = f.w;
+    }
+  } else {
+    Vec16<T> r = ld_vec16(p);
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = Cvt<T>::to_f(r.v[e]);
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void store_ch(T* p, const float (&v)[V]) {
+  if (V == 1) {
+    p[0] = Cvt<T>::from_f(v[0]);
+  } else if (sizeof(T) == 4) {
+#pragma unroll
+    for (int h = 0; h < V / 4; ++h)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + 4 * h) =
+          make_float4(v[4 * h + 0], v[4 * h + 1], v[4 * h + 2], v[4 * h + 3]);
+  } else {
+    Vec16<T> r;
+#pragma unroll
+    for (int e = 0; e < V; ++e) r.v[e] = Cvt<T>::from_f(v[e]);
+    st_vec16(p, r);
+  }
+}
+
+// V = channels per thread (8 when c % 8 == 0, else 1)
+template <typename TX, typename TO, int V>
+__global__ void __launch_bounds__(256) affine_apply_kernel(TO* __restrict__ out, const TX* __restrict__ x,
+                                                           const float* __restrict__ a, const float* __restrict__ b,
+                                                           const TX* __restrict__ res, const float* __restrict__ ra,
+                                                           const float* __restrict__ rb, ppst_apply_desc d) {
+  const int cv = d.c / V;
+  const int hu = d.h * d.up, wu = d.w * d.up;
+  const int oh = hu + d.pad_t + d.pad_b, ow = wu + d.pad_l + d.pad_r;
+  const int64_t total = (int64_t)d.n * oh * ow * cv;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cv);
+    int64_t r = t / cv;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh);
+    const int ni = (int)(r / oh);
+    const int ch = cg * V;
+    bool zero = false;
+    const int uy = map_pad(oy - d.pad_t, hu, d.pad_mode, zero);
+    const int ux = map_pad(ox - d.pad_l, wu, d.pad_mode, zero);
+    float y[V];
+    if (zero) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = 0.0f;
+    } else {
+      const int iy = uy / d.up, ix = ux / d.up;
+      float xv[V];
+      load_ch<TX, V>(xv, x + (((int64_t)ni * d.h + iy) * d.w + ix) * d.c + ch);
+      float av[V], bv[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        av[e] = a ? a[(int64_t)ni * d.c + ch + e] : 1.0f;
+        bv[e] = b ? b[(int64_t)ni * d.c + ch + e] : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
+      if (d.res_mode != 0) {
+        float rv[V];
+        if (d.res_mode == 1) {
+          load_ch<TX, V>(rv, res + (((int64_t)ni * hu + uy) * wu + ux) * d.c + ch);
+        } else {
+          const int lh = hu / 2, lw = wu / 2;
+          const Bilin2 by = bilin_x2(uy, lh), bx = bilin_x2(ux, lw);
+          float v00[V], v01[V], v10[V], v11[V];
+          const TX* rp = res + (int64_t)ni * lh * lw * d.c + ch;
+          load_ch<TX, V>(v00, rp + ((int64_t)by.i0 * lw + bx.i0) * d.c);
+          load_ch<TX, V>(v01, rp + ((int64_t)by.i0 * lw + bx.i1) * d.c);
+          load_ch<TX, V>(v10, rp + ((int64_t)by.i1 * lw + bx.i0) * d.c);
+          load_ch<TX, V>(v11, rp + ((int64_t)by.i1 * lw + bx.i1) * d.c);
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            rv[e] = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float rav = ra ? ra[(int64_t)ni * d.c + ch + e] : 1.0f;
+          const float rbv = rb ? rb[(int64_t)ni * d.c + ch + e] : 0.0f;
+          y[e] += fmaf(rv[e], rav, rbv);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
+    }
+    store_ch<TO, V>(out + (((int64_t)ni * oh + oy) * ow + ox) * d.out_c_stride + d.out_c_off + ch, y);
+  }
+}
+
+// mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows)
+template <typename TX, typename TO, int V>
+__global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, const TX* __restrict__ x, int64_t n,
+                                                       int in_h, int in_w, int out_h, int out_w, int c,
+                                                       int out_c_stride, int out_c_off, int mode) {
+  const int cv = c / V;
+  const int64_t total = n * out_h * out_w * cv;
+  const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cv);
+    int64_t r = t / cv;
+    const int ox = (int)(r % out_w); r /= out_w;
+    const int oy = (int)(r % out_h);
+    const int64_t ni = r / out_h;
+    const int ch = cg * V;
+    const TX* base = x + ni * in_h * in_w * (int64_t)c + ch;
+    float y[V];
+    if (mode == 0) {
+      float sy = sh * ((float)oy + 0.5f) - 0.5f, sx = sw * ((float)ox + 0.5f) - 0.5f;
+      if (sy < 0.f) sy = 0.f;
+      if (sx < 0.f) sx = 0.f;
+      const int y0 = min((int)sy, in_h - 1), x0 = min((int)sx, in_w - 1);
+      const int y1 = y0 + ((y0 < in_h - 1) ? 1 : 0), x1 = x0 + ((x0 < in_w - 1) ? 1 : 0);
+      const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      float v00[V], v01[V], v10[V], v11[V];
+      load_ch<TX, V>(v00, base + ((int64_t)y0 * in_w + x0) * c);
+      load_ch<TX, V>(v01, base + ((int64_t)y0 * in_w + x1) * c);
+      load_ch<TX, V>(v10, base + ((int64_t)y1 * in_w + x0) * c);
+      load_ch<TX, V>(v11, base + ((int64_t)y1 * in_w + x1) * c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
+    } else {
+      const int fh = in_h / out_h, fw = in_w / out_w;
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = 0.f;
+      for (int dy = 0; dy < fh; ++dy)
+        for (int dx = 0; dx < fw; ++dx) {
+          float v[V];
+          load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_w + (ox * fw + dx)) * c);
+#pragma unroll
+          for (int e = 0; e < V; ++e) y[e] += v[e];
+        }
+      const float inv = 1.0f / (float)(fh * fw);
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] *= inv;
+    }
+    store_ch<TO, V>(out + ((ni * out_h + oy) * out_w + ox) * (int64_t)out_c_stride + out_c_off + ch, y);
+  }
+}
+
+static int grid_for(int64_t total) {
+  const int64_t b = (total + 255) / 256;
+  const int64_t cap = 148LL * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace ppst
+
+extern "C" int ppst_in_coeffs(float* a, float* b, const float* sum, const float* sumsq, const float* shift,
+                              const float* style, const float* bias, int64_t n, int64_t c, int64_t n_partials,
+                              double count, float eps, int use_norm, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(a && b && n > 0 && c > 0, PPST_ERR_ARG, "in_coeffs: bad args");
+  PPST_REQUIRE(!use_norm || (sum && sumsq && count > 0), PPST_ERR_ARG, "in_coeffs: statistics missing");
+  in_coeffs_kernel<<<ceil_div(n * c, 256), 256, 0, (cudaStream_t)stream>>>(a, b, sum, sumsq, shift, style, bias, n, c,
+                                                                          n_partials, count, eps, use_norm);
+  PPST_LAUNCH_CHECK("in_coeffs_kernel");
+  return 0;
+}
+
+extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const float* b, const void* res,
+                                 const float* ra, const float* rb, const ppst_apply_desc* dp, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && dp, PPST_ERR_ARG, "affine_apply: null argument");
+  const ppst_apply_desc d = *dp;
+  PPST_REQUIRE(d.n > 0 && d.h > 0 && d.w > 0 && d.c > 0 && (d.up == 1 || d.up == 2), PPST_ERR_ARG,
+               "affine_apply: bad geometry");
+  PPST_REQUIRE(d.res_mode == 0 || res != nullptr, PPST_ERR_ARG, "affine_apply: residual missing");
+  PPST_REQUIRE(d.res_mode != 2 || ((d.h * d.up) % 2 == 0 && (d.w * d.up) % 2 == 0), PPST_ERR_ARG,
+               "affine_apply: bilinear-x2 residual needs even output size");
+  PPST_REQUIRE(d.pad_mode >= 0 && d.pad_mode <= 2, PPST_ERR_ARG, "affine_apply: pad_mode");
+  PPST_REQUIRE(d.pad_mode != 1 || (d.pad_t < d.h * d.up && d.pad_b < d.h * d.up && d.pad_l < d.w * d.up &&
+                                   d.pad_r < d.w * d.up), PPST_ERR_ARG, "affine_apply: reflect pad >= size");
+  PPST_REQUIRE(d.res_mode == 0 || d.res_dtype == d.x_dtype, PPST_ERR_UNSUPPORTED,
+               "affine_apply: residual dtype must equal x dtype");
+  PPST_REQUIRE(d.out_c_off >= 0 && d.out_c_off + d.c <= d.out_c_stride, PPST_ERR_ARG, "affine_apply: channel slice");
+  const bool vec = (d.c % 8 == 0) && (d.out_c_stride % 8 == 0) && (d.out_c_off % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(res)) & 15) == 0;
+  const int64_t total = (int64_t)d.n * (d.h * d.up + d.pad_t + d.pad_b) * (d.w * d.up + d.pad_l + d.pad_r) *
+                        (vec ? d.c / 8 : d.c);
+  const int grid = grid_for(total);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PPST_APPLY(TX, TO)                                                                                           \
+  do {                                                                                                               \
+    if (vec)                                                                                                         \
+      affine_apply_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d); \
+    else                                                                                                             \
+      affine_apply_kernel<TX, TO, 1><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d); \
+  } while (0)
+  if (d.x_dtype == PPST_F32 && d.out_dtype == PPST_F32) PPST_APPLY(float, float);
+  else if (d.x_dtype == PPST_BF16 && d.out_dtype == PPST_BF16) PPST_APPLY(__nv_bfloat16, __nv_bfloat16);
+  else if (d.x_dtype == PPST_BF16 && d.out_dtype == PPST_F32) PPST_APPLY(__nv_bfloat16, float);
+  else if (d.x_dtype == PPST_F32 && d.out_dtype == PPST_BF16) PPST_APPLY(float, __nv_bfloat16);
+  else PPST_REQUIRE(false, PPST_ERR_DTYPE, "affine_apply: dtype combination %d -> %d", d.x_dtype, d.out_dtype);
+#undef PPST_APPLY
+  PPST_LAUNCH_CHECK("affine_apply_kernel");
+  return 0;
+}
+
+extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
+                             int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && c > 0, PPST_ERR_ARG,
+               "resample: bad args");
+  PPST_REQUIRE(mode == 0 || (mode == 1 && in_h % out_h == 0 && in_w % out_w == 0), PPST_ERR_UNSUPPORTED,
+               "resample: adaptive average needs integer windows (%dx%d -> %dx%d)", in_h, in_w, out_h, out_w);
+  PPST_REQUIRE(out_c_off >= 0 && out_c_off + c <= out_c_stride, PPST_ERR_ARG, "resample: channel slice");
+  const bool vec = (c % 8 == 0) && (out_c_stride % 8 == 0) && (out_c_off % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int64_t total = n * out_h * out_w * (vec ? c / 8 : c);
+  const int grid = grid_for(total);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PPST_RS(TX, TO)                                                                                        \
+  do {                                                                                                         \
+    if (vec)                                                                                                   \
+      resample_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
+                                                       out_c_stride, out_c_off, mode);                         \
+    else                                                                                                       \
+      resample_kernel<TX, TO, 1><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
+                                                       out_c_stride, out_c_off, mode);                         \
+  } while (0)
+  if (in_dtype == PPST_F32 && out_dtype == PPST_F32) PPST_RS(float, float);
+  else if (in_dtype == PPST_BF16 && out_dtype == PPST_BF16) PPST_RS(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == PPST_BF16 && out_dtype == PPST_F32) PPST_RS(__nv_bfloat16, float);
+  else if (in_dtype == PPST_F32 && out_dtype == PPST_BF16) PPST_RS(float, __nv_bfloat16);
+  else PPST_REQUIRE(false, PPST_ERR_DTYPE, "resample: dtype combination %d -> %d", in_dtype, out_dtype);
+#undef PPST_RS
+  PPST_LAUNCH_CHECK("resample_kernel");
+  return 0;
+}

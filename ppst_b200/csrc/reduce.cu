@@ -1,0 +1,337 @@
+// Segmented reductions: per-(sample, region, channel) sum / sum of squares / max over H*W.
+// One kernel family serves InstanceNorm statistics, GAP / GMP, the region-masked GAP / GMP of the colour
+// encoder keyed by the integer label map, and function.py's mean/std helpers.
+//
+// HBM-bound: every activation element is read exactly once with 128-bit loads; partial results go to a small
+// scratch buffer and are combined by a second tiny kernel in a fixed order (deterministic; no fp atomics).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace ppst {
+
+constexpr int kMaxRegions = 4;
+constexpr int kReduceThreads = 256;
+
+struct ReducePlan {
+  int chunks;        // partial blocks per sample (NHWC) or per plane (NCHW)
+  int64_t chunk_len; // pixels per chunk
+};
+
+static ReducePlan plan_reduce(int64_t n, int64_t c, int64_t hw, int channels_last) {
+  // aim for >= 4 blocks per SM, but never chunks shorter than 1024 pixels
+  const int64_t units = channels_last ? n : n * c;
+  int64_t chunks = (148LL * 4 + units - 1) / units;
+  const int64_t max_chunks = (hw + 255) / 256;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 1024) chunks = 1024;
+  ReducePlan p;
+  p.chunk_len = (hw + chunks - 1) / chunks;
+  p.chunk_len = (p.chunk_len + 63) / 64 * 64;          // keep chunk starts 16-byte aligned for all dtypes
+  p.chunks = (int)((hw + p.chunk_len - 1) / p.chunk_len);
+  return p;
+}
+
+// scratch layout: [unit][chunk][region][c_or_1][3]   (3 = sum, sumsq, max)
+
+// ------------------------------------------------------------------------------------------------
+// NCHW: grid = (planes, chunks).  Threads stride over the pixels of one plane chunk.
+template <typename T, int R>
+__global__ void __launch_bounds__(kReduceThreads) plane_reduce_nchw_kernel(
+    float* __restrict__ scratch, const T* __restrict__ x, const uint8_t* __restrict__ labels,
+    const float* __restrict__ shift, int64_t c, int64_t hw, int64_t chunk_len, int chunks, int label_mode) {
+  constexpr int VEC = Vec16<T>::N;
+  const int64_t plane = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int64_t nidx = plane / c;
+  const float sh = shift ? shift[plane] : 0.0f;
+  const T* px = x + plane * hw;
+  const uint8_t* pl = labels ? labels + nidx * hw : nullptr;
+  const int64_t beg = (int64_t)chunk * chunk_len;
+  const int64_t end = min(beg + chunk_len, hw);
+  float s[R], q[R], m[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { s[r] = 0.f; q[r] = 0.f; m[r] = -FLT_MAX; }
+  auto accum = [&](float xv, int L) {
+    if (R == 1) {
+      const float d = xv - sh;
+      s[0] += d; q[0] = fmaf(d, d, q[0]); m[0] = fmaxf(m[0], xv);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool in = label_mode ? (((L >> r) & 1) != 0) : (L == r);
+        const float d = in ? xv - sh : 0.0f;
+        s[r] += d; q[r] = fmaf(d, d, q[r]); m[r] = fmaxf(m[r], in ? xv : 0.0f);
+      }
+    }
+  };
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(px + beg) & 15) == 0);
+  int64_t scalar_from = beg;                           // first element left to the scalar loop
+  if (vec_ok) {
+    const int64_t end_vec = beg + (end - beg) / VEC * VEC;
+    for (int64_t i = beg + (int64_t)threadIdx.x * VEC; i < end_vec; i += (int64_t)kReduceThreads * VEC) {
+      Vec16<T> v = ld_vec16_stream(px + i);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) accum(Cvt<T>::to_f(v.v[e]), (R > 1) ? pl[i + e] : 0);
+    }
+    scalar_from = end_vec;
+  }
+  for (int64_t j = scalar_from + threadIdx.x; j < end; j += kReduceThreads)
+    accum(Cvt<T>::to_f(px[j]), (R > 1) ? pl[j] : 0);
+  __shared__ float red[kReduceThreads / 32][R][3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float a = warp_sum(s[r]), b = warp_sum(q[r]), mm = warp_max(m[r]);
+    if (lane == 0) { red[wid][r][0] = a; red[wid][r][1] = b; red[wid][r][2] = mm; }
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    const int r = threadIdx.x;
+    float a = 0.f, b = 0.f, mm = -FLT_MAX;
+    for (int w = 0; w < kReduceThreads / 32; ++w) { a += red[w][r][0]; b += red[w][r][1]; mm = fmaxf(mm, red[w][r][2]); }
+    float* o = scratch + (((int64_t)plane * chunks + chunk) * R + r) * 3;
+    o[0] = a; o[1] = b; o[2] = mm;
+  }
+}
+
+template <int R>
+__global__ void plane_reduce_nchw_final(float* __restrict__ sum, float* __restrict__ sumsq, float* __restrict__ vmax,
+                                        const float* __restrict__ scratch, int64_t n, int64_t c, int chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n*c*R
+  if (t >= n * c * R) return;
+  const int r = (int)(t % R);
+  const int64_t plane = t / R;
+  float a = 0.f, b = 0.f, mm = -FLT_MAX;
+  for (int k = 0; k < chunks; ++k) {
+    const float* o = scratch + ((plane * chunks + k) * R + r) * 3;
+    a += o[0]; b += o[1]; mm = fmaxf(mm, o[2]);
+  }
+  const int64_t nidx = plane / c, ch = plane % c;
+  const int64_t oi = (nidx * R + r) * c + ch;
+  if (sum) sum[oi] = a;
+  if (sumsq) sumsq[oi] = b;
+  if (vmax) vmax[oi] = mm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NHWC: grid = (n, chunks, channel groups).  A block is TCOLS channel-vector columns x (256/TCOLS) pixel lanes.
+template <typename T, int VEC, int R>
+__global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
+    float* __restrict__ scratch, const T* __restrict__ x, const uint8_t* __restrict__ labels,
+    const float* __restrict__ shift, int64_t c, int64_t hw, int64_t chunk_len, int chunks, int tcols,
+    int label_mode) {
+  extern __shared__ float red[];                       // [plane_lanes][tcols*VEC][R][3] -> reduced in place
+  const int64_t nidx = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int col = threadIdx.x % tcols;                 // channel-vector column within the group
+  const int lane_p = threadIdx.x / tcols;              // pixel lane
+  const int planes = kReduceThreads / tcols;
+  const int64_t ch0 = ((int64_t)blockIdx.z * tcols + col) * VEC;
+  const bool active = ch0 < c;
+  const int64_t beg = (int64_t)chunk * chunk_len;
+  const int64_t end = min(beg + chunk_len, hw);
+  float s[R][VEC], q[R][VEC], m[R][VEC], sh[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    sh[e] = (shift && active) ? shift[nidx * c + ch0 + e] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { s[r][e] = 0.f; q[r][e] = 0.f; m[r][e] = -FLT_MAX; }
+  }
+  if (active) {
+    const T* base = x + (nidx * hw) * c + ch0;
+    const uint8_t* pl = labels ? labels + nidx * hw : nullptr;
+    for (int64_t p = beg + lane_p; p < end; p += planes) {
+      float xv[VEC];
+      if (VEC > 1) {
+        Vec16<T> v = ld_vec16_stream(base + p * c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) xv[e] = Cvt<T>::to_f(v.v[e]);
+      } else {
+        xv[0] = Cvt<T>::to_f(base[p * c]);
+      }
+      const int L = (R > 1) ? pl[p] : 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool in = (R == 1) || (label_mode ? (((L >> r) & 1) != 0) : (L == r));
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float d = in ? xv[e] - sh[e] : 0.0f;
+          s[r][e] += d; q[r][e] = fmaf(d, d, q[r][e]); m[r][e] = fmaxf(m[r][e], in ? xv[e] : 0.0f);
+        }
+      }
+    }
+  }
+  // cross-pixel-lane reduction through shared memory, fixed order
+  const int width = tcols * VEC * R * 3;
+  float* mine = red + (int64_t)lane_p * width + (int64_t)col * VEC * R * 3;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mine[(e * R + r) * 3 + 0] = s[r][e];
+      mine[(e * R + r) * 3 + 1] = q[r][e];
+      mine[(e * R + r) * 3 + 2] = m[r][e];
+    }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < width; idx += kReduceThreads) {
+    const int kind = idx % 3;
+    float acc = (kind == 2) ? -FLT_MAX : 0.0f;
+    for (int l = 0; l < planes; ++l) {
+      const float v = red[(int64_t)l * width + idx];
+      acc = (kind == 2) ? fmaxf(acc, v) : acc + v;
+    }
+    // idx -> (col, e, r, kind)
+    const int r = (idx / 3) % R;
+    const int ce = idx / (3 * R);                       // col*VEC + e
+    const int64_t ch = (int64_t)blockIdx.z * tcols * VEC + ce;
+    if (ch < c) scratch[((((int64_t)nidx * chunks + chunk) * R + r) * c + ch) * 3 + kind] = acc;
+  }
+}
+
+template <int R>
+__global__ void plane_reduce_nhwc_final(float* __restrict__ sum, float* __restrict__ sumsq, float* __restrict__ vmax,
+                                        const float* __restrict__ scratch, int64_t n, int64_t c, int chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n*R*c
+  if (t >= n * R * c) return;
+  const int64_t ch = t % c;
+  const int r = (int)((t / c) % R);
+  const int64_t nidx = t / (c * R);
+  float a = 0.f, b = 0.f, mm = -FLT_MAX;
+  for (int k = 0; k < chunks; ++k) {
+    const float* o = scratch + ((((int64_t)nidx * chunks + k) * R + r) * c + ch) * 3;
+    a += o[0]; b += o[1]; mm = fmaxf(mm, o[2]);
+  }
+  if (sum) sum[t] = a;
+  if (sumsq) sumsq[t] = b;
+  if (vmax) vmax[t] = mm;
+}
+
+template <typename T, int R>
+static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, const uint8_t* labels, const float* shift,
+                         float* scratch, int64_t n, int64_t c, int64_t hw, int label_mode, int channels_last, cudaStream_t st) {
+  const ReducePlan pl = plan_reduce(n, c, hw, channels_last);
+  if (!channels_last) {
+    dim3 grid((unsigned)(n * c), pl.chunks);
+    plane_reduce_nchw_kernel<T, R><<<grid, kReduceThreads, 0, st>>>(scratch, x, labels, shift, c, hw, pl.chunk_len,
+                                                                    pl.chunks, label_mode);
+    PPST_LAUNCH_CHECK("plane_reduce_nchw_kernel");
+    const int64_t tot = n * c * R;
+    plane_reduce_nchw_final<R><<<ceil_div(tot, 256), 256, 0, st>>>(sum, sumsq, vmax, scratch, n, c, pl.chunks);
+    PPST_LAUNCH_CHECK("plane_reduce_nchw_final");
+    return 0;
+  }
+  constexpr int VECF = Vec16<T>::N;
+  const bool vec = (c % VECF == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int64_t cols = vec ? c / VECF : c;
+  int tcols = 1;
+  while (tcols < cols && tcols < kReduceThreads) tcols <<= 1;
+  // shared memory: planes * tcols * VEC * R * 3 floats = 256 * VEC * R * 3 floats (<= 256*8*4*3*4 = 96 KB)
+  const int vecn = vec ? VECF : 1;
+  const size_t smem = sizeof(float) * (size_t)kReduceThreads * vecn * R * 3;
+  dim3 grid((unsigned)n, pl.chunks, ceil_div(cols, tcols));
+  if (vec) {
+    auto kern = plane_reduce_nhwc_kernel<T, VECF, R>;
+    if (smem > 48 * 1024) {
+      int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(plane_reduce)");
+      if (rc) return rc;
+    }
+    kern<<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw, pl.chunk_len, pl.chunks, tcols,
+                                             label_mode);
+  } else {
+    plane_reduce_nhwc_kernel<T, 1, R><<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw,
+                                                                          pl.chunk_len, pl.chunks, tcols, label_mode);
+  }
+  PPST_LAUNCH_CHECK("plane_reduce_nhwc_kernel");
+  const int64_t tot = n * c * R;
+  plane_reduce_nhwc_final<R><<<ceil_div(tot, 256), 256, 0, st>>>(sum, sumsq, vmax, scratch, n, c, pl.chunks);
+  PPST_LAUNCH_CHECK("plane_reduce_nhwc_final");
+  return 0;
+}
+
+__global__ void labels_to_onehot_kernel(float* __restrict__ onehot, const uint8_t* __restrict__ labels, int64_t n,
+                                        int64_t hw, int n_labels) {
+  const int64_t total = n * n_labels * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % hw;
+    const int l = (int)((i / hw) % n_labels);
+    const int64_t b = i / (hw * n_labels);
+    onehot[i] = (labels[b * hw + p] == l) ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void labels_pool_or_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in, int64_t n, int h, int w,
+                                      int f, int in_mode) {
+  const int oh = h / f, ow = w / f;
+  const int64_t total = n * oh * ow;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+    const int64_t b = i / ((int64_t)ow * oh);
+    unsigned m = 0;
+    for (int dy = 0; dy < f; ++dy)
+      for (int dx = 0; dx < f; ++dx) {
+        const unsigned L = in[(b * h + oy * f + dy) * (int64_t)w + ox * f + dx];
+        m |= in_mode ? L : (1u << (L & 7));
+      }
+    out[i] = (uint8_t)m;
+  }
+}
+
+}  // namespace ppst
+
+extern "C" int ppst_labels_pool_or(uint8_t* out, const uint8_t* in, int64_t n, int h, int w, int factor, int in_mode,
+                                   void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && in && n > 0 && h > 0 && w > 0 && factor >= 1 && h % factor == 0 && w % factor == 0, PPST_ERR_ARG,
+               "labels_pool_or: bad args");
+  const int64_t total = n * (h / factor) * (w / factor);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  labels_pool_or_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, in, n, h, w, factor, in_mode);
+  PPST_LAUNCH_CHECK("labels_pool_or_kernel");
+  return 0;
+}
+
+extern "C" int64_t ppst_plane_reduce_scratch_elems(int64_t n, int64_t c, int64_t hw, int n_regions) {
+  using namespace ppst;
+  if (n <= 0 || c <= 0 || hw <= 0 || n_regions <= 0) return 0;
+  // upper bound over both layouts
+  const ReducePlan a = plan_reduce(n, c, hw, 0), b = plan_reduce(n, c, hw, 1);
+  const int chunks = a.chunks > b.chunks ? a.chunks : b.chunks;
+  return n * c * (int64_t)chunks * n_regions * 3;
+}
+
+extern "C" int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const void* x, const uint8_t* labels,
+                                 const float* shift, float* scratch, int64_t n, int64_t c, int64_t hw, int n_regions,
+                                 int label_mode, int channels_last, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(x && scratch && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "plane_reduce: bad args");
+  PPST_REQUIRE(n_regions >= 1 && n_regions <= kMaxRegions, PPST_ERR_UNSUPPORTED, "plane_reduce: n_regions=%d (1..%d)",
+               n_regions, kMaxRegions);
+  PPST_REQUIRE((n_regions == 1) == (labels == nullptr), PPST_ERR_ARG,
+               "plane_reduce: a label map needs n_regions >= 2, no label map needs n_regions == 1");
+  cudaStream_t st = (cudaStream_t)stream;
+#define PPST_RED(R_)                                                                                      \
+  PPST_DISPATCH_DTYPE(dtype, T, return launch_reduce<T, R_>(sum, sumsq, vmax, (const T*)x, labels, shift, \
+                                                            scratch, n, c, hw, label_mode, channels_last, st))
+  switch (n_regions) {
+    case 1: PPST_RED(1);
+    case 2: PPST_RED(2);
+    case 3: PPST_RED(3);
+    default: PPST_RED(4);
+  }
+#undef PPST_RED
+  return 0;
+}
+
+extern "C" int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64_t n, int64_t hw, int n_labels,
+                                     void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(onehot && labels && n > 0 && hw > 0 && n_labels > 0, PPST_ERR_ARG, "labels_to_onehot: bad args");
+  const int64_t total = n * n_labels * hw;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  labels_to_onehot_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(onehot, labels, n, hw, n_labels);
+  PPST_LAUNCH_CHECK("labels_to_onehot_kernel");
+  return 0;
+}

@@ -1,0 +1,247 @@
+"""Thin tensor-level wrappers over the C ABI (include/ppst_b200.h).  Device memory, streams and dtypes come
+from PyTorch; every computation happens in libppst_b200.so.  No fallbacks: CPU tensors raise."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ApplyDesc, ConvDesc, F32, BF16, check, dt, ptr, require_cuda, stream
+
+SQRT2 = math.sqrt(2.0)
+_TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16, _lib.F16: torch.float16}
+
+
+def _L():
+    return _lib.load()
+
+
+# ----------------------------------------------------------------------------------------------- layout
+def nchw_to_nhwc(x, dtype=None, out=None, c_off=0):
+    """[n,c,h,w] -> NHWC [n,h,w,C]; writes channel slice [c_off, c_off+c) of `out` if given."""
+    require_cuda(x)
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), device=x.device, dtype=dtype or x.dtype)
+    check(_L().ppst_nchw_to_nhwc(ptr(out), ptr(x), n, c, h * w, out.shape[3], c_off, dt(x), dt(out), stream()))
+    return out
+
+
+def nhwc_to_nchw(x, c=None, c_off=0, dtype=None):
+    require_cuda(x)
+    n, h, w, cs = x.shape
+    c = cs if c is None else c
+    out = torch.empty((n, c, h, w), device=x.device, dtype=dtype or x.dtype)
+    check(_L().ppst_nhwc_to_nchw(ptr(out), ptr(x), n, c, h * w, cs, c_off, dt(x), dt(out), stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- reductions
+_scratch = {}
+
+
+def _get_scratch(device, elems):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < elems:
+        buf = torch.empty(max(int(elems), 1 << 20), device=device, dtype=torch.float32)
+        _scratch[key] = buf
+    return buf
+
+
+def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift=None, want=("sum", "sumsq", "max")):
+    """Per-(n, region, c) sum / sumsq / max over H*W.  x: [n,c,h,w] (channels_last False) or [n,h,w,c] (True).
+    Returns dict of f32 [n, n_regions, c] tensors."""
+    require_cuda(x, labels, shift)
+    assert x.is_contiguous()
+    if channels_last:
+        n, h, w, c = x.shape
+    else:
+        n, c, h, w = x.shape
+    hw = h * w
+    L = _L()
+    scratch = _get_scratch(x.device, L.ppst_plane_reduce_scratch_elems(n, c, hw, n_regions))
+    outs = {k: torch.empty((n, n_regions, c), device=x.device, dtype=torch.float32) for k in want}
+    if labels is not None:
+        assert labels.dtype == torch.uint8 and labels.is_contiguous() and labels.numel() == n * hw
+    check(L.ppst_plane_reduce(ptr(outs.get("sum")), ptr(outs.get("sumsq")), ptr(outs.get("max")), ptr(x), ptr(labels),
+                              ptr(shift), ptr(scratch), n, c, hw, n_regions, label_mode, 1 if channels_last else 0,
+                              dt(x), stream()))
+    return outs
+
+
+def labels_to_onehot(labels, n_labels=3):
+    require_cuda(labels)
+    n, h, w = labels.shape
+    out = torch.empty((n, n_labels, h, w), device=labels.device, dtype=torch.float32)
+    check(_L().ppst_labels_to_onehot(ptr(out), ptr(labels.contiguous()), n, h * w, n_labels, stream()))
+    return out
+
+
+def labels_pool_or(labels, factor, in_mode):
+    require_cuda(labels)
+    n, h, w = labels.shape
+    out = torch.empty((n, h // factor, w // factor), device=labels.device, dtype=torch.uint8)
+    check(_L().ppst_labels_pool_or(ptr(out), ptr(labels.contiguous()), n, h, w, factor, in_mode, stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- convolution
+def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(1, 1), phase_off=(0, 0),
+              full_hw=None, cout_stride=None, c_off=0, act=False, slope=0.2, gain=1.0, noise_w=0.0,
+              in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0):
+    n, in_h, in_w, cin = x_shape
+    d = ConvDesc()
+    d.n, d.in_h, d.in_w, d.cin = n, in_h, in_w, cin
+    d.out_h, d.out_w = out_hw
+    d.cout, d.kh, d.kw, d.stride = cout, kh, kw, stride
+    d.off_y, d.off_x = off
+    d.phases_y, d.phases_x = phases
+    d.phase_off_dy, d.phase_off_dx = phase_off
+    fh, fw = full_hw if full_hw else (out_hw[0] * phases[0], out_hw[1] * phases[1])
+    d.full_h, d.full_w = fh, fw
+    d.cout_stride = cout_stride if cout_stride else cout
+    d.c_off = c_off
+    d.has_act = 1 if act else 0
+    d.slope, d.gain, d.noise_w = slope, gain, noise_w
+    d.in_dtype, d.out_dtype = in_dtype, out_dtype
+    d.in_row_pitch, d.in_img_pitch = in_row_pitch, in_img_pitch
+    return d
+
+
+def conv_simt(out, x, weight_f32, bias, noise, d):
+    require_cuda(out, x, weight_f32, bias, noise)
+    check(_L().ppst_conv_simt(ptr(out), ptr(x), ptr(weight_f32), ptr(bias), ptr(noise), ctypes.byref(d), stream()))
+    return out
+
+
+def conv_tc_stats_elems(d):
+    return int(_L().ppst_conv_tc_stats_elems(ctypes.byref(d)))
+
+
+def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
+    require_cuda(out, x, weight_bf16, bias, noise, stats)
+    check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
+                            stream()))
+    return out
+
+
+def conv_tc_available():
+    return bool(_L().ppst_conv_tc_available())
+
+
+# ----------------------------------------------------------------------------------------------- epilogues
+def in_coeffs(n, c, sum_=None, sumsq=None, count=1.0, shift=None, style=None, bias=None, n_partials=0, eps=1e-5,
+              use_norm=True, device=None):
+    device = device or (sum_ if sum_ is not None else style if style is not None else bias).device
+    a = torch.empty((n, c), device=device, dtype=torch.float32)
+    b = torch.empty((n, c), device=device, dtype=torch.float32)
+    check(_L().ppst_in_coeffs(ptr(a), ptr(b), ptr(sum_), ptr(sumsq), ptr(shift), ptr(style), ptr(bias), n, c,
+                              n_partials, float(count), float(eps), 1 if use_norm else 0, stream()))
+    return a, b
+
+
+def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0, pre_gain=1.0, post_slope=1.0,
+                 post_gain=1.0, res_mode=0, up=1, pad=(0, 0, 0, 0), pad_mode=0, out=None, out_dtype=None, out_c_off=0):
+    """x NHWC [n,h,w,c] (dense); see ppst_affine_apply.  pad = (top, bottom, left, right)."""
+    require_cuda(x, a, b, res, ra, rb)
+    n, h, w, cs = x.shape
+    assert cs == c and x.is_contiguous()
+    oh, ow = h * up + pad[0] + pad[1], w * up + pad[2] + pad[3]
+    if out is None:
+        out = torch.empty((n, oh, ow, c), device=x.device, dtype=out_dtype or x.dtype)
+    assert out.shape[:3] == (n, oh, ow)
+    d = ApplyDesc()
+    d.n, d.h, d.w, d.c, d.up = n, h, w, c, up
+    d.pad_t, d.pad_b, d.pad_l, d.pad_r = pad
+    d.pad_mode = pad_mode
+    d.pre_slope, d.pre_gain, d.post_slope, d.post_gain = pre_slope, pre_gain, post_slope, post_gain
+    d.res_mode = res_mode
+    d.x_dtype, d.out_dtype = dt(x), dt(out)
+    d.res_dtype = dt(res) if res is not None else dt(x)
+    d.out_c_stride, d.out_c_off = out.shape[3], out_c_off
+    check(_L().ppst_affine_apply(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d), stream()))
+    return out
+
+
+def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0):
+    """mode 0 bilinear (align_corners False), 1 adaptive average.  x NHWC dense."""
+    require_cuda(x)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, out_hw[0], out_hw[1], c), device=x.device, dtype=out_dtype or x.dtype)
+    check(_L().ppst_resample(ptr(out), ptr(x), n, h, w, out_hw[0], out_hw[1], c, out.shape[3], out_c_off, mode,
+                             dt(x), dt(out), stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- dense / vectors
+def linear(x, w, b=None, w_scale=1.0, b_scale=1.0, relu_in=False):
+    require_cuda(x, w, b)
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.stride(-1) == 1
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+    check(_L().ppst_linear(ptr(y), ptr(x), ptr(w), ptr(b), m, n, k, x.stride(0), float(w_scale), float(b_scale),
+                           1 if relu_in else 0, stream()))
+    return y
+
+
+def l2_normalize(x, eps, mode):
+    require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(_L().ppst_l2_normalize(ptr(y), ptr(x), x.shape[0], x.shape[1], float(eps), mode, stream()))
+    return y
+
+
+def lerp(a, b, r):
+    require_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    y = torch.empty_like(a)
+    check(_L().ppst_lerp(ptr(y), ptr(a), ptr(b), float(r), a.numel(), stream()))
+    return y
+
+
+def gemm_f32(a, b, trans_b, alpha=1.0, out=None):
+    """a [B,m,k], b [B,k,n] (trans_b False) or [B,n,k] (True), f32 contiguous -> [B,m,n]."""
+    require_cuda(a, b)
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
+    bt, m, k = a.shape
+    n = b.shape[1] if trans_b else b.shape[2]
+    if out is None:
+        out = torch.empty((bt, m, n), device=a.device, dtype=torch.float32)
+    ldb = b.shape[2]
+    check(_L().ppst_gemm_f32(ptr(out), ptr(a), ptr(b), bt, m, n, k, k, ldb, n, m * k, b.shape[1] * b.shape[2], m * n,
+                             1 if trans_b else 0, float(alpha), stream()))
+    return out
+
+
+def softmax_rows_(x, divisor=1.0):
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    cols = x.shape[-1]
+    check(_L().ppst_softmax_rows(ptr(x), x.numel() // cols, cols, float(divisor), stream()))
+    return x
+
+
+# ----------------------------------------------------------------------------------------------- correlation
+def rselfcorr(fea_nhwc, out=None, out_c_off=0, out_dtype=None):
+    require_cuda(fea_nhwc)
+    n, h, w, c = fea_nhwc.shape
+    if out is None:
+        out = torch.empty((n, h // 4, w // 4, 256), device=fea_nhwc.device, dtype=out_dtype or fea_nhwc.dtype)
+    check(_L().ppst_rselfcorr(ptr(out), ptr(fea_nhwc), n, h, w, c, out.shape[3], out_c_off, dt(fea_nhwc), dt(out),
+                              stream()))
+    return out
+
+
+def corr_prepare(x_rows, c_center):
+    """x_rows: [..., c] channels-last; returns f32 of the same shape, centred (first c_center) + L2-normalised."""
+    require_cuda(x_rows)
+    x_rows = x_rows.contiguous()
+    c = x_rows.shape[-1]
+    out = torch.empty(x_rows.shape, device=x_rows.device, dtype=torch.float32)
+    check(_L().ppst_corr_prepare(ptr(out), ptr(x_rows), x_rows.numel() // c, c, c_center, dt(x_rows), stream()))
+    return out

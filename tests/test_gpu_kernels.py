@@ -1,0 +1,471 @@
+"""Kernel-level parity on the GPU: every C-ABI entry point against the oracle / plain fp32 PyTorch math,
+called through the ctypes binding (no fallbacks anywhere)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ppst_oracle as O  # noqa: E402
+
+T = torch.from_numpy
+DEV = "cuda"
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ plugin ops
+def test_fused_leaky_relu_golden_bit_exact(golden):
+    from ppst_b200.stylegan2_op import fused_leaky_relu
+    g = golden("ops")
+    for name in g["flrelu/names"]:
+        slope, scale = (float(v) for v in g["flrelu/%s/cfg" % name])
+        x = T(g["flrelu/%s/x" % name]).to(DEV).requires_grad_(True)
+        b = T(g["flrelu/%s/b" % name]).to(DEV).requires_grad_(True)
+        y = fused_leaky_relu(x, b, slope, scale)
+        assert np.array_equal(y.detach().cpu().numpy(), g["flrelu/%s/y" % name]), name   # bit-exact in fp32
+        go = T(g["flrelu/%s/go" % name]).to(DEV)
+        y.backward(go)
+        assert np.abs(x.grad.cpu().numpy() - g["flrelu/%s/gx" % name]).max() <= 1e-6
+        assert np.abs(b.grad.cpu().numpy() - g["flrelu/%s/gb" % name]).max() <= 2e-4
+
+
+def test_fused_leaky_relu_large_dtypes_and_module():
+    from ppst_b200.stylegan2_op import FusedLeakyReLU, fused_leaky_relu
+    x = torch.randn(2, 64, 128, 128, generator=gen(1))
+    b = torch.randn(64, generator=gen(2))
+    want = O.fused_leaky_relu(x, b)
+    got = fused_leaky_relu(x.to(DEV), b.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    for dtp, tol in ((torch.bfloat16, 2e-2), (torch.float16, 2e-3)):
+        got = fused_leaky_relu(x.to(DEV, dtp), b.to(DEV, dtp)).float().cpu()
+        ref = O.fused_leaky_relu(x.to(dtp).float(), b.to(dtp).float())
+        assert (got - ref).abs().max() <= tol * ref.abs().max()
+    # odd plane length (scalar path) and the [B, C] form
+    x = torch.randn(3, 5, 33, 31, generator=gen(3))
+    b = torch.randn(5, generator=gen(4))
+    assert torch.equal(fused_leaky_relu(x.to(DEV), b.to(DEV)).cpu(), O.fused_leaky_relu(x, b))
+    x = torch.randn(7, 2048, generator=gen(5))
+    b = torch.randn(2048, generator=gen(6))
+    assert torch.equal(fused_leaky_relu(x.to(DEV), b.to(DEV), 0.1, 1.5).cpu(), O.fused_leaky_relu(x, b, 0.1, 1.5))
+    m = FusedLeakyReLU(5).to(DEV)
+    assert list(m.state_dict()) == ["bias"] and float(m.bias.abs().sum()) == 0.0
+    with pytest.raises(RuntimeError):
+        fused_leaky_relu(torch.zeros(1, 2, 3, 3), torch.zeros(2))        # CPU tensors: no fallback
+
+
+def test_fused_leaky_relu_double_backward():
+    from ppst_b200.stylegan2_op import fused_leaky_relu
+    x = torch.randn(2, 3, 9, 9, generator=gen(7)).to(DEV).requires_grad_(True)
+    b = torch.randn(3, generator=gen(8)).to(DEV).requires_grad_(True)
+    y = fused_leaky_relu(x, b)
+    gx, = torch.autograd.grad(y.sum(), x, create_graph=True)
+    # R1-style penalty: second order through the op (ppst_model.py:145-150 uses this on D)
+    (gx.pow(2).sum()).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    br = b.detach().clone().requires_grad_(True)
+    yr = F.leaky_relu(xr + br.view(1, -1, 1, 1), 0.2) * math.sqrt(2)
+    gxr, = torch.autograd.grad(yr.sum(), xr, create_graph=True)
+    gxr.pow(2).sum().backward()
+    assert torch.allclose(gx, gxr, atol=1e-6)
+    # gate is piecewise constant: second derivative w.r.t. x is zero in both implementations
+    assert x.grad is None or float(x.grad.abs().max()) == 0.0 or torch.allclose(x.grad, xr.grad, atol=1e-6)
+
+
+def test_upfirdn2d_golden_all_modes(golden):
+    from ppst_b200.stylegan2_op import upfirdn2d
+    g = golden("ops")
+    for name in g["upfirdn2d/names"]:
+        up, down, p0, p1 = (int(v) for v in g["upfirdn2d/%s/cfg" % name])
+        y = upfirdn2d(T(g["upfirdn2d/%s/x" % name]).to(DEV), T(g["upfirdn2d/%s/k" % name]).to(DEV), up, down, (p0, p1))
+        want = g["upfirdn2d/%s/y" % name]
+        assert tuple(y.shape) == want.shape, name
+        assert np.abs(y.cpu().numpy() - want).max() <= 2e-6, name
+
+
+def test_upfirdn2d_hot_path_sizes_and_dtypes():
+    from ppst_b200.stylegan2_op import upfirdn2d
+    k = O.make_kernel([1, 2, 1])
+    for shape, pad in (((1, 32, 259, 259), (0, 0)), ((2, 16, 256, 256), (1, 0)), ((1, 8, 131, 67), (0, 0))):
+        x = torch.randn(*shape, generator=gen(shape[2]))
+        want = O.upfirdn2d(x, k, pad=pad)
+        got = upfirdn2d(x.to(DEV), k.to(DEV), pad=pad).cpu()
+        assert got.shape == want.shape and (got - want).abs().max() <= 1e-6
+        got16 = upfirdn2d(x.to(DEV, torch.bfloat16), k.to(DEV), pad=pad).float().cpu()
+        assert (got16 - O.upfirdn2d(x.bfloat16().float(), k, pad=pad)).abs().max() <= 2e-2
+    k4 = O.make_kernel([1, 3, 3, 1])
+    x = torch.randn(2, 8, 64, 64, generator=gen(11))
+    for up, down, pad in ((1, 1, (2, 1)), (2, 1, (2, 1)), (1, 2, (1, 1))):
+        kk = k4 * (up ** 2)
+        want = O.upfirdn2d(x, kk, up, down, pad)
+        got = upfirdn2d(x.to(DEV), kk.to(DEV), up, down, pad).cpu()
+        assert got.shape == want.shape and (got - want).abs().max() <= 2e-6
+
+
+def test_upfirdn2d_backward_and_double_backward():
+    from ppst_b200.stylegan2_op import upfirdn2d
+    k = O.make_kernel([1, 3, 3, 1])
+    for up, down, pad in ((1, 1, (2, 1)), (2, 1, (2, 1)), (1, 2, (1, 1))):
+        x = torch.randn(1, 2, 12, 12, generator=gen(up * 10 + down)).to(DEV).requires_grad_(True)
+        y = upfirdn2d(x, k.to(DEV), up, down, pad)
+        go = torch.randn(y.shape, generator=gen(5)).to(DEV).requires_grad_(True)
+        gx, = torch.autograd.grad(y, x, go, create_graph=True)
+        xr = x.detach().cpu().requires_grad_(True)
+        yr = O.upfirdn2d(xr, k, up, down, pad)
+        gxr, = torch.autograd.grad(yr, xr, go.detach().cpu())
+        assert (gx.detach().cpu() - gxr).abs().max() <= 2e-6
+        # double backward: d(gx . v)/d(go) = upfirdn2d(v) (linear op)
+        v = torch.randn(gx.shape, generator=gen(6)).to(DEV)
+        ggo, = torch.autograd.grad(gx, go, v)
+        assert (ggo.cpu() - O.upfirdn2d(v.cpu(), k, up, down, pad)).abs().max() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ reductions
+def test_plane_reduce_layouts_and_regions():
+    from ppst_b200 import ops
+    x = torch.randn(2, 24, 37, 29, generator=gen(21)) * 2 + 0.3
+    ref_sum = x.sum((2, 3))
+    ref_sq = (x * x).sum((2, 3))
+    ref_max = x.amax((2, 3))
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 0.0)):
+        xd = x.to(dtype)
+        xf = xd.float()
+        for cl in (False, True):
+            xin = xd.to(DEV)
+            if cl:
+                xin = xin.permute(0, 2, 3, 1).contiguous()
+            r = ops.plane_reduce(xin, cl)
+            assert torch.allclose(r["sum"][:, 0].cpu(), xf.sum((2, 3)), rtol=1e-4, atol=1e-2)
+            assert torch.allclose(r["sumsq"][:, 0].cpu(), (xf * xf).sum((2, 3)), rtol=1e-4, atol=1e-2)
+            assert torch.equal(r["max"][:, 0].cpu(), xf.amax((2, 3)))
+    # exact two-pass variance
+    xin = x.to(DEV).permute(0, 2, 3, 1).contiguous()
+    r1 = ops.plane_reduce(xin, True, want=("sum",))
+    mean = (r1["sum"][:, 0] / (37 * 29)).contiguous()
+    r2 = ops.plane_reduce(xin, True, shift=mean, want=("sum", "sumsq"))
+    var = r2["sumsq"][:, 0] / (37 * 29) - (r2["sum"][:, 0] / (37 * 29)) ** 2
+    assert torch.allclose(var.cpu(), x.var((2, 3), unbiased=False), rtol=1e-5, atol=1e-6)
+    # regions keyed by the integer label map: bit-exact membership
+    lab = O.make_label_map(2, 37, 29, blocky=False)
+    want = O.masked_gap_gmp(x, lab)
+    for cl in (False, True):
+        xin = x.to(DEV)
+        if cl:
+            xin = xin.permute(0, 2, 3, 1).contiguous()
+        r = ops.plane_reduce(xin, cl, labels=lab.to(DEV), n_regions=3, want=("sum", "max"))
+        for i in range(3):
+            assert torch.allclose(r["sum"][:, i].cpu() / (37 * 29), want[i][0], rtol=1e-4, atol=1e-5)
+            assert torch.equal(r["max"][:, i].cpu(), want[i][1])
+    # one-hot and pooled membership bitmasks == MaxPool2d of the one-hot mask
+    oh = ops.labels_to_onehot(lab.to(DEV)).cpu()
+    assert np.array_equal(oh[0].numpy(), O.mask_labels(lab[0].numpy()).astype(np.float32))
+    lab2 = O.make_label_map(2, 32, 48)
+    oh2 = torch.stack([torch.tensor(O.mask_labels(lab2[b].numpy()), dtype=torch.float) for b in range(2)])
+    pooled = F.max_pool2d(oh2, 2, 2)
+    bits = ops.labels_pool_or(lab2.to(DEV), 2, 0).cpu()
+    for i in range(3):
+        assert torch.equal(((bits >> i) & 1).float(), pooled[:, i])
+    x2 = torch.randn(2, 8, 16, 24, generator=gen(23))
+    r = ops.plane_reduce(x2.to(DEV).permute(0, 2, 3, 1).contiguous(), True, labels=bits.to(DEV), n_regions=3,
+                         label_mode=1, want=("sum", "max"))
+    for i in range(3):
+        xm = x2 * pooled[:, i:i + 1]
+        assert torch.allclose(r["sum"][:, i].cpu(), xm.sum((2, 3)), rtol=1e-4, atol=1e-4)
+        assert torch.equal(r["max"][:, i].cpu(), xm.amax((2, 3)))
+
+
+def test_layout_roundtrip():
+    from ppst_b200 import ops
+    x = torch.randn(2, 19, 13, 21, generator=gen(31))
+    nhwc = ops.nchw_to_nhwc(x.to(DEV))
+    assert torch.equal(nhwc.cpu(), x.permute(0, 2, 3, 1))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc).cpu(), x)
+    b16 = ops.nchw_to_nhwc(x.to(DEV), dtype=torch.bfloat16)
+    assert torch.equal(b16.float().cpu(), x.bfloat16().float().permute(0, 2, 3, 1))
+    buf = torch.zeros(2, 13, 21, 40, device=DEV)
+    ops.nchw_to_nhwc(x.to(DEV), out=buf, c_off=8)
+    assert torch.equal(buf[..., 8:27].cpu(), x.permute(0, 2, 3, 1)) and float(buf[..., :8].abs().sum()) == 0
+    assert torch.equal(ops.nhwc_to_nchw(buf, c=19, c_off=8).cpu(), x)
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def pack_w(w):
+    """[co, ci, kh, kw] -> [co, kh*kw*ci] (tap-major, channel-minor)."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def run_conv(kind, x_nchw, w, bias, stride, off, out_hw, act=False, noise=None, noise_w=0.0, dtype=torch.float32,
+             stats=False):
+    from ppst_b200 import ops
+    from ppst_b200._lib import F32, BF16
+    n, ci, h, wd = x_nchw.shape
+    co = w.shape[0]
+    x = ops.nchw_to_nhwc(x_nchw.to(DEV), dtype=dtype)
+    code = F32 if dtype == torch.float32 else BF16
+    d = ops.conv_desc((n, h, wd, ci), co, w.shape[2], w.shape[3], stride=stride, off=off, out_hw=out_hw, act=act,
+                      slope=0.2, gain=math.sqrt(2) if act else 1.0, noise_w=noise_w, in_dtype=code, out_dtype=code)
+    out = torch.empty((n, out_hw[0], out_hw[1], co), device=DEV, dtype=dtype)
+    b = bias.to(DEV) if bias is not None else None
+    nz = noise.to(DEV).contiguous() if noise is not None else None
+    if kind == "simt":
+        ops.conv_simt(out, x, pack_w(w).to(DEV), b, nz, d)
+        return out
+    st = torch.zeros(ops.conv_tc_stats_elems(d), device=DEV) if stats else None
+    ops.conv_tc(out, x, pack_w(w).to(DEV, torch.bfloat16), b, nz, st, d)
+    return (out, st) if stats else out
+
+
+CONV_CASES = [  # ci, co, k, stride, pad (symmetric zero pad), h, w
+    (16, 24, 3, 1, 1, 19, 23),
+    (3, 32, 1, 1, 0, 17, 17),
+    (32, 8, 3, 2, 0, 21, 21),
+    (16, 16, 5, 2, 0, 19, 19),
+    (7, 5, 3, 1, 1, 9, 11),
+]
+
+
+def test_conv_simt_matches_conv2d():
+    for ci, co, k, s, p, h, w in CONV_CASES:
+        g = gen(ci * 100 + co)
+        x = torch.randn(2, ci, h, w, generator=g)
+        wt = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+        b = torch.randn(co, generator=g)
+        want = F.conv2d(x, wt, b, stride=s, padding=p)
+        oh, ow = want.shape[2:]
+        got = run_conv("simt", x, wt, b, s, (-p, -p), (oh, ow))
+        assert (got.permute(0, 3, 1, 2).cpu() - want).abs().max() <= 2e-5, (ci, co, k, s)
+    # fused epilogue: + bias + noise -> lrelu * sqrt2
+    g = gen(77)
+    x = torch.randn(2, 16, 12, 12, generator=g)
+    wt = torch.randn(8, 16, 3, 3, generator=g) / 12
+    b = torch.randn(8, generator=g)
+    nz = torch.randn(2, 12, 12, generator=g)
+    want = O.fused_leaky_relu(F.conv2d(x, wt, None, padding=1) + 0.3 * nz[:, None], b)
+    got = run_conv("simt", x, wt, b, 1, (-1, -1), (12, 12), act=True, noise=nz, noise_w=0.3)
+    assert (got.permute(0, 3, 1, 2).cpu() - want).abs().max() <= 2e-5
+
+
+def pack_convT(w):
+    """EqualizedConv2d fused upscale (stylegan2_layers.py:312-321) as 4 sub-pixel 2x2 phase convolutions.
+    w: [co, ci, 3, 3] -> packed [4][co][2*2*ci] with tap (t,u) of phase (a,b) = W'[ci,co,3-a-2t,3-b-2u]."""
+    wt = F.pad(w.permute(1, 0, 2, 3), [1, 1, 1, 1])
+    wt = wt[:, :, 1:, 1:] + wt[:, :, :-1, 1:] + wt[:, :, 1:, :-1] + wt[:, :, :-1, :-1]      # [ci, co, 4, 4]
+    ci, co = wt.shape[:2]
+    out = torch.empty(2, 2, co, 2, 2, ci)
+    for a in range(2):
+        for b in range(2):
+            for t in range(2):
+                for u in range(2):
+                    out[a, b, :, t, u, :] = wt[:, :, 3 - a - 2 * t, 3 - b - 2 * u].t()
+    return out.reshape(4, co, 4 * ci).contiguous(), wt
+
+
+def test_conv_transpose_as_phases():
+    from ppst_b200 import ops
+    from ppst_b200._lib import F32, BF16
+    g = gen(99)
+    ci, co, h, w = 64, 32, 18, 20
+    x = torch.randn(2, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g) / math.sqrt(ci * 9)
+    b = torch.randn(co, generator=g)
+    packed, w4 = pack_convT(wt)
+    want = F.conv_transpose2d(x, w4, stride=2, padding=1) + b.view(1, -1, 1, 1)
+    for kind, dtype, tol in (("simt", torch.float32, 3e-5), ("tc", torch.bfloat16, 4e-2)):
+        if kind == "tc" and not ops.conv_tc_available():
+            pytest.skip("tcgen05 path unavailable")
+        code = F32 if dtype == torch.float32 else BF16
+        xin = ops.nchw_to_nhwc(x.to(DEV), dtype=dtype)
+        d = ops.conv_desc((2, h, w, ci), co, 2, 2, off=(-1, -1), out_hw=(h, w), phases=(2, 2), phase_off=(1, 1),
+                          in_dtype=code, out_dtype=code)
+        out = torch.empty((2, 2 * h, 2 * w, co), device=DEV, dtype=dtype)
+        if kind == "simt":
+            ops.conv_simt(out, xin, packed.to(DEV), b.to(DEV), None, d)
+            ref = want
+        else:
+            ops.conv_tc(out, xin, packed.to(DEV, torch.bfloat16), b.to(DEV), None, None, d)
+            ref = F.conv_transpose2d(x.bfloat16().float(), w4.bfloat16().float(), stride=2, padding=1) + b.view(1, -1, 1, 1)
+        err = (out.float().permute(0, 3, 1, 2).cpu() - ref).abs().max()
+        assert err <= tol, (kind, float(err))
+
+
+TC_CASES = [  # ci, co, k, stride, pad, h, w, batch
+    (64, 128, 3, 1, 1, 32, 32, 2),      # BN=128, 128B swizzle
+    (128, 256, 3, 1, 1, 16, 24, 1),     # BN=256, ragged tile edge
+    (64, 64, 1, 1, 0, 20, 20, 2),       # 1x1, BN=64
+    (32, 32, 3, 1, 1, 24, 24, 1),       # cin 32: 64B swizzle, BN=32
+    (32, 64, 5, 2, 0, 35, 35, 1),       # stride 2 via tensor-map element strides
+    (64, 96, 3, 1, 1, 9, 70, 1),        # cout = 3*32, odd sizes
+    (256, 384, 3, 1, 1, 16, 16, 1),     # BN=128 x 3
+]
+
+
+def test_conv_tc_matches_reference():
+    from ppst_b200 import ops
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    for ci, co, k, s, p, h, w, n in TC_CASES:
+        g = gen(ci + co + k)
+        x = torch.randn(n, ci, h, w, generator=g)
+        wt = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+        b = torch.randn(co, generator=g)
+        ref = F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), b, stride=s, padding=p)
+        oh, ow = ref.shape[2:]
+        got, st = run_conv("tc", x, wt, b, s, (-p, -p), (oh, ow), dtype=torch.bfloat16, stats=True)
+        gotf = got.float().permute(0, 3, 1, 2).cpu()
+        err = (gotf - ref).abs().max()
+        assert err <= 2e-2 * max(1.0, float(ref.abs().max())), ((ci, co, k, s), float(err))
+        # per-tile statistics of the stored values reduce to the plane sums
+        half = st.numel() // 2
+        parts = half // (n * co)
+        ssum = st[:half].view(n, parts, co).sum(1).cpu()
+        ssq = st[half:].view(n, parts, co).sum(1).cpu()
+        assert torch.allclose(ssum, gotf.sum((2, 3)), rtol=2e-3, atol=2e-2), (ci, co, k, s)
+        assert torch.allclose(ssq, (gotf * gotf).sum((2, 3)), rtol=2e-3, atol=2e-2), (ci, co, k, s)
+    # fused epilogue on the tensor-core path
+    g = gen(5)
+    x = torch.randn(2, 64, 16, 16, generator=g)
+    wt = torch.randn(64, 64, 3, 3, generator=g) / 24
+    b = torch.randn(64, generator=g)
+    nz = torch.randn(2, 16, 16, generator=g)
+    ref = O.fused_leaky_relu(F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), None, padding=1) + 0.3 * nz[:, None], b)
+    got = run_conv("tc", x, wt, b, 1, (-1, -1), (16, 16), act=True, noise=nz, noise_w=0.3, dtype=torch.bfloat16)
+    assert (got.float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 3e-2
+
+
+def test_conv_reads_interior_of_padded_buffer():
+    from ppst_b200 import ops
+    from ppst_b200._lib import F32
+    g = gen(41)
+    x = torch.randn(1, 16, 10, 12, generator=g)
+    wt = torch.randn(8, 16, 3, 3, generator=g) / 12
+    want = F.conv2d(x, wt, None, stride=2, padding=1)
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")                  # the conv must NOT see this border
+    buf = ops.nchw_to_nhwc(xp.to(DEV))
+    view = buf[:, 1:, 1:, :]
+    d = ops.conv_desc((1, 10, 12, 16), 8, 3, 3, stride=2, off=(-1, -1), out_hw=tuple(want.shape[2:]), in_dtype=F32,
+                      out_dtype=F32, in_row_pitch=14 * 16, in_img_pitch=12 * 14 * 16)
+    out = torch.empty((1,) + tuple(want.shape[2:]) + (8,), device=DEV)
+    ops.conv_simt(out, view, pack_w(wt).to(DEV), None, None, d)
+    assert (out.permute(0, 3, 1, 2).cpu() - want).abs().max() <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ epilogues
+def test_in_coeffs_and_affine_apply():
+    from ppst_b200 import ops
+    g = gen(51)
+    x = torch.randn(2, 16, 10, 14, generator=g) * 1.5 + 0.4
+    style = torch.randn(2, 32, generator=g)
+    bias = torch.randn(16, generator=g)
+    xin = ops.nchw_to_nhwc(x.to(DEV))
+    r = ops.plane_reduce(xin, True, want=("sum", "sumsq"))
+    a, b = ops.in_coeffs(2, 16, r["sum"][:, 0].contiguous(), r["sumsq"][:, 0].contiguous(), count=140,
+                         style=style.to(DEV), bias=bias.to(DEV))
+    y = ops.affine_apply(xin, 16, a, b)
+    s = style.view(2, 2, 16, 1, 1)
+    want = O.instance_norm(x) * (s[:, 0] + 1) + s[:, 1] + bias.view(1, -1, 1, 1)
+    assert (y.permute(0, 3, 1, 2).cpu() - want).abs().max() <= 2e-5
+    # pre-activation, residual with its own affine, post gain  (encoder ResBlock tail)
+    res = torch.randn(2, 16, 10, 14, generator=g)
+    ra, rb = torch.rand(2, 16, generator=g) + 0.5, torch.randn(2, 16, generator=g)
+    y = ops.affine_apply(xin, 16, a, b, res=ops.nchw_to_nhwc(res.to(DEV)), ra=ra.to(DEV), rb=rb.to(DEV),
+                         pre_slope=0.2, pre_gain=math.sqrt(2), res_mode=1, post_gain=1 / math.sqrt(2))
+    w2 = (F.leaky_relu(want, 0.2) * math.sqrt(2) + res * ra[:, :, None, None] + rb[:, :, None, None]) / math.sqrt(2)
+    assert (y.permute(0, 3, 1, 2).cpu() - w2).abs().max() <= 2e-5
+    # post activation after the residual (ResidualBlock tail, generator.py:29-31)
+    y = ops.affine_apply(xin, 16, a, b, res=ops.nchw_to_nhwc(res.to(DEV)), res_mode=1, post_slope=0.3)
+    w3 = want + res
+    w3 = torch.where(w3 >= 0, w3, 0.3 * w3)
+    assert (y.permute(0, 3, 1, 2).cpu() - w3).abs().max() <= 2e-5
+    # paddings, nearest x2, bilinear x2 skip
+    for mode, name in ((1, "reflect"), (2, "replicate"), (0, "constant")):
+        y = ops.affine_apply(xin, 16, a, b, pad=(2, 1, 2, 1), pad_mode=mode)
+        assert (y.permute(0, 3, 1, 2).cpu() - F.pad(want, (2, 1, 2, 1), mode=name)).abs().max() <= 2e-5
+    y = ops.affine_apply(xin, 16, a, b, up=2, pad=(1, 1, 1, 1), pad_mode=0)
+    wu = F.pad(want.repeat_interleave(2, 2).repeat_interleave(2, 3), (1, 1, 1, 1))
+    assert (y.permute(0, 3, 1, 2).cpu() - wu).abs().max() <= 2e-5
+    lo = torch.randn(2, 16, 5, 7, generator=g)
+    y = ops.affine_apply(xin, 16, a, b, res=ops.nchw_to_nhwc(lo.to(DEV)), res_mode=2, post_gain=1 / math.sqrt(2))
+    w4 = (want + F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=False)) / math.sqrt(2)
+    assert (y.permute(0, 3, 1, 2).cpu() - w4).abs().max() <= 2e-5
+    # bf16 storage, 3-channel scalar path, channel-slice destination
+    x3 = torch.randn(1, 3, 6, 6, generator=g)
+    y = ops.affine_apply(ops.nchw_to_nhwc(x3.to(DEV)), 3, None, None, post_gain=2.0)
+    assert torch.equal(y.permute(0, 3, 1, 2).cpu(), x3 * 2)
+    dst = torch.zeros(2, 10, 14, 48, device=DEV, dtype=torch.bfloat16)
+    ops.affine_apply(ops.nchw_to_nhwc(x.to(DEV), dtype=torch.bfloat16), 16, a, b, out=dst, out_c_off=16)
+    assert (dst[..., 16:32].float().permute(0, 3, 1, 2).cpu() - want).abs().max() <= 1e-1
+    assert float(dst[..., :16].abs().sum()) == 0 and float(dst[..., 32:].abs().sum()) == 0
+
+
+def test_resample():
+    from ppst_b200 import ops
+    x = torch.randn(2, 16, 32, 32, generator=gen(61))
+    xin = ops.nchw_to_nhwc(x.to(DEV))
+    for size in ((64, 64), (16, 16), (32, 32), (256, 256)):
+        y = ops.resample(xin, size, 0)
+        assert (y.permute(0, 3, 1, 2).cpu() - F.interpolate(x, size, mode="bilinear")).abs().max() <= 1e-5
+    for size in ((8, 8), (16, 16), (32, 32)):
+        y = ops.resample(xin, size, 1)
+        assert (y.permute(0, 3, 1, 2).cpu() - F.adaptive_avg_pool2d(x, size)).abs().max() <= 1e-5
+    dst = torch.zeros(2, 8, 8, 64, device=DEV)
+    ops.resample(xin, (8, 8), 1, out=dst, out_c_off=32)
+    assert (dst[..., 32:48].permute(0, 3, 1, 2).cpu() - F.adaptive_avg_pool2d(x, 8)).abs().max() <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ dense / corr
+def test_linear_l2norm_lerp():
+    from ppst_b200 import ops
+    g = gen(71)
+    for m, k, n in ((1, 64, 1024), (3, 2048, 2048), (9, 30, 17)):
+        x = torch.randn(m, k, generator=g)
+        w = torch.randn(n, k, generator=g) / math.sqrt(k)
+        b = torch.randn(n, generator=g)
+        y = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), w_scale=0.5, b_scale=2.0, relu_in=True)
+        want = F.linear(F.relu(x), w * 0.5, b * 2.0)
+        assert (y.cpu() - want).abs().max() <= 1e-4
+    v = torch.randn(5, 2048, generator=g)
+    assert torch.allclose(ops.l2_normalize(v.to(DEV), 1e-8, 0).cpu(), O.l2_normalize_rows(v), atol=1e-7)
+    assert torch.allclose(ops.l2_normalize(v.to(DEV), 1e-12, 1).cpu(), F.normalize(v), atol=1e-7)
+    a, b = torch.randn(4, 2048, generator=g), torch.randn(4, 2048, generator=g)
+    assert torch.allclose(ops.lerp(a.to(DEV), b.to(DEV), 0.3).cpu(), O.lerp(a, b, 0.3), atol=1e-7)
+
+
+def test_gemm_and_softmax():
+    from ppst_b200 import ops
+    g = gen(81)
+    a = torch.randn(2, 300, 70, generator=g)
+    bt = torch.randn(2, 130, 70, generator=g)
+    bn = torch.randn(2, 70, 130, generator=g)
+    assert (ops.gemm_f32(a.to(DEV), bt.to(DEV), True, alpha=0.5).cpu() - 0.5 * a @ bt.transpose(1, 2)).abs().max() <= 1e-4
+    assert (ops.gemm_f32(a.to(DEV), bn.to(DEV), False).cpu() - a @ bn).abs().max() <= 1e-4
+    x = torch.randn(33, 4096, generator=g) * 0.3
+    got = ops.softmax_rows_(x.to(DEV).clone(), 0.01).cpu()
+    want = F.softmax(x / 0.01, dim=-1)
+    assert (got - want).abs().max() <= 1e-5 and (got.sum(-1) - 1).abs().max() <= 1e-5
+
+
+def test_rselfcorr_and_corr_prepare():
+    from ppst_b200 import ops
+    g = gen(91)
+    fea = torch.randn(2, 64, 32, 48, generator=g)
+    # oracle reshape is hard-wired to 64x64 patches -> use the general restatement on 8x12 patches
+    b, c, h, w = fea.shape
+    p = fea.reshape(b, c, h // 4, 4, w // 4, 4).permute(0, 1, 2, 4, 3, 5).reshape(b, c, -1, 16)
+    p = p - p.mean(1, keepdim=True)
+    p = p / (p.pow(2).sum(1, keepdim=True).sqrt() + 2.220446049250313e-16)
+    want = torch.einsum("bcli,bclj->blij", p, p).reshape(b, h // 4, w // 4, 256)
+    got = ops.rselfcorr(ops.nchw_to_nhwc(fea.to(DEV)))
+    assert (got.cpu() - want).abs().max() <= 1e-5
+    f = torch.randn(1, 512, 8, 8, generator=g)
+    rows = ops.nchw_to_nhwc(f.to(DEV))
+    prep = ops.corr_prepare(rows, 256).cpu().reshape(64, 512)
+    ff = f.reshape(1, 512, 64)
+    h1 = ff[:, :256] - ff[:, :256].mean(1, keepdim=True)
+    ff = torch.cat((h1, ff[:, 256:]), 1)
+    ff = ff / (ff.pow(2).sum(1, keepdim=True).sqrt() + 2.220446049250313e-16)
+    assert (prep - ff[0].t()).abs().max() <= 1e-6
