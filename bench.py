@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the PPST swap hot path (BASELINE.json metric: swapped images/s @512^2 at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (ppst_b200, bf16 tensor-core mode)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+Workload (config.workload): BASELINE configs[1] "batched swap inference at 512^2, batch 64 ... sharded over
+8xB200" = 8 (content, style) pairs per GPU per step, weak scaling (per-GPU work fixed, 64 pairs at N=8).
+One step = one pass of the whole swap path over one batch of synthetic pairs:
+  E1(c) E2(c) G.extract(c)  E1(s) E2(s) G.extract(s)  Rselfcorr x2  corrm  E2(s, corr)  G.decode   (2.143 TFLOP / image,
+  SURVEY.md 8(d)).  No collective on the data path; torch.distributed is used for barriers and the max-over-ranks time.
+
+One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = through SwapModel.swap() with pinned HOST
+buffers, H2D of both image batches and D2H of the result inside the timed region.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PAIRS_PER_GPU = 8
+SIZE = 512
+FLOP_PER_IMAGE = 2.143e12            # conv + GEMM 2*MAC of the minimal swap unit at 512^2
+METRIC = "swapped images/s @512^2"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(pairs, rank):
+    from oracle import ppst_oracle as O     # seeded synthetic portraits only (input generation, not compute)
+    c = O.make_portraits(pairs, SIZE, SIZE, seed=1234 + rank)
+    s = O.make_portraits(pairs, SIZE, SIZE, seed=4321 + rank, smooth=True)
+    return c, s
+
+
+def cpu_baseline_sample(threads):
+    """The oracle port of the reference's CPU path on a bounded sample: ONE pair at 512^2 (2.143 TFLOP), all host
+    threads.  Returns (images/s, seconds)."""
+    from oracle import ppst_oracle as O
+    torch.set_num_threads(threads)
+    sdE1, sdE2, sdG = O.make_networks(0)
+    c = O.make_portraits(1, SIZE, SIZE, seed=1234)
+    s = O.make_portraits(1, SIZE, SIZE, seed=4321, smooth=True)
+    noises = O.make_noises(1, SIZE, SIZE)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
+        dt = time.perf_counter() - t0
+    return 1.0 / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: /root/reference does not
+    exist on the GPU box and is Python, so nothing can be compiled into oracle/_ref), all host threads, each step a
+    bounded sample of the workload (one pair)."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ppst_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sdE1, sdE2, sdG = O.make_networks(0)
+    c = O.make_portraits(1, SIZE, SIZE, seed=1234)
+    s = O.make_portraits(1, SIZE, SIZE, seed=4321, smooth=True)
+    noises = O.make_noises(1, SIZE, SIZE)
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    with torch.no_grad():
+        for _ in range(warm):
+            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
+        dt = (time.perf_counter() - t0) / steps
+    v = 1.0 / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 swap @512^2; reference arm = bounded sample of 1 (content, style) pair per step "
+                                   "on host cores (oracle port of the reference's pure-PyTorch CPU path)",
+                       "pairs_per_step": 1, "size": SIZE},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "1 pair @512^2 per step, %d step(s)" % steps},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="(content, style) pairs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from ppst_b200 import sharding
+    world, rank, local_rank = sharding.init()
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from oracle import ppst_oracle as O          # weights/inputs generator + the cpu_baseline leg ONLY
+    import ppst_b200
+    from ppst_b200 import _lib, ops
+
+    warm = max(3, args.warmup)
+    pairs = args.pairs
+    sdE1, sdE2, sdG = O.make_networks(0)
+    model = ppst_b200.SwapModel(sdE1, sdE2, sdG, device=dev, mode="bf16")
+    assert model.engine.use_tc, "tcgen05 path inactive"
+    model.noises = {k: v.expand(pairs, -1, -1, -1).contiguous() for k, v in O.make_noises(1, SIZE, SIZE).items()}
+    c_host, s_host = make_inputs(pairs, rank)
+    c_pin, s_pin = c_host.pin_memory(), s_host.pin_memory()
+    out_pin = torch.empty((pairs, 3, SIZE, SIZE), dtype=torch.float32).pin_memory()
+    c_dev, s_dev = c_pin.to(dev), s_pin.to(dev)
+
+    def step_device():
+        return model.swap(c_dev, s_dev)
+
+    def step_e2e():
+        c = c_pin.to(dev, non_blocking=True)
+        s = s_pin.to(dev, non_blocking=True)
+        out = model.swap(c, s)
+        out_pin.copy_(out, non_blocking=True)
+        return out
+
+    def timed(fn, steps):
+        sharding.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        sharding.barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), device=dev)
+        return ms, _lib.launch_count() - l0
+
+    for _ in range(warm):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # per-kernel roofline leg: the same steps with every launch bracketed by CUDA events
+    ops.PROFILE = {}
+    torch.cuda.synchronize()
+    prof_steps = min(args.steps, 2)
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    prof = ops.profile_summary()
+    ops.PROFILE = None
+
+    peaks = load_peaks()
+    total_pairs = pairs * world
+    value = total_pairs * args.steps / (ms * 1e-3)
+    e2e = total_pairs * args.steps / (ms_e2e * 1e-3)
+    tc = prof.get("conv_tc", {"work": 0.0, "ms": 1.0, "launches": 0})
+    achieved_tf = tc["work"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
+    step_ms_prof = sum(v["ms"] for v in prof.values()) / max(prof_steps, 1)
+    kernels = {k: {"launches_per_step": v["launches"] // max(prof_steps, 1), "ms_per_step": v["ms"] / max(prof_steps, 1),
+                   "share": (v["ms"] / max(prof_steps, 1)) / step_ms_prof if step_ms_prof else None,
+                   ("tflops" if k in ("conv_tc", "conv_simt", "gemm_f32") else "gbs"):
+                       v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("conv_tc", "conv_simt", "gemm_f32") else 1e9)
+                       if v["ms"] > 0 else None}
+               for k, v in prof.items()}
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C2 (BASELINE configs[1]): batched swap inference @512^2, %d (content, style) pairs per "
+                               "GPU per step (64 over 8 GPUs), random-init CelebAMaskHQ_default E1/E2/G, full "
+                               "correlation swap (2.143 TFLOP/image)" % pairs,
+                   "pairs_per_gpu": pairs, "size": SIZE, "parallelism": "pairs partitioned, no collective",
+                   "l2": "working set per step >> 126 MB L2 (activations ~ GBs); no explicit flush needed",
+                   "whole_swap_tflops": value * FLOP_PER_IMAGE / 1e12 / world,
+                   "whole_swap_frac_of_bf16_sustained": value * FLOP_PER_IMAGE / 1e12 / world / peaks["tf_sustained"]},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(2 * c_pin.numel() * 4),
+                "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)",
+                     "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "launches_per_step": tc["launches"] // max(prof_steps, 1),
+                     "share_of_step": kernels.get("conv_tc", {}).get("share")},
+        "kernels": kernels,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, secs = cpu_baseline_sample(threads)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "1 pair @512^2 (2.143 TFLOP), one run of %.1f s after no warm-up" % secs}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

@@ -19,13 +19,13 @@ struct ReducePlan {
 };
 
 static ReducePlan plan_reduce(int64_t n, int64_t c, int64_t hw, int channels_last) {
-  // aim for >= 4 blocks per SM, but never chunks shorter than 1024 pixels
-  const int64_t units = channels_last ? n : n * c;
-  int64_t chunks = (148LL * 4 + units - 1) / units;
-  const int64_t max_chunks = (hw + 255) / 256;
-  if (chunks > max_chunks) chunks = max_chunks;
+  // The split depends ONLY on (hw, layout), never on the batch size: a sample's statistics are then bit-identical
+  // whether it is reduced alone or inside a larger batch (the pair-partitioning over GPUs relies on this).
+  (void)n; (void)c;
+  int64_t chunks = channels_last ? hw / 1024 : hw / 16384;
+  const int64_t cap = channels_last ? 128 : 32;
+  if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
-  if (chunks > 1024) chunks = 1024;
   ReducePlan p;
   p.chunk_len = (hw + chunks - 1) / chunks;
   p.chunk_len = (p.chunk_len + 63) / 64 * 64;          // keep chunk starts 16-byte aligned for all dtypes

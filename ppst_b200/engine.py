@@ -1,0 +1,400 @@
+"""Network-level executors for the PPST swap / inference path on the ppst_b200 kernels.
+
+The three networks consume the reference's state_dicts unchanged and are re-expressed
+as kernel sequences over NHWC activations:
+
+  conv (tcgen05 implicit GEMM, or the CUDA-core one)  ->  [per-(n,c) statistics, free in the conv epilogue]
+       ->  ppst_in_coeffs (InstanceNorm + StyleMod / bias collapse to ONE affine per (n,c))
+       ->  ppst_affine_apply (affine + activation + residual/skip + padding/upsampling of the NEXT conv's input)
+
+Two numeric modes:
+  "fp32": fp32 activations, exact two-pass statistics, CUDA-core convolutions  (tolerance: max-abs 1e-4/layer)
+  "bf16": bf16 activations/weights, fp32 accumulation on the tensor cores      (rel-L2 <= 1e-2/layer, PSNR >= 45 dB)
+
+Reference call sites are cited per method (paths relative to the reference repository root).
+"""
+import math
+
+import torch
+
+from . import ops, packing
+from ._lib import BF16, F32
+from .packing import SQRT2, make_spec, make_upscale_spec
+
+INV_SQRT2 = 1.0 / SQRT2
+HEAD_CH = [(256, 256), (256, 256), (256, 384), (384, 512)]      # generator.py:156-165
+UP_CH = [(16, 512, 512), (32, 512, 256), (64, 256, 128)]        # generator.py:167-175
+E_CH = [(32, 64), (64, 128), (128, 256)]                        # encoder_con.py:36-41 / encoder_col.py:31-36
+LEVELS = ["9", "0", "1", "2"]
+
+
+class Engine:
+    def __init__(self, sdE1, sdE2, sdG, device="cuda", mode="bf16"):
+        assert mode in ("bf16", "fp32")
+        self.device = torch.device(device)
+        self.mode = mode
+        self.adt = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.acode = BF16 if mode == "bf16" else F32
+        self.use_tc = mode == "bf16" and ops.conv_tc_available()
+        dev = self.device
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()   # noqa: E731
+        self.E1 = self._pack_encoder(sdE1, "DownToSpatialCode", norm=True)
+        self.E1["tsc0"] = make_spec(sdE1["ToSpatialCode.0.Conv.weight"], dev, scale=1 / math.sqrt(256))
+        self.E1["tsc0_actb"] = f32(sdE1["ToSpatialCode.0.Act.bias"])
+        self.E1["tsc1"] = make_spec(sdE1["ToSpatialCode.1.Conv.weight"], dev, scale=1 / math.sqrt(256),
+                                    bias=sdE1["ToSpatialCode.1.Conv.bias"])
+        self.E2 = self._pack_encoder(sdE2, "DownToGlobalCode1", norm=False)
+        for lvl in LEVELS:
+            w = sdE2["conv1x1_%s.weight" % lvl]
+            self.E2["c1x1_%s" % lvl] = (f32(w.reshape(w.shape[0], -1)), f32(sdE2["conv1x1_%s.bias" % lvl]))
+            self.E2["proj_%s" % lvl] = [(f32(sdE2["projector%s.%d.weight" % (lvl, j)]),
+                                         f32(sdE2["projector%s.%d.bias" % (lvl, j)])) for j in (1, 3, 5)]
+        self.G = self._pack_generator(sdG)
+
+    # ------------------------------------------------------------------------------------------ packing
+    def _pack_encoder(self, sd, down, norm):
+        """FromRGB + 3 ResBlocks (stylegan2_layers.py:497-579).  The 3x3 [1,2,1] blur of the two downsampling
+        branches is folded into their convolutions: conv2 becomes a 5x5 stride-2 conv over the reflect-padded
+        input, skip a 3x3 stride-2 conv with one row/col of zero padding on the top/left."""
+        dev = self.device
+        P = {"norm": norm}
+        P["from_rgb"] = make_spec(sd["FromRGB.Conv.weight"], dev, scale=1 / math.sqrt(3), bias=sd["FromRGB.Act.bias"],
+                                  act=True)
+        for i, (ci, co) in zip((1, 2, 4), E_CH):
+            p = "%s.ResBlockDownBy%d." % (down, i)
+            k = sd[p + "conv2.Blur.kernel"].to(torch.float32)
+            w1 = sd[p + "conv1.Conv.weight"]
+            w2 = packing.fold_fir(sd[p + "conv2.Conv.weight"].to(torch.float32) / math.sqrt(ci * 9), k)
+            ws = packing.fold_fir(sd[p + "skip.Conv.weight"].to(torch.float32) / math.sqrt(ci),
+                                  sd[p + "skip.Blur.kernel"].to(torch.float32))
+            b1, b2 = sd[p + "conv1.Act.bias"], sd[p + "conv2.Act.bias"]
+            blk = {}
+            # norm=True: IN sits between conv and activation, so bias+act move to the apply pass
+            blk["conv1"] = make_spec(w1, dev, scale=1 / math.sqrt(ci * 9), bias=None if norm else b1, act=not norm)
+            blk["conv2"] = make_spec(w2, dev, stride=2, off=(0, 0), bias=None if norm else b2, act=not norm,
+                                     out_hw=lambda h, w: ((h - 5) // 2 + 1, (w - 5) // 2 + 1))
+            blk["skip"] = make_spec(ws, dev, stride=2, off=(-1, -1),
+                                    out_hw=lambda h, w: ((h - 2) // 2 + 1, (w - 2) // 2 + 1))
+            blk["b1"] = b1.detach().to(dev, torch.float32).contiguous()
+            blk["b2"] = b2.detach().to(dev, torch.float32).contiguous()
+            P["res%d" % i] = blk
+        return P
+
+    def _pack_styled(self, sd, p, upsample_fused_ok=True):
+        """StyledConv (stylegan2_layers.py:439-475): all three additive per-channel terms (conv.bias, .bias,
+        activate.bias) are pre-summed; noise and leaky-ReLU*sqrt2 run in the conv epilogue."""
+        dev = self.device
+        bias = sd[p + "conv.bias"].float() + sd[p + "bias"].float().reshape(-1) + sd[p + "activate.bias"].float()
+        nw = float(sd[p + "noise.weight"].reshape(-1)[0])
+        d = {"plain": make_spec(sd[p + "conv.weight"], dev, bias=bias, act=True, pad=1, noise_w=nw),
+             "lin_w": sd[p + "epi1.style_mod.lin.weight"].detach().to(dev, torch.float32).contiguous(),
+             "lin_b": sd[p + "epi1.style_mod.lin.bias"].detach().to(dev, torch.float32).contiguous(),
+             "noise_w": nw}
+        return d
+
+    def _pack_generator(self, sd):
+        dev = self.device
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()   # noqa: E731
+        G = {}
+        for n in ("scale", "bias"):
+            G["scm_" + n] = (f32(sd["SpatialCodeModulation.%s.weight" % n]), f32(sd["SpatialCodeModulation.%s.bias" % n]))
+        for i, (ci, co) in enumerate(HEAD_CH):
+            p = "HeadResnetBlock%d." % i
+            blk = {"conv1": self._pack_styled(sd, p + "conv1."), "conv2": self._pack_styled(sd, p + "conv2.")}
+            if ci != co:
+                blk["skip"] = make_spec(sd[p + "skip.Conv.weight"], dev, scale=1 / math.sqrt(ci))
+            G["head%d" % i] = blk
+        for res, ci, co in UP_CH:
+            p = "UpsamplingResBlock%d." % res
+            c1 = self._pack_styled(sd, p + "conv1.")
+            c1["fused_up"] = make_upscale_spec(sd[p + "conv1.conv.weight"], dev, bias=c1["plain"].bias, act=True,
+                                               noise_w=c1["noise_w"])
+            blk = {"conv1": c1, "conv2": self._pack_styled(sd, p + "conv2.")}
+            if ci != co:
+                blk["skip"] = make_spec(sd[p + "skip.Conv.weight"], dev, scale=1 / math.sqrt(ci),
+                                        bias=sd[p + "skip.Act.bias"], act=True)
+            G["up%d" % res] = blk
+        G["rgb"] = make_spec(sd["ToRGB.conv.weight"], dev, scale=1 / math.sqrt(128),
+                             bias=sd["ToRGB.conv.bias"].float() + sd["ToRGB.bias"].float().reshape(-1), tc=False)
+        G["rgb_lin"] = (f32(sd["ToRGB.epi1.style_mod.lin.weight"]), f32(sd["ToRGB.epi1.style_mod.lin.bias"]))
+        for name, k in (("layer32", 3), ("layer64", 3), ("layer128", 3), ("layer256", 1)):
+            G[name] = {"k": k,
+                       "c1": make_spec(sd[name + ".2.weight"], dev, bias=sd[name + ".2.bias"]),
+                       "a1": float(sd[name + ".4.weight"].reshape(-1)[0]),
+                       "c2": make_spec(sd[name + ".6.weight"], dev, bias=sd[name + ".6.bias"]),
+                       "a2": float(sd[name + ".8.weight"].reshape(-1)[0])}
+        for name in ("layert.0", "layert.1", "layert.2", "layert1.0"):
+            G[name] = {"c1": make_spec(sd[name + ".conv1.weight"], dev, bias=sd[name + ".conv1.bias"]),
+                       "c2": make_spec(sd[name + ".conv2.weight"], dev, bias=sd[name + ".conv2.bias"]),
+                       "a": float(sd[name + ".prelu.weight"].reshape(-1)[0])}
+        G["layert1.1"] = make_spec(sd["layert1.1.weight"], dev, bias=sd["layert1.1.bias"])
+        return G
+
+    # ------------------------------------------------------------------------------------------ primitives
+    def conv(self, x, spec, noise=None, out=None, c_off=0, out_dtype=None, want_stats=False):
+        """x: dense NHWC.  Returns (y, stats) with stats = None | dict(partials...) for in_coeffs."""
+        n, h, w, cin = x.shape
+        assert cin == spec.cin, (cin, spec.cin)
+        oh, ow = spec.out_hw(h, w)
+        fh, fw = oh * spec.phases[0], ow * spec.phases[1]
+        odt = out_dtype or self.adt
+        if out is None:
+            out = torch.empty((n, fh, fw, spec.cout), device=x.device, dtype=odt)
+        tc = self.use_tc and spec.w16 is not None and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+        code_in = BF16 if x.dtype == torch.bfloat16 else F32
+        code_out = BF16 if out.dtype == torch.bfloat16 else F32
+        d = ops.conv_desc((n, h, w, cin), spec.cout, spec.kh, spec.kw, stride=spec.stride, off=spec.off,
+                          out_hw=(oh, ow), phases=spec.phases, phase_off=spec.phase_off, full_hw=(fh, fw),
+                          cout_stride=out.shape[3], c_off=c_off, act=spec.act, slope=0.2,
+                          gain=SQRT2 if spec.act else 1.0, noise_w=spec.noise_w if noise is not None else 0.0,
+                          in_dtype=code_in, out_dtype=code_out)
+        stats = None
+        if tc:
+            sbuf = None
+            if want_stats:
+                sbuf = torch.empty(ops.conv_tc_stats_elems(d), device=x.device, dtype=torch.float32)
+            ops.conv_tc(out, x, spec.w16, spec.bias, noise, sbuf, d)
+            if want_stats:
+                half = sbuf.numel() // 2
+                stats = {"sum": sbuf[:half], "sumsq": sbuf[half:], "n_partials": half // (n * spec.cout),
+                         "count": fh * fw}
+        else:
+            ops.conv_simt(out, x, spec.w32, spec.bias, noise, d)
+        return out, stats
+
+    def coeffs(self, y, stats=None, style=None, bias=None, c=None):
+        """InstanceNorm (biased var, eps 1e-5) of NHWC `y` (+ StyleMod style [n,2c], + per-channel bias)
+        -> (a, b) f32 [n, c]."""
+        n, h, w, cs = y.shape
+        c = c or cs
+        if stats is not None:
+            return ops.in_coeffs(n, c, stats["sum"], stats["sumsq"], count=stats["count"], style=style, bias=bias,
+                                 n_partials=stats["n_partials"])
+        if self.mode == "fp32" or y.dtype == torch.float32:
+            r1 = ops.plane_reduce(y, True, want=("sum",))
+            mean = (r1["sum"].view(n, c) / float(h * w)).contiguous()
+            r2 = ops.plane_reduce(y, True, shift=mean, want=("sum", "sumsq"))
+            return ops.in_coeffs(n, c, r2["sum"].view(n, c), r2["sumsq"].view(n, c), count=h * w, shift=mean,
+                                 style=style, bias=bias)
+        r = ops.plane_reduce(y, True, want=("sum", "sumsq"))
+        return ops.in_coeffs(n, c, r["sum"].view(n, c), r["sumsq"].view(n, c), count=h * w, style=style, bias=bias)
+
+    def apply(self, x, a=None, b=None, **kw):
+        return ops.affine_apply(x, x.shape[3], a, b, **kw)
+
+    def to_nhwc(self, x_nchw, dtype=None):
+        return ops.nchw_to_nhwc(x_nchw.to(self.device, torch.float32), dtype=dtype or self.adt)
+
+    # ------------------------------------------------------------------------------------------ encoders
+    def _res_block(self, blk, x, norm):
+        """ResBlock (stylegan2_layers.py:559-579) with reflection padding, on NHWC x."""
+        xp = self.apply(x, pad=(1, 1, 1, 1), pad_mode=1)
+        c1, st1 = self.conv(xp, blk["conv1"], want_stats=norm)
+        if norm:
+            a, b = self.coeffs(c1, st1, bias=blk["b1"])
+            h1p = self.apply(c1, a, b, pre_slope=0.2, pre_gain=SQRT2, pad=(2, 1, 2, 1), pad_mode=1)
+        else:
+            h1p = self.apply(c1, pad=(2, 1, 2, 1), pad_mode=1)
+        c2, st2 = self.conv(h1p, blk["conv2"], want_stats=norm)
+        cs, sts = self.conv(x, blk["skip"], want_stats=norm)
+        if norm:
+            a2, b2 = self.coeffs(c2, st2, bias=blk["b2"])
+            as_, bs = self.coeffs(cs, sts)
+            return self.apply(c2, a2, b2, pre_slope=0.2, pre_gain=SQRT2, res=cs, ra=as_, rb=bs, res_mode=1,
+                              post_gain=INV_SQRT2)
+        return self.apply(c2, res=cs, res_mode=1, post_gain=INV_SQRT2)
+
+    def encoder_con(self, x_nhwc, taps=None):
+        """E1: StyleGAN2ResnetEncodercon.forward (encoder_con.py:82-92).  x NHWC [n,h,w,3] -> sp NHWC [n,h/8,w/8,256]."""
+        P = self.E1
+        x, _ = self.conv(x_nhwc, P["from_rgb"])
+        if taps is not None:
+            taps["FromRGB"] = x
+        for i in (1, 2, 4):
+            x = self._res_block(P["res%d" % i], x, True)
+            if taps is not None:
+                taps["ResBlockDownBy%d" % i] = x
+        c, st = self.conv(x, P["tsc0"], want_stats=True)
+        a, b = self.coeffs(c, st, bias=P["tsc0_actb"])
+        h = self.apply(c, a, b, pre_slope=0.2, pre_gain=SQRT2)
+        c, st = self.conv(h, P["tsc1"], want_stats=True)
+        a, b = self.coeffs(c, st)
+        return self.apply(c, a, b)
+
+    def _code_head(self, lvl, gap_sum, gmax, hw):
+        """GAP || GMP -> conv1x1 -> projector MLP -> F.normalize (encoder_col.py:160-166)."""
+        v = torch.cat([gap_sum * (1.0 / hw), gmax], dim=1).contiguous()
+        w, b = self.E2["c1x1_%s" % lvl]
+        v = ops.linear(v, w, b)
+        for (pw, pb) in self.E2["proj_%s" % lvl]:
+            v = ops.linear(v, pw, pb, relu_in=True)
+        return ops.l2_normalize(v, 1e-12, 1)
+
+    def _pooled_head(self, lvl, x, labels=None, label_mode=0):
+        n, h, w, c = x.shape
+        if labels is None:
+            r = ops.plane_reduce(x, True, want=("sum", "max"))
+            return self._code_head(lvl, r["sum"].view(n, c), r["max"].view(n, c), h * w)
+        r = ops.plane_reduce(x, True, labels=labels, n_regions=3, label_mode=label_mode, want=("sum", "max"))
+        return [self._code_head(lvl, r["sum"][:, i].contiguous(), r["max"][:, i].contiguous(), h * w) for i in range(3)]
+
+    def _e2_warp(self, x, corr, resize, scale):
+        """StyleGAN2ResnetEncodercol.warp (encoder_col.py:100-138): pool to 64x64, corr @ feat, bilinear up."""
+        n, h, w, c = x.shape
+        if resize:
+            size = (int(64 * h / w), 64) if h > w else (64, int(64 * w / h))
+            pooled = ops.resample(x, size, 1, out_dtype=torch.float32)
+        else:
+            size = (h, w)
+            pooled = x if x.dtype == torch.float32 else self.apply(x, out_dtype=torch.float32)
+        wf = ops.gemm_f32(corr, pooled.view(n, size[0] * size[1], c), False)
+        wf = wf.view(n, -1, 64, c) if h > w else wf.view(n, 64, -1, c)
+        if resize and scale != 1:
+            wf = ops.resample(wf, (wf.shape[1] * scale, wf.shape[2] * scale), 0)
+        return wf
+
+    def encoder_col(self, x_nhwc, corr=None, labels=None, taps=None):
+        """E2: StyleGAN2ResnetEncodercol.forward (encoder_col.py:150-251).
+        corr: f32 [n,4096,4096] or None.  labels: uint8 [n,h,w] region map or None (training-path mask branch;
+        the reference takes the one-hot float mask -- see SwapModel.E2_forward for that signature).
+        Returns (vectors, vectors_w) or (vectors, projections_m, vectors_w, projections_mw)."""
+        P = self.E2
+        vectors, vectors_w, pm, pmw = [], [], [], []
+        x, _ = self.conv(x_nhwc, P["from_rgb"])
+        bits = bits_sw = None
+        for li, lvl in enumerate(LEVELS):
+            if li > 0:
+                x = self._res_block(P["res%d" % (2 ** (li - 1))], x, False)
+            if taps is not None:
+                taps["level" + lvl] = x
+            vectors.append(self._pooled_head(lvl, x))
+            xx = None
+            if corr is not None:
+                xx = self._e2_warp(x, corr, resize=(li < 3), scale=2 ** (3 - li))
+                vectors_w.append(self._pooled_head(lvl, xx))
+            if labels is not None:
+                bits = ops.labels_pool_or(labels, 1, 0) if li == 0 else ops.labels_pool_or(bits, 2, 1)
+                pm.extend(self._pooled_head(lvl, x, labels=bits, label_mode=1))
+                if corr is not None:
+                    n = bits.shape[0]
+                    perm = torch.arange(n, device=bits.device).view(n // 2, 2).flip(1).reshape(-1)
+                    bits_sw = bits[perm].contiguous()          # encoder_col.py:140-148 (swap adjacent pairs)
+                    pmw.extend(self._pooled_head(lvl, xx, labels=bits_sw, label_mode=1))
+        if labels is not None:
+            return vectors, pm, vectors_w, pmw
+        return vectors, vectors_w
+
+    # ------------------------------------------------------------------------------------------ generator
+    def _styled(self, P, x, style, noise, upsample=False):
+        """StyledConv.forward up to (and excluding) the application of IN+StyleMod: returns (y, a, b)."""
+        s = ops.linear(style, P["lin_w"], P["lin_b"], w_scale=P["lin_w"].shape[1] ** -0.5)
+        if upsample and min(x.shape[1:3]) * 2 >= 128:
+            y, st = self.conv(x, P["fused_up"], noise=noise, want_stats=True)
+        else:
+            if upsample:
+                x = self.apply(x, up=2)                              # Upscale2d nearest (stylegan2_layers.py:88-105)
+            y, st = self.conv(x, P["plain"], noise=noise, want_stats=True)
+        a, b = self.coeffs(y, st, style=s)
+        return y, a, b
+
+    def _feature_head(self, P, x):
+        """layer32/64/128/256 (generator.py:180-231): [ReplPad] -> IN (on the padded tensor) -> conv -> IN -> PReLU
+        -> [ReplPad] -> conv -> IN -> PReLU."""
+        pad = (1, 1, 1, 1) if P["k"] == 3 else (0, 0, 0, 0)
+        xp = self.apply(x, pad=pad, pad_mode=2) if P["k"] == 3 else x
+        a, b = self.coeffs(xp)
+        xn = self.apply(xp, a, b)
+        c1, st = self.conv(xn, P["c1"], want_stats=True)
+        a, b = self.coeffs(c1, st)
+        h = self.apply(c1, a, b, pre_slope=P["a1"], pad=pad, pad_mode=2)
+        c2, st = self.conv(h, P["c2"], want_stats=True)
+        a, b = self.coeffs(c2, st)
+        return c2, a, b, P["a2"]
+
+    def _residual_block(self, P, x):
+        """ResidualBlock (generator.py:10-32)."""
+        xp = self.apply(x, pad=(1, 1, 1, 1), pad_mode=2)
+        c1, st = self.conv(xp, P["c1"], want_stats=True)
+        a, b = self.coeffs(c1, st)
+        h = self.apply(c1, a, b, pre_slope=P["a"], pad=(1, 1, 1, 1), pad_mode=2)
+        c2, st = self.conv(h, P["c2"], want_stats=True)
+        a, b = self.coeffs(c2, st)
+        return self.apply(c2, a, b, res=x, res_mode=1, post_slope=P["a"])
+
+    def generator(self, sp, codes, extract_features=False, noises=None, taps=None):
+        """StyleGAN2ResnetGenerator.forward (generator.py:244-281).  sp NHWC [n,h,w,256] (engine dtype),
+        codes: 4 x f32 [n,2048].  Returns rgb NHWC f32 [n,8h,8w,3] (and fea NHWC [n,64,64,256], fea1 NHWC
+        [n,256,256,64] when extract_features)."""
+        G = self.G
+        noises = {k_: v.to(self.device, torch.float32).contiguous() for k_, v in (noises or {}).items()}
+        codes = [ops.l2_normalize(c.to(self.device, torch.float32), 1e-8, 0) for c in codes]   # util.normalize
+        g = codes[-1]
+        k = g.shape[1]
+        sc = ops.linear(g, *G["scm_scale"], w_scale=k ** -0.5)
+        sb = ops.linear(g, *G["scm_bias"], w_scale=k ** -0.5)
+        x = self.apply(sp, sc, sb)                                   # GeneratorModulation, generator.py:80-91
+        if taps is not None:
+            taps["SpatialCodeModulation"] = x
+        for i, (ci, co) in enumerate(HEAD_CH):
+            B = G["head%d" % i]
+            name = "HeadResnetBlock%d" % i
+            skip = self.conv(x, B["skip"])[0] if "skip" in B else x
+            y, a, b = self._styled(B["conv1"], x, g, noises.get(name + ".conv1"))
+            h = self.apply(y, a, b)
+            y, a, b = self._styled(B["conv2"], h, g, noises.get(name + ".conv2"))
+            x = self.apply(y, a, b, res=skip, res_mode=1, post_gain=INV_SQRT2)
+            if taps is not None:
+                taps[name] = x
+        feas = []
+        if extract_features:
+            pool_hw = (x.shape[1], x.shape[2])
+            feas.append(self._feature_head(G["layer32"], x))
+        for j, (res, ci, co) in enumerate(UP_CH):
+            B = G["up%d" % res]
+            name = "UpsamplingResBlock%d" % res
+            g = codes[-2 - j]
+            skip = self.conv(x, B["skip"])[0] if "skip" in B else x
+            y, a, b = self._styled(B["conv1"], x, g, noises.get(name + ".conv1"), upsample=True)
+            h = self.apply(y, a, b)
+            y, a, b = self._styled(B["conv2"], h, g, noises.get(name + ".conv2"))
+            x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2)     # bilinear x2 skip, generator.py:75
+            if taps is not None:
+                taps[name] = x
+            if extract_features:
+                feas.append(self._feature_head(G["layer%d" % (2 ** (j + 6))], x))
+        # ToRGB (stylegan2_layers.py:477-495); fp32 from here on (3-channel IN is sensitive)
+        n, h, w, _ = x.shape
+        yrgb, _ = self.conv(x, G["rgb"], out_dtype=torch.float32)
+        s = ops.linear(codes[0], *G["rgb_lin"], w_scale=k ** -0.5)
+        a, b = self.coeffs(yrgb, style=s)
+        rgb = self.apply(yrgb, a, b)
+        if not extract_features:
+            return rgb
+        # generator.py:272-280: concat pooled / bilinear-resampled heads, then layert / layert1
+        feat = torch.empty((n, pool_hw[0], pool_hw[1], 256), device=x.device, dtype=self.adt)
+        feat1 = torch.empty((n, 256, 256, 256), device=x.device, dtype=self.adt)
+        for i, (c2, a, b, slope) in enumerate(feas):
+            f = self.apply(c2, a, b, pre_slope=slope)
+            ops.resample(f, pool_hw, 1, out=feat, out_c_off=64 * i)       # nn.AdaptiveAvgPool2d((h, w))
+            ops.resample(f, (256, 256), 0, out=feat1, out_c_off=64 * i)
+        if taps is not None:
+            taps["feat_cat"], taps["feat1_cat"] = feat, feat1
+        for i in range(3):
+            feat = self._residual_block(G["layert.%d" % i], feat)
+        feat1 = self._residual_block(G["layert1.0"], feat1)
+        feat1, _ = self.conv(feat1, G["layert1.1"])
+        return rgb, feat, feat1
+
+    # ------------------------------------------------------------------------------------------ correlation
+    def rselfcorr_into(self, fea1, out, c_off):
+        """PPSTModel.Rselfcorr (ppst_model.py:330-339) written into a channel slice of `out`."""
+        return ops.rselfcorr(fea1, out=out, out_c_off=c_off)
+
+    def corrm(self, fea_rows, fea0_rows):
+        """PPSTModel.corrm (ppst_model.py:341-364).  fea_rows / fea0_rows: NHWC [n,64,64,512] (any float dtype).
+        corr[b, i, j] = softmax_j( <fea0[b,:,i], fea[b,:,j]> / 0.01 )  -> f32 [n, L0, L]."""
+        n = fea_rows.shape[0]
+        a = ops.corr_prepare(fea_rows, 256).view(n, -1, fea_rows.shape[3])
+        q = ops.corr_prepare(fea0_rows, 256).view(n, -1, fea0_rows.shape[3])
+        logits = ops.gemm_f32(q, a, True)
+        return ops.softmax_rows_(logits, 0.01)

@@ -1,0 +1,155 @@
+"""PPSTModel-compatible front end (models/ppst_model.py:264-268,288-315,330-387; models/base_model.py:114-123).
+
+`SwapModel` keeps the reference's inference entry points -- encode / encode2 / decode / extract_feat /
+extract_feat_from_image / Rselfcorr / corrm / warp -- with the reference's tensor conventions (NCHW float32 in
+and out) and its `model(*args, command="...")` dispatch, so the evaluators' call sequences run unchanged on
+top of it.  `swap()` is the same sequence kept on the device in NHWC end to end (the benchmarked path).
+"""
+import torch
+
+from . import ops
+from .engine import Engine
+
+
+def split_state_dict(sd):
+    """PPSTModel.state_dict() keys are prefixed E1. / E2. / G.."""
+    out = {"E1": {}, "E2": {}, "G": {}}
+    for k, v in sd.items():
+        head, _, rest = k.partition(".")
+        if head in out:
+            out[head][rest] = v
+    return out["E1"], out["E2"], out["G"]
+
+
+class SwapModel:
+    def __init__(self, sdE1, sdE2, sdG, device="cuda", mode="bf16"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ppst_b200.SwapModel needs a CUDA device (there is no CPU fallback)")
+        self.engine = Engine(sdE1, sdE2, sdG, device=device, mode=mode)
+        self.device = self.engine.device
+        self.noises = None            # optional dict '<block>.conv{1,2}' -> [B,1,H,W]; None = noise term skipped
+
+    @classmethod
+    def from_model_state_dict(cls, sd, **kw):
+        return cls(*split_state_dict(sd), **kw)
+
+    # -- BaseModel.forward(command=...) ---------------------------------------------------------------
+    def __call__(self, *args, command=None, **kwargs):
+        if command is None:
+            raise ValueError(command)
+        method = getattr(self, command)
+        assert callable(method), "[%s] is not a method of %s" % (command, type(self).__name__)
+        return method(*args, **kwargs)
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def _in(self, image):
+        return self.engine.to_nhwc(image)
+
+    @staticmethod
+    def _out(x_nhwc):
+        return ops.nhwc_to_nchw(x_nhwc, dtype=torch.float32)
+
+    # -- PPSTModel API ------------------------------------------------------------------------------------
+    def encode(self, image, extract_features=False, testtime=False):
+        """ppst_model.py:264-265 -> (sp [B,256,H/8,W/8], [4 x [B,2048]])."""
+        x = self._in(image)
+        sp = self.engine.encoder_con(x)
+        gl, _ = self.engine.encoder_col(x)
+        return self._out(sp), gl
+
+    def encode2(self, image, corrmatrix):
+        """ppst_model.py:267-268.  Accepts the tensor or the 1-element list that
+        evaluation/simple_swapping_evaluator.py:53 passes."""
+        if isinstance(corrmatrix, (list, tuple)):
+            corrmatrix = corrmatrix[0]
+        corr = corrmatrix.to(self.device, torch.float32).contiguous()
+        return self.engine.encoder_col(self._in(image), corr=corr)
+
+    def E2_forward(self, image, mask=None, corrmatrix=None):
+        """StyleGAN2ResnetEncodercol.forward signature (encoder_col.py:150): `mask` is the one-hot float mask
+        [B,3,H,W] of the training path; it is converted to the integer label map the kernels key on."""
+        labels = None
+        if mask is not None:
+            labels = mask.to(self.device).argmax(dim=1).to(torch.uint8).contiguous()
+        corr = None
+        if corrmatrix is not None:
+            if isinstance(corrmatrix, (list, tuple)):
+                corrmatrix = corrmatrix[0]
+            corr = corrmatrix.to(self.device, torch.float32).contiguous()
+        return self.engine.encoder_col(self._in(image), corr=corr, labels=labels)
+
+    def decode(self, spatial_code, global_code, target=None):
+        """ppst_model.py:288-306 with target=None (the guided-filter post-process is SURVEY 8(f) 'next')."""
+        if target is not None:
+            raise NotImplementedError("decode(target=...) post-processing (photo_gif.GIFSmoothing) is out of scope")
+        sp = self.engine.to_nhwc(spatial_code)
+        rgb = self.engine.generator(sp, global_code, noises=self.noises)
+        return self._out(rgb)
+
+    def extract_feat(self, spatial_code, global_code):
+        """ppst_model.py:308-309 -> (rgb, fea, fea1)."""
+        sp = self.engine.to_nhwc(spatial_code)
+        rgb, fea, fea1 = self.engine.generator(sp, global_code, extract_features=True, noises=self.noises)
+        return self._out(rgb), self._out(fea), self._out(fea1)
+
+    def extract_feat_from_image(self, img):
+        """ppst_model.py:311-315 -> (fea [B,256,64,64], fea1 [B,64,256,256])."""
+        x = self._in(img)
+        sp = self.engine.encoder_con(x)
+        gl, _ = self.engine.encoder_col(x)
+        _, fea, fea1 = self.engine.generator(sp, gl, extract_features=True, noises=self.noises)
+        return self._out(fea), self._out(fea1)
+
+    def Rselfcorr(self, fea):
+        """ppst_model.py:330-339: [B,64,256,256] -> [B,256,64,64]."""
+        x = ops.nchw_to_nhwc(fea.to(self.device, torch.float32))
+        return self._out(ops.rselfcorr(x))
+
+    def corrm(self, fea, fea0):
+        """ppst_model.py:341-364: ([B,512,64,64], [B,512,64,64]) -> [B,4096,4096]."""
+        a = ops.nchw_to_nhwc(fea.to(self.device, torch.float32))
+        q = ops.nchw_to_nhwc(fea0.to(self.device, torch.float32))
+        return self.engine.corrm(a, q)
+
+    def warp(self, fea, corr):
+        """ppst_model.py:366-387 (both the full-resolution and the s x s unfold branch)."""
+        fea = fea.to(self.device, torch.float32)
+        corr = corr.to(self.device, torch.float32).contiguous()
+        b, c, h, w = fea.shape
+        H = corr.shape[1]
+        x = ops.nchw_to_nhwc(fea)                                        # [b,h,w,c]
+        if H != h * w:
+            s = int(((h * w) / H) ** 0.5)
+            # unfold(s, stride=s): rows = (h/s * w/s) patches, features ordered (c, dy, dx)
+            pt = x.view(b, h // s, s, w // s, s, c).permute(0, 1, 3, 5, 2, 4).reshape(b, H, c * s * s).contiguous()
+            wf = ops.gemm_f32(corr, pt, False)
+            wf = wf.view(b, h // s, w // s, c, s, s).permute(0, 3, 1, 4, 2, 5).reshape(b, c, h, w)
+            return wf.contiguous()
+        wf = ops.gemm_f32(corr, x.view(b, h * w, c), False).view(b, h, w, c)
+        return self._out(wf)
+
+    # -- the fused device-resident swap -------------------------------------------------------------------
+    def swap(self, content, style, alpha=1.0, return_nhwc=False):
+        """One (content, style) -> swapped image per batch row: the minimal unit of SURVEY.md 8(d) C2
+        {E1(c), E2(c), G.extract(c), E1(s), E2(s), G.extract(s), Rselfcorr x2, corrm, E2(s,corr), G.decode},
+        i.e. evaluation/simple_swapping_evaluator.py:44-59 without the duplicated content encode."""
+        e = self.engine
+        xc, xs = self._in(content), self._in(style)
+        n = xc.shape[0]
+        sp_c = e.encoder_con(xc)
+        gl_c, _ = e.encoder_col(xc)
+        _, fea_c, fea_c1 = e.generator(sp_c, gl_c, extract_features=True, noises=self.noises)
+        sp_s = e.encoder_con(xs)
+        gl_s, _ = e.encoder_col(xs)
+        _, fea_s, fea_s1 = e.generator(sp_s, gl_s, extract_features=True, noises=self.noises)
+        fc = torch.empty((n, 64, 64, 512), device=self.device, dtype=torch.float32)
+        fs = torch.empty_like(fc)
+        ops.affine_apply(fea_c, 256, out=fc, out_c_off=0)
+        ops.affine_apply(fea_s, 256, out=fs, out_c_off=0)
+        ops.rselfcorr(fea_c1, out=fc, out_c_off=256)
+        ops.rselfcorr(fea_s1, out=fs, out_c_off=256)
+        corr = e.corrm(fs, fc)
+        _, gl_w = e.encoder_col(xs, corr=corr)
+        codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
+        rgb = e.generator(sp_c, codes, noises=self.noises)
+        return rgb if return_nhwc else self._out(rgb)

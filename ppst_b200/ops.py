@@ -16,6 +16,43 @@ def _L():
     return _lib.load()
 
 
+# Optional per-launch timing (bench.py's roofline leg): PROFILE = {} enables it; every wrapped launch is bracketed
+# by CUDA events on the launching stream and filed under its kernel name with its algorithmic work
+# (FLOPs for GEMM-shaped kernels, bytes for HBM-bound ones).
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault(self.name, []).append((self.work, self.e0, self.e1))
+        return False
+
+
+def profile_summary():
+    """name -> dict(launches, work, ms) after a torch.cuda.synchronize()."""
+    out = {}
+    for name, recs in (PROFILE or {}).items():
+        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in recs)
+        out[name] = {"launches": len(recs), "work": float(sum(w for w, _, _ in recs)), "ms": ms}
+    return out
+
+
+def _conv_flops(d):
+    return 2.0 * d.n * d.out_h * d.out_w * d.phases_y * d.phases_x * d.cout * d.kh * d.kw * d.cin
+
+
 # ----------------------------------------------------------------------------------------------- layout
 def nchw_to_nhwc(x, dtype=None, out=None, c_off=0):
     """[n,c,h,w] -> NHWC [n,h,w,C]; writes channel slice [c_off, c_off+c) of `out` if given."""
@@ -65,9 +102,10 @@ def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift
     outs = {k: torch.empty((n, n_regions, c), device=x.device, dtype=torch.float32) for k in want}
     if labels is not None:
         assert labels.dtype == torch.uint8 and labels.is_contiguous() and labels.numel() == n * hw
-    check(L.ppst_plane_reduce(ptr(outs.get("sum")), ptr(outs.get("sumsq")), ptr(outs.get("max")), ptr(x), ptr(labels),
-                              ptr(shift), ptr(scratch), n, c, hw, n_regions, label_mode, 1 if channels_last else 0,
-                              dt(x), stream()))
+    with _Prof("plane_reduce", x.numel() * x.element_size()):
+        check(L.ppst_plane_reduce(ptr(outs.get("sum")), ptr(outs.get("sumsq")), ptr(outs.get("max")), ptr(x),
+                                  ptr(labels), ptr(shift), ptr(scratch), n, c, hw, n_regions, label_mode,
+                                  1 if channels_last else 0, dt(x), stream()))
     return outs
 
 
@@ -112,7 +150,8 @@ def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(
 
 def conv_simt(out, x, weight_f32, bias, noise, d):
     require_cuda(out, x, weight_f32, bias, noise)
-    check(_L().ppst_conv_simt(ptr(out), ptr(x), ptr(weight_f32), ptr(bias), ptr(noise), ctypes.byref(d), stream()))
+    with _Prof("conv_simt", _conv_flops(d)):
+        check(_L().ppst_conv_simt(ptr(out), ptr(x), ptr(weight_f32), ptr(bias), ptr(noise), ctypes.byref(d), stream()))
     return out
 
 
@@ -122,8 +161,9 @@ def conv_tc_stats_elems(d):
 
 def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
     require_cuda(out, x, weight_bf16, bias, noise, stats)
-    check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
-                            stream()))
+    with _Prof("conv_tc", _conv_flops(d)):
+        check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
+                                stream()))
     return out
 
 
@@ -161,7 +201,12 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
     d.x_dtype, d.out_dtype = dt(x), dt(out)
     d.res_dtype = dt(res) if res is not None else dt(x)
     d.out_c_stride, d.out_c_off = out.shape[3], out_c_off
-    check(_L().ppst_affine_apply(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d), stream()))
+    nbytes = x.numel() * x.element_size() + n * oh * ow * c * out.element_size()
+    if res is not None:
+        nbytes += (res.numel() if res_mode == 1 else n * oh * ow * c) * res.element_size()
+    with _Prof("affine_apply", nbytes):
+        check(_L().ppst_affine_apply(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d),
+                                     stream()))
     return out
 
 
@@ -171,8 +216,9 @@ def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0):
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty((n, out_hw[0], out_hw[1], c), device=x.device, dtype=out_dtype or x.dtype)
-    check(_L().ppst_resample(ptr(out), ptr(x), n, h, w, out_hw[0], out_hw[1], c, out.shape[3], out_c_off, mode,
-                             dt(x), dt(out), stream()))
+    with _Prof("resample", x.numel() * x.element_size() + n * out_hw[0] * out_hw[1] * c * out.element_size()):
+        check(_L().ppst_resample(ptr(out), ptr(x), n, h, w, out_hw[0], out_hw[1], c, out.shape[3], out_c_off, mode,
+                                 dt(x), dt(out), stream()))
     return out
 
 
@@ -213,8 +259,9 @@ def gemm_f32(a, b, trans_b, alpha=1.0, out=None):
     if out is None:
         out = torch.empty((bt, m, n), device=a.device, dtype=torch.float32)
     ldb = b.shape[2]
-    check(_L().ppst_gemm_f32(ptr(out), ptr(a), ptr(b), bt, m, n, k, k, ldb, n, m * k, b.shape[1] * b.shape[2], m * n,
-                             1 if trans_b else 0, float(alpha), stream()))
+    with _Prof("gemm_f32", 2.0 * bt * m * n * k):
+        check(_L().ppst_gemm_f32(ptr(out), ptr(a), ptr(b), bt, m, n, k, k, ldb, n, m * k, b.shape[1] * b.shape[2],
+                                 m * n, 1 if trans_b else 0, float(alpha), stream()))
     return out
 
 

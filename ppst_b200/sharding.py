@@ -1,0 +1,70 @@
+"""Batch partitioning of independent (content, style) pairs across the GPUs of one box.
+
+The inference path has NO data-path collective: every pair is independent, InstanceNorm is per
+sample, weights are replicated.  One process per GPU; torch.distributed is used only for the rendezvous, the
+barriers around the timed region and the max-over-ranks reduction of the elapsed time.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_world():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def partition(n_items, world, rank):
+    """Contiguous, balanced split of `n_items` work items: rank r gets items [lo, hi).  The first (n % world) ranks get
+    one extra item; every item is owned by exactly one rank."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad world/rank %d/%d" % (rank, world))
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+def init(backend=None):
+    """Join the process group described by the torchrun environment (no-op for a single process)."""
+    world, rank, local_rank = env_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return world, rank, local_rank
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value, device="cpu"):
+    """The step time of a multi-GPU job is the slowest rank's."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device="cpu"):
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def swap_sharded(model, contents, styles, alpha=1.0):
+    """Run this rank's share of the pair list.  contents/styles: [P,3,H,W] host or device tensors holding ALL pairs;
+    returns (lo, hi, images[lo:hi])."""
+    world, rank, _ = env_world()
+    lo, hi = partition(contents.shape[0], world, rank)
+    if hi == lo:
+        return lo, hi, None
+    out = model.swap(contents[lo:hi], styles[lo:hi], alpha=alpha)
+    return lo, hi, out

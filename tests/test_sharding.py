@@ -1,0 +1,80 @@
+"""Host-side logic of the multi-GPU path on CPU: pair partitioning and the gloo (world_size 2) barrier /
+max-over-ranks plumbing that bench.py uses.  No kernels run here."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ppst_b200 import sharding
+
+
+def test_partition_covers_every_pair_once():
+    for n in (0, 1, 7, 8, 64, 65, 256):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            sizes = []
+            for r in range(world):
+                lo, hi = sharding.partition(n, world, r)
+                assert 0 <= lo <= hi <= n
+                seen.extend(range(lo, hi))
+                sizes.append(hi - lo)
+            assert seen == list(range(n))
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.partition(64, 8, 3) == (24, 32)           # BASELINE configs[1]: 64 pairs, 8 per GPU
+    assert sharding.partition(256, 8, 7) == (224, 256)        # configs[2]: 16 x 16 grid cells, 32 per GPU
+    with pytest.raises(ValueError):
+        sharding.partition(8, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    w, r, lr = sharding.init(backend="gloo")
+    assert (w, r) == (world, rank) and dist.get_backend() == "gloo"
+    sharding.barrier()
+    slow = sharding.max_over_ranks(10.0 + 5.0 * rank)          # step time = slowest rank
+    total = sharding.sum_over_ranks(8)                          # pairs processed by the whole job
+
+    class FakeModel:                                            # stands in for SwapModel on a CPU-only host
+        def swap(self, c, s, alpha=1.0):
+            return c * 2 + s
+
+    contents = torch.arange(6, dtype=torch.float32).view(6, 1, 1, 1)
+    styles = torch.ones(6, 1, 1, 1)
+    lo, hi, out = sharding.swap_sharded(FakeModel(), contents, styles)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, out.flatten().tolist()))
+    sharding.barrier()
+    dist.destroy_process_group()
+    q.put((rank, slow, total, gathered))
+
+
+def test_two_rank_gloo_plumbing():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, slow, total, gathered in results:
+        assert slow == 15.0 and total == 16.0
+        rows = sorted(gathered)
+        assert [(lo, hi) for lo, hi, _ in rows] == [(0, 3), (3, 6)]
+        merged = [v for _, _, vals in rows for v in vals]
+        assert merged == [2 * i + 1 for i in range(6)]          # identical to the single-process result
