@@ -163,6 +163,18 @@ PPST_API int ppst_conv_simt(void* out, const void* in, const float* weight, cons
 PPST_API int64_t ppst_conv_tc_stats_elems(const ppst_conv_desc* d);
 PPST_API int ppst_conv_tc(void* out, const void* in, const void* weight, const float* bias, const float* noise,
                  float* stats, const ppst_conv_desc* d, void* stream);
+/* Thin 1x1 convolutions that are HBM streams rather than GEMMs.
+ * ppst_conv1x1_in_nchw : FromRGB = ConvLayer(3, 32, 1) + FusedLeakyReLU (stylegan2_layers.py:497-555;
+ *   encoder_con.py:26, encoder_col.py:27).  x is the NCHW f32 image [n, cin<=4, hw] (the layout conversion is fused),
+ *   out NHWC [n, hw, cout_stride] slice [c_off, c_off+cout); w f32 [cout][cin]; v = lrelu(x.w + bias) * gain.
+ * ppst_conv1x1_thin_out: ToRGB's EqualConv2d(128, 3, 1) (stylegan2_layers.py:484): x NHWC [pixels, cin],
+ *   out f32 [pixels, cout], w f32 [cout][cin]. */
+PPST_API int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, const float* bias, int64_t n, int cin,
+                         int64_t hw, int cout, int cout_stride, int c_off, int has_act, float slope, float gain,
+                         int out_dtype, void* stream);
+PPST_API int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, const float* bias, int64_t pixels, int cin,
+                          int cout, int in_dtype, void* stream);
+
 /* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
 PPST_API int ppst_conv_tc_available(void);
 
@@ -173,12 +185,13 @@ PPST_API int ppst_conv_tc_available(void);
  *   mean = sum/count (+ shift), var = sumsq/count - (sum/count)^2  (biased, nn.InstanceNorm2d), rstd = rsqrt(var+eps)
  *   a = rstd * (1 + style[n, c]) ; b = -mean * a + style[n, C + c] + bias[c]
  * i.e. InstanceNorm followed by StyleMod `x * (s + 1) + b` (stylegan2_layers.py:361-374) and/or a
- * per-channel bias (FusedLeakyReLU bias after IN in ConvLayer, :527-531).  style (f32 [n, 2c]) / bias /
+ * per-channel bias (FusedLeakyReLU bias after IN in ConvLayer, :527-531).  style (f32, row n = [scale(c) | shift(c)],
+ * row stride style_ld elements, 0 = 2c: all style vectors of a generator pass come out of ONE batched linear) / bias /
  * shift may be NULL.  If use_norm == 0: a = 1 + style, b = style_shift + bias.
  * partials: if n_partials > 0, sum/sumsq are [n][n_partials][c] tile partials (from ppst_conv_tc) and are
  * reduced here in a fixed order. */
 PPST_API int ppst_in_coeffs(float* a, float* b, const float* sum, const float* sumsq, const float* shift,
-                   const float* style, const float* bias, int64_t n, int64_t c, int64_t n_partials,
+                   const float* style, int64_t style_ld, const float* bias, int64_t n, int64_t c, int64_t n_partials,
                    double count, float eps, int use_norm, void* stream);
 
 typedef struct {

@@ -52,7 +52,10 @@ _SIGS = {
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_available": (c_int, []),
-    "ppst_in_coeffs": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
+    "ppst_conv1x1_in_nchw": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_float, c_float,
+                                                     c_int, c_void_p]),
+    "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),
+    "ppst_in_coeffs": (c_int, [c_void_p] * 6 + [c_i64, c_void_p, c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),
     "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p]),
     "ppst_linear": (c_int, [c_void_p] * 4 + [c_i64] * 4 + [c_float, c_float, c_int, c_void_p]),

@@ -1,0 +1,143 @@
+// Thin 1x1 convolutions that are pure HBM streams, not GEMMs:
+//   FromRGB  (ConvLayer 3 -> 32, 1x1 + FusedLeakyReLU, stylegan2_layers.py:497-555; encoder_con.py:26, encoder_col.py:27):
+//            reads the NCHW fp32 image planes directly (fusing the NCHW->NHWC conversion) and writes NHWC.
+//   ToRGB    (EqualConv2d 128 -> 3, 1x1, stylegan2_layers.py:484): a per-pixel dot product over the channel vector.
+#include "common.cuh"
+
+namespace ppst {
+
+// out NHWC [n, hw, cout_stride] (slice c_off..c_off+COUT), x NCHW f32 [n, cin, hw]; one thread per pixel.
+template <typename TO, int COUT>
+__global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ out, const float* __restrict__ x,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              int64_t n, int cin, int64_t hw, int cout_stride, int c_off,
+                                                              int has_act, float slope, float gain) {
+  __shared__ float sw[COUT * 4];
+  __shared__ float sb[COUT];
+  for (int i = threadIdx.x; i < COUT * cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
+  __syncthreads();
+  const int64_t total = n * hw;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ni = p / hw, pix = p - ni * hw;
+    float xin[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ci = 0; ci < cin; ++ci) xin[ci] = x[(ni * cin + ci) * hw + pix];
+    TO* o = out + p * cout_stride + c_off;
+#pragma unroll
+    for (int g = 0; g < COUT / 8; ++g) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int co = g * 8 + e;
+        float acc = sb[co];
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(xin[ci], sw[co * cin + ci], acc);
+        if (has_act) acc = (acc > 0.f) ? acc : acc * slope;
+        v[e] = acc * gain;
+      }
+      if (sizeof(TO) == 2) {
+        Vec16<TO> r;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r.v[e] = Cvt<TO>::from_f(v[e]);
+        st_vec16(o + g * 8, r);
+      } else {
+        float* of = reinterpret_cast<float*>(o) + g * 8;
+        *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+}
+
+// out f32 [pixels, COUT], x NHWC [pixels, cin] with cin = 8 * L, L lanes per pixel (L divides 32).
+template <typename TI, int COUT>
+__global__ void __launch_bounds__(256) conv1x1_thin_out_kernel(float* __restrict__ out, const TI* __restrict__ x,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               int64_t pixels, int cin) {
+  const int L = cin / 8;                         // lanes cooperating on one pixel
+  const int lane = threadIdx.x & 31;
+  const int cg = lane % L, sub = lane / L;
+  const int per_warp = 32 / L;
+  float wr[COUT][8];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wr[co][e] = w[co * cin + cg * 8 + e];
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p0 = warp * per_warp; p0 < pixels; p0 += nwarps * per_warp) {
+    const int64_t p = p0 + sub;
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+    if (p < pixels) {
+      float xv[8];
+      if (sizeof(TI) == 2) {
+        Vec16<TI> r = ld_vec16_stream(x + p * cin + cg * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xv[e] = Cvt<TI>::to_f(r.v[e]);
+      } else {
+        const float* xf = reinterpret_cast<const float*>(x) + p * cin + cg * 8;
+        const float4 f0 = *reinterpret_cast<const float4*>(xf), f1 = *reinterpret_cast<const float4*>(xf + 4);
+        xv[0] = f0.x; xv[1] = f0.y; xv[2] = f0.z; xv[3] = f0.w; xv[4] = f1.x; xv[5] = f1.y; xv[6] = f1.z; xv[7] = f1.w;
+      }
+#pragma unroll
+      for (int co = 0; co < COUT; ++co)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[co] = fmaf(xv[e], wr[co][e], acc[co]);
+    }
+    for (int o = L >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    if (cg == 0 && p < pixels) {
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) out[p * COUT + co] = acc[co] + (bias ? bias[co] : 0.f);
+    }
+  }
+}
+
+}  // namespace ppst
+
+extern "C" int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, const float* bias, int64_t n, int cin,
+                                    int64_t hw, int cout, int cout_stride, int c_off, int has_act, float slope,
+                                    float gain, int out_dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && w && n > 0 && hw > 0 && cin >= 1 && cin <= 4, PPST_ERR_ARG, "conv1x1_in_nchw: bad args");
+  PPST_REQUIRE(cout == 32, PPST_ERR_UNSUPPORTED, "conv1x1_in_nchw: cout=%d (32 supported: FromRGB)", cout);
+  PPST_REQUIRE(c_off % 8 == 0 && cout_stride % 8 == 0 && c_off + cout <= cout_stride, PPST_ERR_ARG,
+               "conv1x1_in_nchw: channel slice");
+  const int64_t total = n * hw;
+  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == PPST_BF16)
+    conv1x1_in_nchw_kernel<__nv_bfloat16, 32><<<blocks, 256, 0, st>>>((__nv_bfloat16*)out, x, w, bias, n, cin, hw,
+                                                                      cout_stride, c_off, has_act, slope, gain);
+  else if (out_dtype == PPST_F32)
+    conv1x1_in_nchw_kernel<float, 32><<<blocks, 256, 0, st>>>((float*)out, x, w, bias, n, cin, hw, cout_stride, c_off,
+                                                              has_act, slope, gain);
+  else
+    PPST_REQUIRE(false, PPST_ERR_DTYPE, "conv1x1_in_nchw: out dtype %d", out_dtype);
+  PPST_LAUNCH_CHECK("conv1x1_in_nchw_kernel");
+  return 0;
+}
+
+extern "C" int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, const float* bias, int64_t pixels,
+                                     int cin, int cout, int in_dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && w && pixels > 0, PPST_ERR_ARG, "conv1x1_thin_out: bad args");
+  PPST_REQUIRE(cout == 3, PPST_ERR_UNSUPPORTED, "conv1x1_thin_out: cout=%d (3 supported: ToRGB)", cout);
+  const int L = cin / 8;
+  PPST_REQUIRE(cin % 8 == 0 && L >= 1 && L <= 32 && (32 % L) == 0, PPST_ERR_UNSUPPORTED,
+               "conv1x1_thin_out: cin=%d must be 8*L with L dividing 32", cin);
+  const int per_warp = 32 / L;
+  const int64_t warps = (pixels + per_warp - 1) / per_warp;
+  const int blocks = (int)((warps + 7) / 8 < 148 * 8 ? (warps + 7) / 8 : 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == PPST_BF16)
+    conv1x1_thin_out_kernel<__nv_bfloat16, 3><<<blocks, 256, 0, st>>>(out, (const __nv_bfloat16*)x, w, bias, pixels, cin);
+  else if (in_dtype == PPST_F32)
+    conv1x1_thin_out_kernel<float, 3><<<blocks, 256, 0, st>>>(out, (const float*)x, w, bias, pixels, cin);
+  else
+    PPST_REQUIRE(false, PPST_ERR_DTYPE, "conv1x1_thin_out: in dtype %d", in_dtype);
+  PPST_LAUNCH_CHECK("conv1x1_thin_out_kernel");
+  return 0;
+}

@@ -12,25 +12,11 @@
 
 namespace ppst {
 
-__global__ void in_coeffs_kernel(float* __restrict__ a, float* __restrict__ b, const float* __restrict__ sum,
-                                 const float* __restrict__ sumsq, const float* __restrict__ shift,
-                                 const float* __restrict__ style, const float* __restrict__ bias, int64_t n, int64_t c,
-                                 int64_t n_partials, double count, float eps, int use_norm) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * c) return;
-  const int64_t ni = t / c, ch = t % c;
+__device__ __forceinline__ void coeffs_finish(float* a, float* b, double s, double q, int64_t t, int64_t ni, int64_t ch,
+                                              int64_t c, const float* shift, const float* style, int64_t style_ld,
+                                              const float* bias, double count, float eps, int use_norm) {
   double scale = 1.0, off = 0.0;
   if (use_norm) {
-    double s = 0.0, q = 0.0;
-    if (n_partials > 0) {
-      for (int64_t p = 0; p < n_partials; ++p) {          // fixed order -> deterministic
-        s += (double)sum[(ni * n_partials + p) * c + ch];
-        q += (double)sumsq[(ni * n_partials + p) * c + ch];
-      }
-    } else {
-      s = sum[t];
-      q = sumsq[t];
-    }
     const double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -40,13 +26,52 @@ __global__ void in_coeffs_kernel(float* __restrict__ a, float* __restrict__ b, c
     off = -mean * rstd;
   }
   if (style) {
-    const double s1 = 1.0 + (double)style[ni * 2 * c + ch];
+    const double s1 = 1.0 + (double)style[ni * style_ld + ch];
     scale *= s1;
-    off = off * s1 + (double)style[ni * 2 * c + c + ch];
+    off = off * s1 + (double)style[ni * style_ld + c + ch];
   }
   if (bias) off += (double)bias[ch];
   a[t] = (float)scale;
   b[t] = (float)off;
+}
+
+__global__ void in_coeffs_kernel(float* __restrict__ a, float* __restrict__ b, const float* __restrict__ sum,
+                                 const float* __restrict__ sumsq, const float* __restrict__ shift,
+                                 const float* __restrict__ style, int64_t style_ld, const float* __restrict__ bias,
+                                 int64_t n, int64_t c, double count, float eps, int use_norm) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  coeffs_finish(a, b, use_norm ? (double)sum[t] : 0.0, use_norm ? (double)sumsq[t] : 0.0, t, t / c, t % c, c, shift,
+                style, style_ld, bias, count, eps, use_norm);
+}
+
+// Tile partials [n][P][c] (from the conv epilogue) -> coefficients.  Block = 32 channels x 32 partial lanes; every
+// lane accumulates a fixed arithmetic progression of partials in double and the 32 lane sums are combined in a
+// fixed order: deterministic, and P = 2048 partials cost 64 dependent steps instead of 2048.
+__global__ void __launch_bounds__(1024) in_coeffs_partials_kernel(
+    float* __restrict__ a, float* __restrict__ b, const float* __restrict__ sum, const float* __restrict__ sumsq,
+    const float* __restrict__ shift, const float* __restrict__ style, int64_t style_ld,
+    const float* __restrict__ bias, int64_t n, int64_t c, int64_t n_partials, double count, float eps) {
+  __shared__ double ss[32][33], sq[32][33];
+  const int64_t ni = blockIdx.y;
+  const int64_t ch = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0, q = 0.0;
+  if (ch < c) {
+    const float* ps = sum + ni * n_partials * c + ch;
+    const float* pq = sumsq + ni * n_partials * c + ch;
+    for (int64_t p = threadIdx.y; p < n_partials; p += 32) {
+      s += (double)ps[p * c];
+      q += (double)pq[p * c];
+    }
+  }
+  ss[threadIdx.y][threadIdx.x] = s;
+  sq[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && ch < c) {
+    s = 0.0; q = 0.0;
+    for (int l = 0; l < 32; ++l) { s += ss[l][threadIdx.x]; q += sq[l][threadIdx.x]; }
+    coeffs_finish(a, b, s, q, ni * c + ch, ni, ch, c, shift, style, style_ld, bias, count, eps, 1);
+  }
 }
 
 __device__ __forceinline__ float lrelu_slope(float v, float slope) { return v >= 0.0f ? v : v * slope; }
@@ -179,6 +204,85 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(TO* __restrict__ out,
   }
 }
 
+// Row-oriented variant for c % 8 == 0 (the hot path): one block per output row of one image; a thread owns ONE group of
+// 8 channels (its a/b coefficients stay in registers) and walks along the row, so the per-element work is one 16-byte
+// load, 8 FMAs and one 16-byte store with no integer division and no coefficient reloads.
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(256) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
+                                                                const float* __restrict__ a, const float* __restrict__ b,
+                                                                const TX* __restrict__ res, const float* __restrict__ ra,
+                                                                const float* __restrict__ rb, ppst_apply_desc d) {
+  constexpr int V = 8;
+  const int cv = d.c / V;
+  const int lanes = 256 / cv;
+  const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
+  if (lane >= lanes) return;
+  const int oy = blockIdx.x, ni = blockIdx.y;
+  const int ch = cg * V;
+  const int hu = d.h * d.up, wu = d.w * d.up;
+  const int oh = hu + d.pad_t + d.pad_b, ow = wu + d.pad_l + d.pad_r;
+  float av[V], bv[V], rav[V], rbv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; rav[e] = 1.0f; rbv[e] = 0.0f; }
+  if (a) load_ch<float, V>(av, a + (int64_t)ni * d.c + ch);
+  if (b) load_ch<float, V>(bv, b + (int64_t)ni * d.c + ch);
+  if (ra) load_ch<float, V>(rav, ra + (int64_t)ni * d.c + ch);
+  if (rb) load_ch<float, V>(rbv, rb + (int64_t)ni * d.c + ch);
+  bool zero_row = false;
+  const int uy = map_pad(oy - d.pad_t, hu, d.pad_mode, zero_row);
+  const int iy = uy / d.up;
+  const TX* xrow = x + (((int64_t)ni * d.h + iy) * d.w) * d.c + ch;
+  TO* orow = out + (((int64_t)ni * oh + oy) * ow) * d.out_c_stride + d.out_c_off + ch;
+  const TX* r0 = nullptr;
+  const TX* r1 = nullptr;
+  Bilin2 by{0, 0, 1.f, 0.f};
+  const int lw = wu / 2;
+  if (d.res_mode == 1) {
+    r0 = res + (((int64_t)ni * hu + uy) * wu) * d.c + ch;
+  } else if (d.res_mode == 2) {
+    const int lh = hu / 2;
+    by = bilin_x2(uy, lh);
+    r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
+    r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
+  }
+#pragma unroll 2
+  for (int ox = lane; ox < ow; ox += lanes) {
+    bool zero = zero_row;
+    const int ux = map_pad(ox - d.pad_l, wu, d.pad_mode, zero);
+    float y[V];
+    if (zero) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = 0.0f;
+    } else {
+      float xv[V];
+      load_ch<TX, V>(xv, xrow + (int64_t)(ux / d.up) * d.c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
+      if (d.res_mode == 1) {
+        float rv[V];
+        load_ch<TX, V>(rv, r0 + (int64_t)ux * d.c);
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] += fmaf(rv[e], rav[e], rbv[e]);
+      } else if (d.res_mode == 2) {
+        const Bilin2 bx = bilin_x2(ux, lw);
+        float v00[V], v01[V], v10[V], v11[V];
+        load_ch<TX, V>(v00, r0 + (int64_t)bx.i0 * d.c);
+        load_ch<TX, V>(v01, r0 + (int64_t)bx.i1 * d.c);
+        load_ch<TX, V>(v10, r1 + (int64_t)bx.i0 * d.c);
+        load_ch<TX, V>(v11, r1 + (int64_t)bx.i1 * d.c);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float rv = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
+          y[e] += fmaf(rv, rav[e], rbv[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
+    }
+    store_ch<TO, V>(orow + (int64_t)ox * d.out_c_stride, y);
+  }
+}
+
 // mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows)
 template <typename TX, typename TO, int V>
 __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, const TX* __restrict__ x, int64_t n,
@@ -238,13 +342,21 @@ static int grid_for(int64_t total) {
 }  // namespace ppst
 
 extern "C" int ppst_in_coeffs(float* a, float* b, const float* sum, const float* sumsq, const float* shift,
-                              const float* style, const float* bias, int64_t n, int64_t c, int64_t n_partials,
-                              double count, float eps, int use_norm, void* stream) {
+                              const float* style, int64_t style_ld, const float* bias, int64_t n, int64_t c,
+                              int64_t n_partials, double count, float eps, int use_norm, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(a && b && n > 0 && c > 0, PPST_ERR_ARG, "in_coeffs: bad args");
   PPST_REQUIRE(!use_norm || (sum && sumsq && count > 0), PPST_ERR_ARG, "in_coeffs: statistics missing");
-  in_coeffs_kernel<<<ceil_div(n * c, 256), 256, 0, (cudaStream_t)stream>>>(a, b, sum, sumsq, shift, style, bias, n, c,
-                                                                          n_partials, count, eps, use_norm);
+  if (style_ld <= 0) style_ld = 2 * c;
+  if (use_norm && n_partials > 0) {
+    PPST_REQUIRE(n <= 65535, PPST_ERR_ARG, "in_coeffs: batch too large");
+    dim3 grid(ceil_div(c, 32), (unsigned)n), block(32, 32);
+    in_coeffs_partials_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(a, b, sum, sumsq, shift, style, style_ld, bias, n,
+                                                                        c, n_partials, count, eps);
+  } else {
+    in_coeffs_kernel<<<ceil_div(n * c, 256), 256, 0, (cudaStream_t)stream>>>(a, b, sum, sumsq, shift, style, style_ld, bias,
+                                                                            n, c, count, eps, use_norm);
+  }
   PPST_LAUNCH_CHECK("in_coeffs_kernel");
   return 0;
 }
@@ -272,9 +384,16 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
                         (vec ? d.c / 8 : d.c);
   const int grid = grid_for(total);
   cudaStream_t st = (cudaStream_t)stream;
+  const int oh_ = d.h * d.up + d.pad_t + d.pad_b;
+  const bool rows = vec && (d.c / 8) <= 256 && d.n <= 65535 &&
+                    ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ra) |
+                      reinterpret_cast<uintptr_t>(rb)) & 15) == 0;
 #define PPST_APPLY(TX, TO)                                                                                           \
   do {                                                                                                               \
-    if (vec)                                                                                                         \
+    if (rows)                                                                                                        \
+      affine_apply_rows_kernel<TX, TO><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, \
+                                                                       ra, rb, d);                                   \
+    else if (vec)                                                                                                    \
       affine_apply_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d); \
     else                                                                                                             \
       affine_apply_kernel<TX, TO, 1><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d); \

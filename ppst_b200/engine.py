@@ -128,6 +128,27 @@ class Engine:
                        "c2": make_spec(sd[name + ".conv2.weight"], dev, bias=sd[name + ".conv2.bias"]),
                        "a": float(sd[name + ".prelu.weight"].reshape(-1)[0])}
         G["layert1.1"] = make_spec(sd["layert1.1.weight"], dev, bias=sd["layert1.1.bias"])
+        # every style / modulation vector of a pass comes out of ONE batched linear per texture code
+        # (EqualLinear and EqualizedLinear(use_wscale) share the run-time scale in_dim**-0.5)
+        groups = {-1: [("scm_scale",) + G["scm_scale"], ("scm_bias",) + G["scm_bias"]], -2: [], -3: [], -4: [], 0: []}
+        for i in range(len(HEAD_CH)):
+            for c_ in ("conv1", "conv2"):
+                P = G["head%d" % i][c_]
+                groups[-1].append(("head%d.%s" % (i, c_), P["lin_w"], P["lin_b"]))
+        for j, (res, _, _) in enumerate(UP_CH):
+            for c_ in ("conv1", "conv2"):
+                P = G["up%d" % res][c_]
+                groups[-2 - j].append(("up%d.%s" % (res, c_), P["lin_w"], P["lin_b"]))
+        groups[0].append(("rgb",) + G["rgb_lin"])
+        G["style_groups"] = []
+        for idx, items in groups.items():
+            w = torch.cat([it[1] for it in items], 0).contiguous()
+            b = torch.cat([it[2] for it in items], 0).contiguous()
+            slices, o = [], 0
+            for it in items:
+                slices.append((it[0], o, it[1].shape[0]))
+                o += it[1].shape[0]
+            G["style_groups"].append((idx, w, b, slices))
         return G
 
     # ------------------------------------------------------------------------------------------ primitives
@@ -185,6 +206,12 @@ class Engine:
     def to_nhwc(self, x_nchw, dtype=None):
         return ops.nchw_to_nhwc(x_nchw.to(self.device, torch.float32), dtype=dtype or self.adt)
 
+    def from_rgb(self, P, image_nchw):
+        """FromRGB = ConvLayer(3, 32, 1) + FusedLeakyReLU straight from the NCHW fp32 image (layout change fused)."""
+        spec = P["from_rgb"]
+        x = image_nchw.to(self.device, torch.float32)
+        return ops.conv1x1_in_nchw(x, spec.w32[0], spec.bias, True, self.adt)
+
     # ------------------------------------------------------------------------------------------ encoders
     def _res_block(self, blk, x, norm):
         """ResBlock (stylegan2_layers.py:559-579) with reflection padding, on NHWC x."""
@@ -204,10 +231,10 @@ class Engine:
                               post_gain=INV_SQRT2)
         return self.apply(c2, res=cs, res_mode=1, post_gain=INV_SQRT2)
 
-    def encoder_con(self, x_nhwc, taps=None):
-        """E1: StyleGAN2ResnetEncodercon.forward (encoder_con.py:82-92).  x NHWC [n,h,w,3] -> sp NHWC [n,h/8,w/8,256]."""
+    def encoder_con(self, image_nchw, taps=None):
+        """E1: StyleGAN2ResnetEncodercon.forward (encoder_con.py:82-92).  NCHW f32 image -> sp NHWC [n,h/8,w/8,256]."""
         P = self.E1
-        x, _ = self.conv(x_nhwc, P["from_rgb"])
+        x = self.from_rgb(P, image_nchw)
         if taps is not None:
             taps["FromRGB"] = x
         for i in (1, 2, 4):
@@ -253,14 +280,14 @@ class Engine:
             wf = ops.resample(wf, (wf.shape[1] * scale, wf.shape[2] * scale), 0)
         return wf
 
-    def encoder_col(self, x_nhwc, corr=None, labels=None, taps=None):
+    def encoder_col(self, image_nchw, corr=None, labels=None, taps=None):
         """E2: StyleGAN2ResnetEncodercol.forward (encoder_col.py:150-251).
         corr: f32 [n,4096,4096] or None.  labels: uint8 [n,h,w] region map or None (training-path mask branch;
         the reference takes the one-hot float mask -- see SwapModel.E2_forward for that signature).
         Returns (vectors, vectors_w) or (vectors, projections_m, vectors_w, projections_mw)."""
         P = self.E2
         vectors, vectors_w, pm, pmw = [], [], [], []
-        x, _ = self.conv(x_nhwc, P["from_rgb"])
+        x = self.from_rgb(P, image_nchw)
         bits = bits_sw = None
         for li, lvl in enumerate(LEVELS):
             if li > 0:
@@ -285,9 +312,18 @@ class Engine:
         return vectors, vectors_w
 
     # ------------------------------------------------------------------------------------------ generator
-    def _styled(self, P, x, style, noise, upsample=False):
-        """StyledConv.forward up to (and excluding) the application of IN+StyleMod: returns (y, a, b)."""
-        s = ops.linear(style, P["lin_w"], P["lin_b"], w_scale=P["lin_w"].shape[1] ** -0.5)
+    def styles(self, codes):
+        """All StyleMod / SpatialCodeModulation vectors of one generator pass: one batched linear per code."""
+        out = {}
+        for idx, w, b, slices in self.G["style_groups"]:
+            y = ops.linear(codes[idx], w, b, w_scale=w.shape[1] ** -0.5)
+            for key, o, size in slices:
+                out[key] = y[:, o:o + size]
+        return out
+
+    def _styled(self, P, x, s, noise, upsample=False):
+        """StyledConv.forward up to (and excluding) the application of IN+StyleMod: returns (y, a, b).
+        s: the layer's style vector [n, 2c] (a row-strided view into the batched linear's output)."""
         if upsample and min(x.shape[1:3]) * 2 >= 128:
             y, st = self.conv(x, P["fused_up"], noise=noise, want_stats=True)
         else:
@@ -326,22 +362,19 @@ class Engine:
         codes: 4 x f32 [n,2048].  Returns rgb NHWC f32 [n,8h,8w,3] (and fea NHWC [n,64,64,256], fea1 NHWC
         [n,256,256,64] when extract_features)."""
         G = self.G
-        noises = {k_: v.to(self.device, torch.float32).contiguous() for k_, v in (noises or {}).items()}
+        noises = noises or {}          # device f32 [n,1,H,W] tensors (SwapModel.set_noises moves them once)
         codes = [ops.l2_normalize(c.to(self.device, torch.float32), 1e-8, 0) for c in codes]   # util.normalize
-        g = codes[-1]
-        k = g.shape[1]
-        sc = ops.linear(g, *G["scm_scale"], w_scale=k ** -0.5)
-        sb = ops.linear(g, *G["scm_bias"], w_scale=k ** -0.5)
-        x = self.apply(sp, sc, sb)                                   # GeneratorModulation, generator.py:80-91
+        st = self.styles(codes)
+        x = self.apply(sp, st["scm_scale"].contiguous(), st["scm_bias"].contiguous())   # GeneratorModulation, generator.py:80-91
         if taps is not None:
             taps["SpatialCodeModulation"] = x
         for i, (ci, co) in enumerate(HEAD_CH):
             B = G["head%d" % i]
             name = "HeadResnetBlock%d" % i
             skip = self.conv(x, B["skip"])[0] if "skip" in B else x
-            y, a, b = self._styled(B["conv1"], x, g, noises.get(name + ".conv1"))
+            y, a, b = self._styled(B["conv1"], x, st["head%d.conv1" % i], noises.get(name + ".conv1"))
             h = self.apply(y, a, b)
-            y, a, b = self._styled(B["conv2"], h, g, noises.get(name + ".conv2"))
+            y, a, b = self._styled(B["conv2"], h, st["head%d.conv2" % i], noises.get(name + ".conv2"))
             x = self.apply(y, a, b, res=skip, res_mode=1, post_gain=INV_SQRT2)
             if taps is not None:
                 taps[name] = x
@@ -352,11 +385,10 @@ class Engine:
         for j, (res, ci, co) in enumerate(UP_CH):
             B = G["up%d" % res]
             name = "UpsamplingResBlock%d" % res
-            g = codes[-2 - j]
             skip = self.conv(x, B["skip"])[0] if "skip" in B else x
-            y, a, b = self._styled(B["conv1"], x, g, noises.get(name + ".conv1"), upsample=True)
+            y, a, b = self._styled(B["conv1"], x, st["up%d.conv1" % res], noises.get(name + ".conv1"), upsample=True)
             h = self.apply(y, a, b)
-            y, a, b = self._styled(B["conv2"], h, g, noises.get(name + ".conv2"))
+            y, a, b = self._styled(B["conv2"], h, st["up%d.conv2" % res], noises.get(name + ".conv2"))
             x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2)     # bilinear x2 skip, generator.py:75
             if taps is not None:
                 taps[name] = x
@@ -364,9 +396,8 @@ class Engine:
                 feas.append(self._feature_head(G["layer%d" % (2 ** (j + 6))], x))
         # ToRGB (stylegan2_layers.py:477-495); fp32 from here on (3-channel IN is sensitive)
         n, h, w, _ = x.shape
-        yrgb, _ = self.conv(x, G["rgb"], out_dtype=torch.float32)
-        s = ops.linear(codes[0], *G["rgb_lin"], w_scale=k ** -0.5)
-        a, b = self.coeffs(yrgb, style=s)
+        yrgb = ops.conv1x1_thin_out(x, G["rgb"].w32[0], G["rgb"].bias)
+        a, b = self.coeffs(yrgb, style=st["rgb"])
         rgb = self.apply(yrgb, a, b)
         if not extract_features:
             return rgb

@@ -27,7 +27,20 @@ class SwapModel:
             raise RuntimeError("ppst_b200.SwapModel needs a CUDA device (there is no CPU fallback)")
         self.engine = Engine(sdE1, sdE2, sdG, device=device, mode=mode)
         self.device = self.engine.device
-        self.noises = None            # optional dict '<block>.conv{1,2}' -> [B,1,H,W]; None = noise term skipped
+        self._noises = None
+        self._graphs = {}
+
+    @property
+    def noises(self):
+        """Optional dict '<block>.conv{1,2}' -> [B,1,H,W] NoiseInjection inputs (stylegan2_layers.py:376-399).  None:
+        the noise term is skipped (the reference would draw fresh N(0,1) noise; its weight is 0 at init)."""
+        return self._noises
+
+    @noises.setter
+    def noises(self, value):
+        self._noises = None if value is None else {
+            k: v.to(self.device, torch.float32).contiguous() for k, v in value.items()}
+        self._graphs.clear()
 
     @classmethod
     def from_model_state_dict(cls, sd, **kw):
@@ -43,7 +56,7 @@ class SwapModel:
 
     # -- helpers ------------------------------------------------------------------------------------------
     def _in(self, image):
-        return self.engine.to_nhwc(image)
+        return image.to(self.device, torch.float32).contiguous()
 
     @staticmethod
     def _out(x_nhwc):
@@ -132,7 +145,7 @@ class SwapModel:
     def swap(self, content, style, alpha=1.0, return_nhwc=False):
         """One (content, style) -> swapped image per batch row: the minimal unit of SURVEY.md 8(d) C2
         {E1(c), E2(c), G.extract(c), E1(s), E2(s), G.extract(s), Rselfcorr x2, corrm, E2(s,corr), G.decode},
-        i.e. evaluation/simple_swapping_evaluator.py:44-59 without the duplicated content encode."""
+        i.e. evaluation/simple_swapping_evaluator.py:44-59 without the duplicated content encode.  Eager launches."""
         e = self.engine
         xc, xs = self._in(content), self._in(style)
         n = xc.shape[0]
@@ -153,3 +166,32 @@ class SwapModel:
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
         rgb = e.generator(sp_c, codes, noises=self.noises)
         return rgb if return_nhwc else self._out(rgb)
+
+    def swap_graph(self, content, style, alpha=1.0):
+        """swap() replayed from a CUDA graph: the ~600 kernel launches of one step are captured once per
+        (batch shape, alpha) and replayed with a single host call.  `content` / `style` may be pinned host tensors
+        (the copies into the graph's static inputs are part of the call).  The returned tensor is the graph's static
+        output buffer: consume or copy it before the next call with the same shapes."""
+        key = (tuple(content.shape), tuple(style.shape), float(alpha))
+        entry = self._graphs.get(key)
+        if entry is None:
+            c_static = torch.empty(tuple(content.shape), device=self.device, dtype=torch.float32)
+            s_static = torch.empty(tuple(style.shape), device=self.device, dtype=torch.float32)
+            c_static.copy_(content)
+            s_static.copy_(style)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                       # warm-up off the capture: attribute setup, tensor maps
+                for _ in range(2):
+                    self.swap(c_static, s_static, alpha)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_static = self.swap(c_static, s_static, alpha)
+            entry = (graph, c_static, s_static, out_static)
+            self._graphs[key] = entry
+        graph, c_static, s_static, out_static = entry
+        c_static.copy_(content, non_blocking=True)
+        s_static.copy_(style, non_blocking=True)
+        graph.replay()
+        return out_static

@@ -20,6 +20,7 @@ def _L():
 # by CUDA events on the launching stream and filed under its kernel name with its algorithmic work
 # (FLOPs for GEMM-shaped kernels, bytes for HBM-bound ones).
 PROFILE = None
+_prof_count = 0
 
 
 class _Prof:
@@ -27,7 +28,13 @@ class _Prof:
         self.name, self.work = name, work
 
     def __enter__(self):
+        global _prof_count
         if PROFILE is not None:
+            # keep the GPU busy every so often so that the host runs AHEAD of the device: otherwise the interval
+            # between the two events also contains the host time spent issuing the launch (Python, ~50-100 us)
+            if _prof_count % 64 == 0:
+                torch.cuda._sleep(30_000_000)
+            _prof_count += 1
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
@@ -167,6 +174,31 @@ def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
     return out
 
 
+def conv1x1_in_nchw(x_nchw, w, bias, act, out_dtype, slope=0.2, gain=SQRT2):
+    """FromRGB: NCHW f32 image -> NHWC [n,h,w,cout]."""
+    require_cuda(x_nchw, w, bias)
+    x_nchw = x_nchw.contiguous()
+    n, cin, h, wd = x_nchw.shape
+    cout = w.shape[0]
+    out = torch.empty((n, h, wd, cout), device=x_nchw.device, dtype=out_dtype)
+    with _Prof("conv1x1_in_nchw", x_nchw.numel() * 4 + out.numel() * out.element_size()):
+        check(_L().ppst_conv1x1_in_nchw(ptr(out), ptr(x_nchw), ptr(w), ptr(bias), n, cin, h * wd, cout, cout, 0,
+                                        1 if act else 0, float(slope), float(gain if act else 1.0), dt(out), stream()))
+    return out
+
+
+def conv1x1_thin_out(x_nhwc, w, bias):
+    """ToRGB conv: NHWC [n,h,w,cin] -> f32 NHWC [n,h,w,cout]."""
+    require_cuda(x_nhwc, w, bias)
+    n, h, wd, cin = x_nhwc.shape
+    cout = w.shape[0]
+    out = torch.empty((n, h, wd, cout), device=x_nhwc.device, dtype=torch.float32)
+    with _Prof("conv1x1_thin_out", x_nhwc.numel() * x_nhwc.element_size() + out.numel() * 4):
+        check(_L().ppst_conv1x1_thin_out(ptr(out), ptr(x_nhwc), ptr(w), ptr(bias), n * h * wd, cin, cout, dt(x_nhwc),
+                                         stream()))
+    return out
+
+
 def conv_tc_available():
     return bool(_L().ppst_conv_tc_available())
 
@@ -177,7 +209,11 @@ def in_coeffs(n, c, sum_=None, sumsq=None, count=1.0, shift=None, style=None, bi
     device = device or (sum_ if sum_ is not None else style if style is not None else bias).device
     a = torch.empty((n, c), device=device, dtype=torch.float32)
     b = torch.empty((n, c), device=device, dtype=torch.float32)
-    check(_L().ppst_in_coeffs(ptr(a), ptr(b), ptr(sum_), ptr(sumsq), ptr(shift), ptr(style), ptr(bias), n, c,
+    style_ld = 0
+    if style is not None:
+        assert style.stride(1) == 1 and style.shape[1] == 2 * c
+        style_ld = style.stride(0)
+    check(_L().ppst_in_coeffs(ptr(a), ptr(b), ptr(sum_), ptr(sumsq), ptr(shift), ptr(style), style_ld, ptr(bias), n, c,
                               n_partials, float(count), float(eps), 1 if use_norm else 0, stream()))
     return a, b
 

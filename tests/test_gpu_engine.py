@@ -79,7 +79,7 @@ def model_bf16(world):
 # ------------------------------------------------------------------------------------------------ fp32 mode
 def test_fp32_encoders_per_layer(world, model_fp32, golden):
     e = model_fp32.engine
-    x = e.to_nhwc(world["c"])
+    x = world["c"].cuda()
     taps = {}
     sp = e.encoder_con(x, taps=taps)
     for k, ref in world["tE1"].items():
@@ -103,8 +103,8 @@ def test_fp32_generator_per_layer(world, model_fp32, golden):
     e = model_fp32.engine
     sp = e.to_nhwc(world["sp_c"])
     taps = {}
-    rgb, fea, fea1 = e.generator(sp, [t.cuda() for t in world["gl_c"]], extract_features=True, noises=world["noises"],
-                                 taps=taps)
+    rgb, fea, fea1 = e.generator(sp, [t.cuda() for t in world["gl_c"]], extract_features=True,
+                                 noises=model_fp32.noises, taps=taps)
     for k in ["SpatialCodeModulation"] + ["HeadResnetBlock%d" % i for i in range(4)] + \
             ["UpsamplingResBlock%d" % r for r in (16, 32, 64)] + ["feat_cat", "feat1_cat"]:
         err = (nchw(taps[k]) - world["tG"][k]).abs().max()
@@ -115,7 +115,7 @@ def test_fp32_generator_per_layer(world, model_fp32, golden):
     g = golden("nets")
     check_summary(g, "G/rec_c", nchw(rgb), atol=3e-4)
     check_summary(g, "G/fea_c", nchw(fea), atol=3e-4)
-    rgb2 = e.generator(sp, [t.cuda() for t in world["gl_c"]], noises=world["noises"])
+    rgb2 = e.generator(sp, [t.cuda() for t in world["gl_c"]], noises=model_fp32.noises)
     assert torch.equal(rgb2, rgb)                                             # deterministic, extract does not perturb rgb
 
 
@@ -189,9 +189,9 @@ def test_bf16_per_layer_and_output(world, model_bf16):
     the error of that layer alone; the drift accumulated through a whole network is bounded separately."""
     e = model_bf16.engine
     assert e.use_tc, "the tcgen05 path must be the one that runs in bf16 mode"
-    x = e.to_nhwc(world["c"])
+    x = world["c"].cuda()
     # --- E1, block by block from the oracle's activations
-    y, _ = e.conv(x, e.E1["from_rgb"])
+    y = e.from_rgb(e.E1, x)
     assert rel_l2(nchw(y), world["tE1"]["FromRGB"]) <= 1e-2
     prev = "FromRGB"
     for i in (1, 2, 4):
@@ -216,7 +216,7 @@ def test_bf16_per_layer_and_output(world, model_bf16):
         assert rel_l2(gl[i].cpu(), world["gl_c"][i]) <= 1e-2
     # --- generator: each block from the oracle's input of that block (per-layer error) ...
     G = e.G
-    codes = [ops_l2(t) for t in world["gl_c"]]
+    st = e.styles([ops_l2(t) for t in world["gl_c"]])
     names = ["SpatialCodeModulation"] + ["HeadResnetBlock%d" % i for i in range(4)] + \
             ["UpsamplingResBlock%d" % r for r in (16, 32, 64)]
     from ppst_b200.engine import HEAD_CH, UP_CH, INV_SQRT2
@@ -224,9 +224,9 @@ def test_bf16_per_layer_and_output(world, model_bf16):
         B = G["head%d" % i]
         xin = e.to_nhwc(world["tG"][names[i]])
         skip = e.conv(xin, B["skip"])[0] if "skip" in B else xin
-        y, a, b = e._styled(B["conv1"], xin, codes[-1], world["noises"]["HeadResnetBlock%d.conv1" % i].cuda())
+        y, a, b = e._styled(B["conv1"], xin, st["head%d.conv1" % i], world["noises"]["HeadResnetBlock%d.conv1" % i].cuda())
         h = e.apply(y, a, b)
-        y, a, b = e._styled(B["conv2"], h, codes[-1], world["noises"]["HeadResnetBlock%d.conv2" % i].cuda())
+        y, a, b = e._styled(B["conv2"], h, st["head%d.conv2" % i], world["noises"]["HeadResnetBlock%d.conv2" % i].cuda())
         out = e.apply(y, a, b, res=skip, res_mode=1, post_gain=INV_SQRT2)
         r = rel_l2(nchw(out), world["tG"]["HeadResnetBlock%d" % i])
         assert r <= 1e-2, ("G.HeadResnetBlock%d" % i, r)
@@ -235,9 +235,9 @@ def test_bf16_per_layer_and_output(world, model_bf16):
         name = "UpsamplingResBlock%d" % res
         xin = e.to_nhwc(world["tG"][names[4 + j]])
         skip = e.conv(xin, B["skip"])[0] if "skip" in B else xin
-        y, a, b = e._styled(B["conv1"], xin, codes[-2 - j], world["noises"][name + ".conv1"].cuda(), upsample=True)
+        y, a, b = e._styled(B["conv1"], xin, st["up%d.conv1" % res], world["noises"][name + ".conv1"].cuda(), upsample=True)
         h = e.apply(y, a, b)
-        y, a, b = e._styled(B["conv2"], h, codes[-2 - j], world["noises"][name + ".conv2"].cuda())
+        y, a, b = e._styled(B["conv2"], h, st["up%d.conv2" % res], world["noises"][name + ".conv2"].cuda())
         out = e.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2)
         r = rel_l2(nchw(out), world["tG"][name])
         assert r <= 1e-2, ("G." + name, r)
@@ -245,7 +245,7 @@ def test_bf16_per_layer_and_output(world, model_bf16):
     taps = {}
     sp_ref = e.to_nhwc(world["sp_c"])
     rgb, fea, fea1 = e.generator(sp_ref, [t.cuda() for t in world["gl_c"]], extract_features=True,
-                                 noises=world["noises"], taps=taps)
+                                 noises=model_bf16.noises, taps=taps)
     gdrift = {k: rel_l2(nchw(taps[k]), world["tG"][k]) for k in names}
     assert max(gdrift.values()) <= 2e-2, gdrift
     assert psnr(nchw(rgb), world["rgb_c"]) >= 45.0, psnr(nchw(rgb), world["rgb_c"])
@@ -264,6 +264,10 @@ def test_bf16_end_to_end_swap(world, model_bf16):
     assert p >= 45.0, p
     out2 = model_bf16.swap(world["c"], world["s"])
     assert torch.equal(out, out2)                                      # run-to-run deterministic (no fp atomics)
+    # the CUDA-graph replay of the same step is bit-identical to the eager launches, also from pinned host inputs
+    g1 = model_bf16.swap_graph(world["c"].pin_memory(), world["s"].pin_memory()).clone()
+    g2 = model_bf16.swap_graph(world["c"].cuda(), world["s"].cuda()).clone()
+    assert torch.equal(g1, out) and torch.equal(g2, out)
 
 
 def test_batch_rows_are_independent(world, model_bf16):
