@@ -147,6 +147,13 @@ typedef struct {
   /* input addressing in ELEMENTS: pixel (y,x) of image i starts at i*in_img_pitch + y*in_row_pitch + x*cin.
      0 = dense (in_w*cin, in_h*in_w*cin).  Lets a conv read the interior of a padded buffer. */
   int64_t in_row_pitch, in_img_pitch;
+  /* GEMM use of the tensor-core kernel (ppst_conv_tc only; corrm / warp, ppst_model.py:363, encoder_col.py:124):
+     w_img_rows  > 0: image i multiplies rows [i*w_img_rows, ...) of `weight` (a per-sample B matrix) instead of a
+                      shared weight.
+     split_terms = 3: fp32-accurate product from bf16 operands.  Both operands hold [hi | lo] halves along the
+                      channel dim (cin = 2 x segment; hi = bf16(x), lo = bf16(x - hi)); the kernel accumulates
+                      hi*hi + hi*lo + lo*hi.  Requires kh = kw = 1. */
+  int32_t w_img_rows, split_terms;
 } ppst_conv_desc;
 
 /* CUDA-core implicit GEMM (fp32 accumulate; any channel counts).  fp32 mode and the thin layers
@@ -155,8 +162,8 @@ typedef struct {
 PPST_API int ppst_conv_simt(void* out, const void* in, const float* weight, const float* bias, const float* noise,
                    const ppst_conv_desc* d, void* stream);
 
-/* tcgen05 / TMEM / TMA implicit GEMM (bf16 in, fp32 accumulate in tensor memory, bf16 out).
- * Requires cin % 64 == 0, cout % 16 == 0, stride == 1.  weight: bf16, same packing as above.
+/* tcgen05 / TMEM / TMA implicit GEMM (bf16 in, fp32 accumulate in tensor memory, bf16 or f32 out).
+ * Requires cin % 32 == 0, cout % 32 == 0, stride 1 or 2.  weight: bf16, same packing as above.
  * stats (optional, f32 [n_tiles][2][cout_stride]... see ppst_conv_tc_stats_elems): per-tile partial sum / sum of
  * squares of the stored (rounded) outputs, reduced later by ppst_in_coeffs -- the instance-norm statistics
  * of LayerEpilogue (stylegan2_layers.py:414-437) come for free with the convolution. */
@@ -247,6 +254,18 @@ PPST_API int ppst_rselfcorr(void* out, const void* fea, int64_t n, int h, int w,
 /* corrm preparation (:349-361): per pixel, centre the first `c_center` channels over the channel dim, then
  * L2-normalise all c channels (+ DBL_EPSILON).  in: NHWC [rows, c]; out f32 [rows, c]. */
 PPST_API int ppst_corr_prepare(float* out, const void* in, int64_t rows, int c, int c_center, int in_dtype, void* stream);
+
+/* Operands of the 3-term split tensor-core GEMM (ppst_conv_desc.split_terms = 3): every f32 value x becomes
+ * hi = bf16(x), lo = bf16(x - hi), stored as [hi | lo] halves along the K dimension.
+ *   ppst_corr_prepare_split : ppst_corr_prepare with split output, bf16 [rows, 2c]
+ *   ppst_split_bf16         : f32 [batch, rows, cols] -> bf16 [batch, rows, 2*cols]; transpose=1: -> bf16
+ *                             [batch, cols, 2*rows] (K-major B operand of corr @ feat from an NHWC feature map)
+ *   ppst_softmax_rows_split : softmax(x / divisor) per row, bf16 [rows, 2*cols] (corr as the A operand of warp) */
+PPST_API int ppst_corr_prepare_split(void* out, const void* in, int64_t rows, int c, int c_center, int in_dtype,
+                            void* stream);
+PPST_API int ppst_split_bf16(void* out, const float* in, int64_t batch, int64_t rows, int64_t cols, int transpose,
+                    void* stream);
+PPST_API int ppst_softmax_rows_split(void* out, const float* x, int64_t rows, int64_t cols, float divisor, void* stream);
 
 /* Batched f32 GEMM  C[b] = alpha * A[b] (m x k, row-major, lda) * B[b]  with B either k x n row-major
  * (trans_b = 0) or n x k row-major (trans_b = 1); 3-term bf16 split on tcgen05 is a later round -- this is

@@ -23,7 +23,8 @@ class ConvDesc(ctypes.Structure):
                  "has_act")] + \
                [("slope", c_float), ("gain", c_float), ("noise_w", c_float),
                 ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
-                ("in_row_pitch", ctypes.c_int64), ("in_img_pitch", ctypes.c_int64)]
+                ("in_row_pitch", ctypes.c_int64), ("in_img_pitch", ctypes.c_int64),
+                ("w_img_rows", ctypes.c_int32), ("split_terms", ctypes.c_int32)]
 
 
 class ApplyDesc(ctypes.Structure):
@@ -63,6 +64,9 @@ _SIGS = {
     "ppst_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p]),
     "ppst_rselfcorr": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 7 + [c_void_p]),
     "ppst_corr_prepare": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
+    "ppst_corr_prepare_split": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
+    "ppst_split_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ppst_softmax_rows_split": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
     "ppst_gemm_f32": (c_int, [c_void_p] * 3 + [c_i64] * 10 + [c_int, c_float, c_void_p]),
     "ppst_softmax_rows": (c_int, [c_void_p, c_i64, c_i64, c_float, c_void_p]),
 }

@@ -44,6 +44,8 @@ struct Params {
   int has_act;
   float slope, gain, noise_w;
   int stats_partials;                   // partial slots per image = tiles_y*tiles_x*phases
+  int w_img_rows;                       // weight rows per image (0: one weight matrix for the whole batch)
+  int split_seg_kb;                     // 3-term split GEMM: k-blocks per [hi]/[lo] segment (0: plain)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -196,10 +198,10 @@ struct Smem {
   static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
 };
 
-template <int BN, int BKC, int STAGES>
+template <int BN, int BKC, int STAGES, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ noise,
+               void* __restrict__ out_raw, const float* __restrict__ bias, const float* __restrict__ noise,
                float* __restrict__ stats_sum, float* __restrict__ stats_sq, const Params p) {
   using S = Smem<BN, BKC, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -236,7 +238,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   const int taps = p.kh * p.kw;
-  const int kblocks = taps * p.kblocks_per_tap;
+  // split mode (1x1 only): logical K = [hi|hi|lo] x [hi|lo|hi] over physical [hi|lo] operands
+  const int kblocks = p.split_seg_kb ? 3 * p.split_seg_kb : taps * p.kblocks_per_tap;
   const int n_phases = p.phases_y * p.phases_x;
 
   // work item -> (n-tile, phase, spatial tile, image); n-tile fastest so that neighbouring CTAs share A in L2
@@ -258,16 +261,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int py = ph / p.phases_x, px = ph % p.phases_x;
         const int iy0 = ty * p.th * p.stride + p.off_y + py * p.phase_off_dy;
         const int ix0 = tx * p.tw * p.stride + p.off_x + px * p.phase_off_dx;
-        const int brow = ph * p.cout + nt * BN;
+        const int brow = img * p.w_img_rows + ph * p.cout + nt * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / p.kblocks_per_tap, cb = kb - tap * p.kblocks_per_tap;
+          int tap, ca, cbk;
+          if (p.split_seg_kb) {
+            const int seg = kb / p.split_seg_kb, r = kb - seg * p.split_seg_kb;
+            tap = 0;
+            ca = ((seg == 2 ? p.split_seg_kb : 0) + r) * BKC;        // A: hi, hi, lo
+            cbk = ((seg == 1 ? p.split_seg_kb : 0) + r) * BKC;       // B: hi, lo, hi
+          } else {
+            tap = kb / p.kblocks_per_tap;
+            ca = (kb - tap * p.kblocks_per_tap) * BKC;
+            cbk = tap * p.cin + ca;
+          }
           const int ky = tap / p.kw, kx = tap - ky * p.kw;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::kStageBytes;
           uint8_t* sb = sa + S::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_4d(sa, &map_a, &full_bar[stage], cb * BKC, ix0 + kx, iy0 + ky, img);
-          tma_load_2d(sb, &map_b, &full_bar[stage], tap * p.cin + cb * BKC, brow);
+          tma_load_4d(sa, &map_a, &full_bar[stage], ca, ix0 + kx, iy0 + ky, img);
+          tma_load_2d(sb, &map_b, &full_bar[stage], cbk, brow);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -318,7 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool valid = (oy < p.out_h) && (ox < p.out_w);
       const int64_t pix = ((int64_t)img * p.full_h + (oy * p.phases_y + py)) * p.full_w + (ox * p.phases_x + px);
       const float nz = (noise != nullptr && valid) ? p.noise_w * noise[pix] : 0.0f;
-      __nv_bfloat16* orow = out + pix * p.cout_stride + p.c_off + nt * BN;
+      const int64_t obase = pix * p.cout_stride + p.c_off + nt * BN;
       float* st_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN + q * BN;
       float* st_sq = s_stats + (size_t)(as * 2 + 1) * 4 * BN + q * BN;
 
@@ -337,11 +350,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
           v[j] = a * p.gain;
         }
+        if (OUT_F32) {
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_raw) + obase + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          continue;
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
         if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_raw) + obase + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
         }
@@ -368,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
 
-      if (stats_sum != nullptr) {
+      if (!OUT_F32 && stats_sum != nullptr) {
         asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps
         const int e = threadIdx.x - kEpiWarp0 * 32;
         const float* b_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN;
@@ -469,7 +490,7 @@ static void pick_tile(int out_h, int out_w, int& th, int& tw) {
 
 static int g_num_sms = 0;
 
-template <int BN, int BKC, int STAGES>
+template <int BN, int BKC, int STAGES, bool OUT_F32>
 static int launch(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
                   const float* noise, float* stats, cudaStream_t st) {
   using S = Smem<BN, BKC, STAGES>;
@@ -487,6 +508,8 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_tc: too many tiles");
   p.num_tiles = (int)tiles;
   p.kblocks_per_tap = d.cin / BKC;
+  p.w_img_rows = d.w_img_rows;
+  p.split_seg_kb = d.split_terms == 3 ? (d.cin / 2) / BKC : 0;
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
   p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
 
@@ -503,7 +526,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   }
   {
     const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
-    const uint64_t dims[2] = {K, (uint64_t)d.cout * n_phases};
+    const uint64_t dims[2] = {K, d.w_img_rows ? (uint64_t)d.w_img_rows * d.n : (uint64_t)d.cout * n_phases};
     const uint64_t strides[1] = {K * 2};
     const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)BN};
     const uint32_t est[2] = {1, 1};
@@ -516,7 +539,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  auto kern = conv_tc_kernel<BN, BKC, STAGES>;
+  auto kern = conv_tc_kernel<BN, BKC, STAGES, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
@@ -527,7 +550,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   float* ssum = stats;
   float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
-  kern<<<grid, kThreads, S::kTotal, st>>>(map_a, map_b, (__nv_bfloat16*)out, bias, noise, ssum, ssq, p);
+  kern<<<grid, kThreads, S::kTotal, st>>>(map_a, map_b, out, bias, noise, ssum, ssq, p);
   PPST_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
 }
@@ -557,7 +580,13 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
   const ppst_conv_desc d = *dp;
   int rc = validate_conv_desc(d, "conv_tc");
   if (rc) return rc;
-  PPST_REQUIRE(d.in_dtype == PPST_BF16 && d.out_dtype == PPST_BF16, PPST_ERR_DTYPE, "conv_tc: bf16 in / bf16 out only");
+  PPST_REQUIRE(d.in_dtype == PPST_BF16 && (d.out_dtype == PPST_BF16 || d.out_dtype == PPST_F32), PPST_ERR_DTYPE,
+               "conv_tc: bf16 in, bf16 or f32 out");
+  PPST_REQUIRE(d.split_terms == 0 || (d.split_terms == 3 && d.kh == 1 && d.kw == 1 && d.cin % 128 == 0), PPST_ERR_UNSUPPORTED,
+               "conv_tc: split_terms=%d needs a 1x1 kernel and cin (= 2 x segment) a multiple of 128", d.split_terms);
+  PPST_REQUIRE(d.w_img_rows == 0 || (d.phases_y * d.phases_x == 1 && d.w_img_rows >= d.cout), PPST_ERR_ARG,
+               "conv_tc: per-image weights need a single phase and w_img_rows >= cout");
+  PPST_REQUIRE(d.out_dtype == PPST_BF16 || stats == nullptr, PPST_ERR_UNSUPPORTED, "conv_tc: statistics need bf16 output");
   PPST_REQUIRE(d.cin % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cin=%d must be a multiple of 32", d.cin);
   PPST_REQUIRE(d.cout % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cout=%d must be a multiple of 32", d.cout);
   PPST_REQUIRE(d.stride == 1 || d.stride == 2, PPST_ERR_UNSUPPORTED, "conv_tc: stride %d", d.stride);
@@ -567,7 +596,12 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
                PPST_ERR_ARG, "conv_tc: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const bool k64 = (d.cin % 64 == 0);
-#define PPST_TC(BN_, BKC_, ST_) return tc::launch<BN_, BKC_, ST_>(d, out, in, weight, bias, noise, stats, st)
+#define PPST_TC(BN_, BKC_, ST_)                                                                   \
+  do {                                                                                            \
+    if (d.out_dtype == PPST_F32)                                                                  \
+      return tc::launch<BN_, BKC_, ST_, true>(d, out, in, weight, bias, noise, stats, st);        \
+    return tc::launch<BN_, BKC_, ST_, false>(d, out, in, weight, bias, noise, stats, st);         \
+  } while (0)
   if (k64) {
     if (d.cout % 256 == 0) PPST_TC(256, 64, 4);
     if (d.cout % 128 == 0) PPST_TC(128, 64, 6);

@@ -79,7 +79,154 @@ __global__ void __launch_bounds__(256) corr_prepare_kernel(float* __restrict__ o
     out[row * c + ch] = (Cvt<TI>::to_f(p[ch]) - (ch < c_center ? mu : 0.f)) * inv;
 }
 
+__device__ __forceinline__ void split2(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// corr_prepare with the result emitted as [hi | lo] bf16 halves (operand of the 3-term split GEMM).
+template <typename TI>
+__global__ void __launch_bounds__(256) corr_prepare_split_kernel(__nv_bfloat16* __restrict__ out, const TI* __restrict__ in,
+                                                                 int64_t rows, int c, int c_center) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TI* p = in + row * c;
+  float s = 0.f;
+  for (int ch = lane; ch < c_center; ch += 32) s += Cvt<TI>::to_f(p[ch]);
+  s = warp_sum(s);
+  const float mu = c_center > 0 ? s / (float)c_center : 0.f;
+  float q = 0.f;
+  for (int ch = lane; ch < c; ch += 32) {
+    const float v = Cvt<TI>::to_f(p[ch]) - (ch < c_center ? mu : 0.f);
+    q = fmaf(v, v, q);
+  }
+  q = warp_sum(q);
+  const float inv = 1.0f / (sqrtf(q) + (float)DBL_EPSILON);
+  __nv_bfloat16* o = out + row * 2 * c;
+  for (int ch = lane; ch < c; ch += 32) {
+    __nv_bfloat16 hi, lo;
+    split2((Cvt<TI>::to_f(p[ch]) - (ch < c_center ? mu : 0.f)) * inv, hi, lo);
+    o[ch] = hi;
+    o[c + ch] = lo;
+  }
+}
+
+// f32 [rows, cols] -> bf16 [rows, 2*cols] = [hi | lo]
+__global__ void split_bf16_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, cidx = i - r * cols;
+    __nv_bfloat16 hi, lo;
+    split2(in[i], hi, lo);
+    out[r * 2 * cols + cidx] = hi;
+    out[r * 2 * cols + cols + cidx] = lo;
+  }
+}
+
+// f32 [n, L, C] -> bf16 [n, C, 2L] = per channel row [hi(L) | lo(L)]  (the K-major B operand of corr @ feat)
+__global__ void __launch_bounds__(256) split_bf16_t_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ in,
+                                                           int64_t L, int64_t C) {
+  __shared__ float tile[32][33];
+  const int64_t n = blockIdx.z;
+  const int64_t l0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t l = l0 + j, c = c0 + tx;
+    tile[j][tx] = (l < L && c < C) ? in[(n * L + l) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, l = l0 + tx;
+    if (c < C && l < L) {
+      __nv_bfloat16 hi, lo;
+      split2(tile[tx][j], hi, lo);
+      out[(n * C + c) * 2 * L + l] = hi;
+      out[(n * C + c) * 2 * L + L + l] = lo;
+    }
+  }
+}
+
+// softmax(x / divisor) per row, written as [hi | lo] bf16 halves; one block per row
+__global__ void __launch_bounds__(256) softmax_rows_split_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+                                                                 int64_t cols, float divisor) {
+  const float* xr = x + (int64_t)blockIdx.x * cols;
+  __nv_bfloat16* o = out + (int64_t)blockIdx.x * 2 * cols;
+  __shared__ float sm[8];
+  __shared__ float bc;
+  float mx = -FLT_MAX;
+  for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) mx = fmaxf(mx, xr[i] / divisor);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = sm[0];
+    for (int i = 1; i < 8; ++i) t = fmaxf(t, sm[i]);
+    bc = t;
+  }
+  __syncthreads();
+  mx = bc;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) s += expf(xr[i] / divisor - mx);
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    bc = t;
+  }
+  __syncthreads();
+  const float tot = bc;
+  for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) {
+    __nv_bfloat16 hi, lo;
+    split2(expf(xr[i] / divisor - mx) / tot, hi, lo);
+    o[i] = hi;
+    o[cols + i] = lo;
+  }
+}
+
 }  // namespace ppst
+
+extern "C" int ppst_corr_prepare_split(void* out, const void* in, int64_t rows, int c, int c_center, int in_dtype,
+                                       void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && in && rows > 0 && c > 0 && c_center >= 0 && c_center <= c, PPST_ERR_ARG,
+               "corr_prepare_split: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  PPST_DISPATCH_DTYPE(in_dtype, T, corr_prepare_split_kernel<T><<<ceil_div(rows, 8), 256, 0, st>>>(
+                                       (__nv_bfloat16*)out, (const T*)in, rows, c, c_center));
+  PPST_LAUNCH_CHECK("corr_prepare_split_kernel");
+  return 0;
+}
+
+extern "C" int ppst_split_bf16(void* out, const float* in, int64_t batch, int64_t rows, int64_t cols, int transpose,
+                               void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && in && batch > 0 && rows > 0 && cols > 0, PPST_ERR_ARG, "split_bf16: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (transpose) {
+    PPST_REQUIRE(batch <= 65535 && (cols + 31) / 32 <= 65535, PPST_ERR_ARG, "split_bf16: grid too large");
+    dim3 grid(ceil_div(rows, 32), ceil_div(cols, 32), (unsigned)batch);
+    split_bf16_t_kernel<<<grid, 256, 0, st>>>((__nv_bfloat16*)out, in, rows, cols);
+  } else {
+    const int64_t total = batch * rows * cols;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    split_bf16_kernel<<<blocks, 256, 0, st>>>((__nv_bfloat16*)out, in, batch * rows, cols);
+  }
+  PPST_LAUNCH_CHECK("split_bf16_kernel");
+  return 0;
+}
+
+extern "C" int ppst_softmax_rows_split(void* out, const float* x, int64_t rows, int64_t cols, float divisor,
+                                       void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && rows > 0 && cols > 0 && divisor != 0.0f, PPST_ERR_ARG, "softmax_rows_split: bad args");
+  softmax_rows_split_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, cols, divisor);
+  PPST_LAUNCH_CHECK("softmax_rows_split_kernel");
+  return 0;
+}
 
 extern "C" int ppst_rselfcorr(void* out, const void* fea, int64_t n, int h, int w, int c, int out_c_stride, int c_off,
                               int in_dtype, int out_dtype, void* stream) {

@@ -245,41 +245,54 @@ __global__ void __launch_bounds__(256) affine_apply_rows_kernel(TO* __restrict__
     r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
     r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
   }
-#pragma unroll 2
-  for (int ox = lane; ox < ow; ox += lanes) {
-    bool zero = zero_row;
-    const int ux = map_pad(ox - d.pad_l, wu, d.pad_mode, zero);
-    float y[V];
-    if (zero) {
+  constexpr int U = 4;                       // pixels in flight per thread: all loads of a batch are issued first
+  for (int ox0 = lane; ox0 < ow; ox0 += U * lanes) {
+    float xv[U][V], rv[U][V];
+    int uxs[U];
+    bool live[U], zero[U];
 #pragma unroll
-      for (int e = 0; e < V; ++e) y[e] = 0.0f;
-    } else {
-      float xv[V];
-      load_ch<TX, V>(xv, xrow + (int64_t)(ux / d.up) * d.c);
-#pragma unroll
-      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
-      if (d.res_mode == 1) {
-        float rv[V];
-        load_ch<TX, V>(rv, r0 + (int64_t)ux * d.c);
-#pragma unroll
-        for (int e = 0; e < V; ++e) y[e] += fmaf(rv[e], rav[e], rbv[e]);
-      } else if (d.res_mode == 2) {
-        const Bilin2 bx = bilin_x2(ux, lw);
-        float v00[V], v01[V], v10[V], v11[V];
-        load_ch<TX, V>(v00, r0 + (int64_t)bx.i0 * d.c);
-        load_ch<TX, V>(v01, r0 + (int64_t)bx.i1 * d.c);
-        load_ch<TX, V>(v10, r1 + (int64_t)bx.i0 * d.c);
-        load_ch<TX, V>(v11, r1 + (int64_t)bx.i1 * d.c);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float rv = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
-          y[e] += fmaf(rv, rav[e], rbv[e]);
-        }
+    for (int u = 0; u < U; ++u) {
+      const int ox = ox0 + u * lanes;
+      live[u] = ox < ow;
+      zero[u] = zero_row;
+      uxs[u] = map_pad(ox - d.pad_l, wu, d.pad_mode, zero[u]);
+      if (live[u] && !zero[u]) {
+        load_ch<TX, V>(xv[u], xrow + (int64_t)(uxs[u] / d.up) * d.c);
+        if (d.res_mode == 1) load_ch<TX, V>(rv[u], r0 + (int64_t)uxs[u] * d.c);
       }
-#pragma unroll
-      for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
     }
-    store_ch<TO, V>(orow + (int64_t)ox * d.out_c_stride, y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      const int ox = ox0 + u * lanes;
+      float y[V];
+      if (zero[u]) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] = 0.0f;
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[u][e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
+        if (d.res_mode == 1) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) y[e] += fmaf(rv[u][e], rav[e], rbv[e]);
+        } else if (d.res_mode == 2) {
+          const Bilin2 bx = bilin_x2(uxs[u], lw);
+          float v00[V], v01[V], v10[V], v11[V];
+          load_ch<TX, V>(v00, r0 + (int64_t)bx.i0 * d.c);
+          load_ch<TX, V>(v01, r0 + (int64_t)bx.i1 * d.c);
+          load_ch<TX, V>(v10, r1 + (int64_t)bx.i0 * d.c);
+          load_ch<TX, V>(v11, r1 + (int64_t)bx.i1 * d.c);
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const float r = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
+            y[e] += fmaf(r, rav[e], rbv[e]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
+      }
+      store_ch<TO, V>(orow + (int64_t)ox * d.out_c_stride, y);
+    }
   }
 }
 

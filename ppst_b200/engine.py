@@ -274,7 +274,12 @@ class Engine:
         else:
             size = (h, w)
             pooled = x if x.dtype == torch.float32 else self.apply(x, out_dtype=torch.float32)
-        wf = ops.gemm_f32(corr, pooled.view(n, size[0] * size[1], c), False)
+        if corr.dtype == torch.bfloat16:
+            # corr as [hi | lo] bf16 halves: fp32-accurate product on the tensor cores (3-term split GEMM)
+            bsp = ops.split_bf16(pooled.view(n, size[0] * size[1], c), transpose=True)       # [n, c, 2L]
+            wf = ops.gemm_split_tc(corr, bsp, (corr.shape[1] // 64, 64))
+        else:
+            wf = ops.gemm_f32(corr, pooled.view(n, size[0] * size[1], c), False)
         wf = wf.view(n, -1, 64, c) if h > w else wf.view(n, 64, -1, c)
         if resize and scale != 1:
             wf = ops.resample(wf, (wf.shape[1] * scale, wf.shape[2] * scale), 0)
@@ -282,7 +287,8 @@ class Engine:
 
     def encoder_col(self, image_nchw, corr=None, labels=None, taps=None):
         """E2: StyleGAN2ResnetEncodercol.forward (encoder_col.py:150-251).
-        corr: f32 [n,4096,4096] or None.  labels: uint8 [n,h,w] region map or None (training-path mask branch;
+        corr: f32 [n,4096,4096], or its [hi | lo] bf16 split [n,4096,8192] (ops.split_bf16 / corrm(split_out=True)),
+        or None.  labels: uint8 [n,h,w] region map or None (training-path mask branch;
         the reference takes the one-hot float mask -- see SwapModel.E2_forward for that signature).
         Returns (vectors, vectors_w) or (vectors, projections_m, vectors_w, projections_mw)."""
         P = self.E2
@@ -421,11 +427,21 @@ class Engine:
         """PPSTModel.Rselfcorr (ppst_model.py:330-339) written into a channel slice of `out`."""
         return ops.rselfcorr(fea1, out=out, out_c_off=c_off)
 
-    def corrm(self, fea_rows, fea0_rows):
+    def corrm(self, fea_rows, fea0_rows, split_out=False):
         """PPSTModel.corrm (ppst_model.py:341-364).  fea_rows / fea0_rows: NHWC [n,64,64,512] (any float dtype).
-        corr[b, i, j] = softmax_j( <fea0[b,:,i], fea[b,:,j]> / 0.01 )  -> f32 [n, L0, L]."""
-        n = fea_rows.shape[0]
-        a = ops.corr_prepare(fea_rows, 256).view(n, -1, fea_rows.shape[3])
-        q = ops.corr_prepare(fea0_rows, 256).view(n, -1, fea0_rows.shape[3])
-        logits = ops.gemm_f32(q, a, True)
+        corr[b, i, j] = softmax_j( <fea0[b,:,i], fea[b,:,j]> / 0.01 )  -> f32 [n, L0, L]
+        (split_out: the same numbers as [hi | lo] bf16 halves [n, L0, 2L], the A operand of the warp GEMMs).
+        bf16 mode: 3-term split GEMM on tcgen05 (fp32-accurate logits: T = 0.01 turns a 1e-3 cosine error into
+        0.1 in the exponent); fp32 mode: exact CUDA-core GEMM."""
+        n, c = fea_rows.shape[0], fea_rows.shape[3]
+        if self.use_tc:
+            a = ops.corr_prepare_split(fea_rows, 256).view(n, -1, 2 * c)
+            q = ops.corr_prepare_split(fea0_rows, 256).view(n, -1, 2 * c)
+            logits = ops.gemm_split_tc(q, a, (q.shape[1] // 64, 64))
+        else:
+            a = ops.corr_prepare(fea_rows, 256).view(n, -1, c)
+            q = ops.corr_prepare(fea0_rows, 256).view(n, -1, c)
+            logits = ops.gemm_f32(q, a, True)
+        if split_out:
+            return ops.softmax_rows_split(logits, 0.01)
         return ops.softmax_rows_(logits, 0.01)

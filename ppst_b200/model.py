@@ -75,8 +75,14 @@ class SwapModel:
         evaluation/simple_swapping_evaluator.py:53 passes."""
         if isinstance(corrmatrix, (list, tuple)):
             corrmatrix = corrmatrix[0]
-        corr = corrmatrix.to(self.device, torch.float32).contiguous()
+        corr = self._corr_operand(corrmatrix)
         return self.engine.encoder_col(self._in(image), corr=corr)
+
+    def _corr_operand(self, corrmatrix):
+        corr = corrmatrix.to(self.device, torch.float32).contiguous()
+        if self.engine.use_tc:
+            corr = ops.split_bf16(corr)          # [hi | lo] bf16 halves for the split tensor-core GEMM
+        return corr
 
     def E2_forward(self, image, mask=None, corrmatrix=None):
         """StyleGAN2ResnetEncodercol.forward signature (encoder_col.py:150): `mask` is the one-hot float mask
@@ -88,7 +94,7 @@ class SwapModel:
         if corrmatrix is not None:
             if isinstance(corrmatrix, (list, tuple)):
                 corrmatrix = corrmatrix[0]
-            corr = corrmatrix.to(self.device, torch.float32).contiguous()
+            corr = self._corr_operand(corrmatrix)
         return self.engine.encoder_col(self._in(image), corr=corr, labels=labels)
 
     def decode(self, spatial_code, global_code, target=None):
@@ -161,7 +167,7 @@ class SwapModel:
         ops.affine_apply(fea_s, 256, out=fs, out_c_off=0)
         ops.rselfcorr(fea_c1, out=fc, out_c_off=256)
         ops.rselfcorr(fea_s1, out=fs, out_c_off=256)
-        corr = e.corrm(fs, fc)
+        corr = e.corrm(fs, fc, split_out=e.use_tc)
         _, gl_w = e.encoder_col(xs, corr=corr)
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
         rgb = e.generator(sp_c, codes, noises=self.noises)

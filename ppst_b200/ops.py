@@ -23,9 +23,13 @@ PROFILE = None
 _prof_count = 0
 
 
+PROFILE_DETAIL = False        # file launches under "name|tag" (tag = shape string) instead of "name"
+
+
 class _Prof:
-    def __init__(self, name, work):
-        self.name, self.work = name, work
+    def __init__(self, name, work, tag=None):
+        self.name = name if not (PROFILE_DETAIL and tag) else "%s|%s" % (name, tag)
+        self.work = work
 
     def __enter__(self):
         global _prof_count
@@ -57,7 +61,8 @@ def profile_summary():
 
 
 def _conv_flops(d):
-    return 2.0 * d.n * d.out_h * d.out_w * d.phases_y * d.phases_x * d.cout * d.kh * d.kw * d.cin
+    k = d.kh * d.kw * d.cin * (1.5 if d.split_terms == 3 else 1.0)       # split: 3 segments of cin/2
+    return 2.0 * d.n * d.out_h * d.out_w * d.phases_y * d.phases_x * d.cout * k
 
 
 # ----------------------------------------------------------------------------------------------- layout
@@ -109,7 +114,7 @@ def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift
     outs = {k: torch.empty((n, n_regions, c), device=x.device, dtype=torch.float32) for k in want}
     if labels is not None:
         assert labels.dtype == torch.uint8 and labels.is_contiguous() and labels.numel() == n * hw
-    with _Prof("plane_reduce", x.numel() * x.element_size()):
+    with _Prof("plane_reduce", x.numel() * x.element_size(), "n%d hw%d c%d cl%d %s" % (n, hw, c, int(channels_last), str(x.dtype)[6:])):
         check(L.ppst_plane_reduce(ptr(outs.get("sum")), ptr(outs.get("sumsq")), ptr(outs.get("max")), ptr(x),
                                   ptr(labels), ptr(shift), ptr(scratch), n, c, hw, n_regions, label_mode,
                                   1 if channels_last else 0, dt(x), stream()))
@@ -135,7 +140,7 @@ def labels_pool_or(labels, factor, in_mode):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(1, 1), phase_off=(0, 0),
               full_hw=None, cout_stride=None, c_off=0, act=False, slope=0.2, gain=1.0, noise_w=0.0,
-              in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0):
+              in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0, w_img_rows=0, split_terms=0):
     n, in_h, in_w, cin = x_shape
     d = ConvDesc()
     d.n, d.in_h, d.in_w, d.cin = n, in_h, in_w, cin
@@ -152,12 +157,13 @@ def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(
     d.slope, d.gain, d.noise_w = slope, gain, noise_w
     d.in_dtype, d.out_dtype = in_dtype, out_dtype
     d.in_row_pitch, d.in_img_pitch = in_row_pitch, in_img_pitch
+    d.w_img_rows, d.split_terms = w_img_rows, split_terms
     return d
 
 
 def conv_simt(out, x, weight_f32, bias, noise, d):
     require_cuda(out, x, weight_f32, bias, noise)
-    with _Prof("conv_simt", _conv_flops(d)):
+    with _Prof("conv_simt", _conv_flops(d), "n%d %dx%d ci%d co%d k%dx%d s%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride)):
         check(_L().ppst_conv_simt(ptr(out), ptr(x), ptr(weight_f32), ptr(bias), ptr(noise), ctypes.byref(d), stream()))
     return out
 
@@ -168,7 +174,7 @@ def conv_tc_stats_elems(d):
 
 def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
     require_cuda(out, x, weight_bf16, bias, noise, stats)
-    with _Prof("conv_tc", _conv_flops(d)):
+    with _Prof("conv_tc", _conv_flops(d), "n%d %dx%d ci%d co%d k%dx%d s%d ph%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride, d.phases_y * d.phases_x)):
         check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
                                 stream()))
     return out
@@ -240,7 +246,7 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
     nbytes = x.numel() * x.element_size() + n * oh * ow * c * out.element_size()
     if res is not None:
         nbytes += (res.numel() if res_mode == 1 else n * oh * ow * c) * res.element_size()
-    with _Prof("affine_apply", nbytes):
+    with _Prof("affine_apply", nbytes, "n%d %dx%d c%d up%d pad%s res%d %s->%s" % (n, h, w, c, up, "".join(map(str, pad)), res_mode, str(x.dtype)[6:], str(out.dtype)[6:])):
         check(_L().ppst_affine_apply(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d),
                                      stream()))
     return out
@@ -295,7 +301,7 @@ def gemm_f32(a, b, trans_b, alpha=1.0, out=None):
     if out is None:
         out = torch.empty((bt, m, n), device=a.device, dtype=torch.float32)
     ldb = b.shape[2]
-    with _Prof("gemm_f32", 2.0 * bt * m * n * k):
+    with _Prof("gemm_f32", 2.0 * bt * m * n * k, "b%d m%d n%d k%d t%d" % (bt, m, n, k, int(trans_b))):
         check(_L().ppst_gemm_f32(ptr(out), ptr(a), ptr(b), bt, m, n, k, k, ldb, n, m * k, b.shape[1] * b.shape[2],
                                  m * n, 1 if trans_b else 0, float(alpha), stream()))
     return out
@@ -327,4 +333,52 @@ def corr_prepare(x_rows, c_center):
     c = x_rows.shape[-1]
     out = torch.empty(x_rows.shape, device=x_rows.device, dtype=torch.float32)
     check(_L().ppst_corr_prepare(ptr(out), ptr(x_rows), x_rows.numel() // c, c, c_center, dt(x_rows), stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- split tensor-core GEMM
+def corr_prepare_split(x_rows, c_center):
+    """corr_prepare with [hi | lo] bf16 output: [..., c] -> bf16 [..., 2c]."""
+    require_cuda(x_rows)
+    x_rows = x_rows.contiguous()
+    c = x_rows.shape[-1]
+    out = torch.empty(x_rows.shape[:-1] + (2 * c,), device=x_rows.device, dtype=torch.bfloat16)
+    check(_L().ppst_corr_prepare_split(ptr(out), ptr(x_rows), x_rows.numel() // c, c, c_center, dt(x_rows), stream()))
+    return out
+
+
+def split_bf16(x, transpose=False):
+    """f32 [b, rows, cols] -> bf16 [b, rows, 2*cols] ([hi | lo]);  transpose: -> bf16 [b, cols, 2*rows]."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    b, r, c = x.shape
+    out = torch.empty((b, c, 2 * r) if transpose else (b, r, 2 * c), device=x.device, dtype=torch.bfloat16)
+    check(_L().ppst_split_bf16(ptr(out), ptr(x), b, r, c, 1 if transpose else 0, stream()))
+    return out
+
+
+def softmax_rows_split(logits, divisor):
+    """softmax(logits / divisor, -1) as [hi | lo] bf16: f32 [..., cols] -> bf16 [..., 2*cols]."""
+    require_cuda(logits)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    cols = logits.shape[-1]
+    out = torch.empty(logits.shape[:-1] + (2 * cols,), device=logits.device, dtype=torch.bfloat16)
+    check(_L().ppst_softmax_rows_split(ptr(out), ptr(logits), logits.numel() // cols, cols, float(divisor), stream()))
+    return out
+
+
+def gemm_split_tc(a_split, b_split, m_hw, out=None):
+    """C[b] = A[b] . B[b]^T with fp32-level accuracy on the tensor cores (3-term bf16 split).
+    a_split: bf16 [b, M, 2K] ([hi | lo]), M = m_hw[0] * m_hw[1];  b_split: bf16 [b, N, 2K];  -> f32 [b, M, N].
+    Runs ppst_conv_tc as a 1x1 'convolution' over an [b, m_h, m_w, 2K] image with per-sample weights."""
+    require_cuda(a_split, b_split)
+    bt, M, k2 = a_split.shape
+    N = b_split.shape[1]
+    assert b_split.shape == (bt, N, k2) and M == m_hw[0] * m_hw[1]
+    if out is None:
+        out = torch.empty((bt, M, N), device=a_split.device, dtype=torch.float32)
+    d = conv_desc((bt, m_hw[0], m_hw[1], k2), N, 1, 1, out_hw=m_hw, in_dtype=BF16, out_dtype=F32, w_img_rows=N,
+                  split_terms=3)
+    with _Prof("gemm_split_tc", 2.0 * bt * M * N * (k2 // 2) * 3, "b%d m%d n%d k%d" % (bt, M, N, k2 // 2)):
+        check(_L().ppst_conv_tc(ptr(out), ptr(a_split), ptr(b_split), None, None, None, ctypes.byref(d), stream()))
     return out

@@ -469,3 +469,30 @@ def test_rselfcorr_and_corr_prepare():
     ff = torch.cat((h1, ff[:, 256:]), 1)
     ff = ff / (ff.pow(2).sum(1, keepdim=True).sqrt() + 2.220446049250313e-16)
     assert (prep - ff[0].t()).abs().max() <= 1e-6
+
+
+def test_split_gemm_on_tensor_cores_is_fp32_accurate():
+    """corrm logits and corr @ feat in bf16 mode: hi*hi + hi*lo + lo*hi on tcgen05 (ppst_conv_tc, split_terms=3)."""
+    from ppst_b200 import ops
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    g = gen(101)
+    a = torch.randn(2, 256, 512, generator=g) / math.sqrt(512)
+    b = torch.randn(2, 320, 512, generator=g) / math.sqrt(512)
+    want = (a.double() @ b.double().transpose(1, 2)).float()
+    got = ops.gemm_split_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(b.to(DEV)), (4, 64)).cpu()
+    assert (got - want).abs().max() <= 2e-5 * float(want.abs().max()) + 1e-6
+    # transposed split (NHWC feature map -> K-major B operand) and the split softmax
+    f = torch.randn(2, 512, 96, generator=g)
+    corr = torch.softmax(torch.randn(2, 128, 512, generator=g) * 3, -1)
+    want = (corr.double() @ f.double()).float()
+    got = ops.gemm_split_tc(ops.split_bf16(corr.to(DEV)), ops.split_bf16(f.to(DEV), transpose=True), (2, 64)).cpu()
+    assert (got - want).abs().max() <= 2e-5
+    logits = torch.randn(64, 4096, generator=g) * 0.3
+    sp = ops.softmax_rows_split(logits.to(DEV), 0.01).float().cpu()
+    rec = sp[:, :4096] + sp[:, 4096:]
+    assert (rec - F.softmax(logits / 0.01, -1)).abs().max() <= 1e-5
+    x = torch.randn(1, 8, 8, 512, generator=g)
+    sp = ops.corr_prepare_split(x.to(DEV), 256).float().cpu().view(64, 1024)
+    ref = ops.corr_prepare(x.to(DEV), 256).cpu().view(64, 512)
+    assert (sp[:, :512] + sp[:, 512:] - ref).abs().max() <= 1e-6
