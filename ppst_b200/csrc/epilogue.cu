@@ -204,15 +204,46 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(TO* __restrict__ out,
   }
 }
 
+// 8 channels of T kept PACKED in registers (4 regs for bf16, 8 for f32) until they are consumed
+template <typename T> struct Raw8 { uint4 q[sizeof(T) / 2]; };
+template <typename T>
+__device__ __forceinline__ Raw8<T> ld_raw8(const T* p) {
+  Raw8<T> r;
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 2); ++i) {
+    const uint4* src = reinterpret_cast<const uint4*>(p) + i;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.q[i].x), "=r"(r.q[i].y), "=r"(r.q[i].z), "=r"(r.q[i].w)
+                 : "l"(src));
+  }
+  return r;
+}
+__device__ __forceinline__ void cvt8(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.q[0].x, r.q[0].y, r.q[0].z, r.q[0].w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void cvt8(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = __uint_as_float(r.q[0].x); f[1] = __uint_as_float(r.q[0].y); f[2] = __uint_as_float(r.q[0].z);
+  f[3] = __uint_as_float(r.q[0].w); f[4] = __uint_as_float(r.q[1].x); f[5] = __uint_as_float(r.q[1].y);
+  f[6] = __uint_as_float(r.q[1].z); f[7] = __uint_as_float(r.q[1].w);
+}
+
 // Row-oriented variant for c % 8 == 0 (the hot path): one block per output row of one image; a thread owns ONE group of
-// 8 channels (its a/b coefficients stay in registers) and walks along the row, so the per-element work is one 16-byte
-// load, 8 FMAs and one 16-byte store with no integer division and no coefficient reloads.
-template <typename TX, typename TO>
-__global__ void __launch_bounds__(256) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
-                                                                const float* __restrict__ a, const float* __restrict__ b,
-                                                                const TX* __restrict__ res, const float* __restrict__ ra,
-                                                                const float* __restrict__ rb, ppst_apply_desc d) {
+// 8 channels (its a/b coefficients stay in registers) and walks along the row.  Per element: one 16-byte load, 8 FMAs,
+// one 16-byte store; no integer division, no coefficient reloads.  U pixels are in flight per thread (loads issued
+// before any use, data kept packed) and the residual mode is a template parameter so that the common no-residual
+// instance stays small enough for 3+ resident blocks per SM.
+template <typename TX, typename TO, int RES>
+__global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
+                                                                   const float* __restrict__ a, const float* __restrict__ b,
+                                                                   const TX* __restrict__ res, const float* __restrict__ ra,
+                                                                   const float* __restrict__ rb, ppst_apply_desc d) {
   constexpr int V = 8;
+  constexpr int U = 4;
   const int cv = d.c / V;
   const int lanes = 256 / cv;
   const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
@@ -221,77 +252,89 @@ __global__ void __launch_bounds__(256) affine_apply_rows_kernel(TO* __restrict__
   const int ch = cg * V;
   const int hu = d.h * d.up, wu = d.w * d.up;
   const int oh = hu + d.pad_t + d.pad_b, ow = wu + d.pad_l + d.pad_r;
-  float av[V], bv[V], rav[V], rbv[V];
+  float av[V], bv[V];
 #pragma unroll
-  for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; rav[e] = 1.0f; rbv[e] = 0.0f; }
+  for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; }
   if (a) load_ch<float, V>(av, a + (int64_t)ni * d.c + ch);
   if (b) load_ch<float, V>(bv, b + (int64_t)ni * d.c + ch);
-  if (ra) load_ch<float, V>(rav, ra + (int64_t)ni * d.c + ch);
-  if (rb) load_ch<float, V>(rbv, rb + (int64_t)ni * d.c + ch);
+  float rav[RES ? V : 1], rbv[RES ? V : 1];
+  if (RES) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { rav[e] = 1.0f; rbv[e] = 0.0f; }
+    if (ra) load_ch<float, V>(*reinterpret_cast<float(*)[V]>(rav), ra + (int64_t)ni * d.c + ch);
+    if (rb) load_ch<float, V>(*reinterpret_cast<float(*)[V]>(rbv), rb + (int64_t)ni * d.c + ch);
+  }
   bool zero_row = false;
   const int uy = map_pad(oy - d.pad_t, hu, d.pad_mode, zero_row);
-  const int iy = uy / d.up;
-  const TX* xrow = x + (((int64_t)ni * d.h + iy) * d.w) * d.c + ch;
+  const TX* xrow = x + (((int64_t)ni * d.h + uy / d.up) * d.w) * d.c + ch;
   TO* orow = out + (((int64_t)ni * oh + oy) * ow) * d.out_c_stride + d.out_c_off + ch;
   const TX* r0 = nullptr;
   const TX* r1 = nullptr;
   Bilin2 by{0, 0, 1.f, 0.f};
   const int lw = wu / 2;
-  if (d.res_mode == 1) {
+  if (RES == 1) {
     r0 = res + (((int64_t)ni * hu + uy) * wu) * d.c + ch;
-  } else if (d.res_mode == 2) {
+  } else if (RES == 2) {
     const int lh = hu / 2;
     by = bilin_x2(uy, lh);
     r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
     r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
   }
-  constexpr int U = 4;                       // pixels in flight per thread: all loads of a batch are issued first
+  const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
   for (int ox0 = lane; ox0 < ow; ox0 += U * lanes) {
-    float xv[U][V], rv[U][V];
+    Raw8<TX> xr[U], rr[RES == 1 ? U : 1];
     int uxs[U];
-    bool live[U], zero[U];
+    unsigned live = 0, zero = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int ox = ox0 + u * lanes;
-      live[u] = ox < ow;
-      zero[u] = zero_row;
-      uxs[u] = map_pad(ox - d.pad_l, wu, d.pad_mode, zero[u]);
-      if (live[u] && !zero[u]) {
-        load_ch<TX, V>(xv[u], xrow + (int64_t)(uxs[u] / d.up) * d.c);
-        if (d.res_mode == 1) load_ch<TX, V>(rv[u], r0 + (int64_t)uxs[u] * d.c);
+      bool z = zero_row;
+      uxs[u] = map_pad(ox - d.pad_l, wu, d.pad_mode, z);
+      if (ox < ow) live |= 1u << u;
+      if (z) zero |= 1u << u;
+      if (ox < ow && !z) {
+        xr[u] = ld_raw8<TX>(xrow + (int64_t)(uxs[u] / d.up) * d.c);
+        if (RES == 1) rr[u] = ld_raw8<TX>(r0 + (int64_t)uxs[u] * d.c);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (!live[u]) continue;
-      const int ox = ox0 + u * lanes;
+      if (!((live >> u) & 1)) continue;
       float y[V];
-      if (zero[u]) {
+      if ((zero >> u) & 1) {
 #pragma unroll
         for (int e = 0; e < V; ++e) y[e] = 0.0f;
       } else {
+        cvt8(xr[u], y);
 #pragma unroll
-        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[u][e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
-        if (d.res_mode == 1) {
+        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(y[e], av[e], bv[e]), pre_slope) * pre_gain;
+        if (RES == 1) {
+          float rv[V];
+          cvt8(rr[u], rv);
 #pragma unroll
-          for (int e = 0; e < V; ++e) y[e] += fmaf(rv[u][e], rav[e], rbv[e]);
-        } else if (d.res_mode == 2) {
+          for (int e = 0; e < V; ++e) y[e] += fmaf(rv[e], rav[e], rbv[e]);
+        } else if (RES == 2) {
           const Bilin2 bx = bilin_x2(uxs[u], lw);
-          float v00[V], v01[V], v10[V], v11[V];
-          load_ch<TX, V>(v00, r0 + (int64_t)bx.i0 * d.c);
-          load_ch<TX, V>(v01, r0 + (int64_t)bx.i1 * d.c);
-          load_ch<TX, V>(v10, r1 + (int64_t)bx.i0 * d.c);
-          load_ch<TX, V>(v11, r1 + (int64_t)bx.i1 * d.c);
+          const Raw8<TX> q00 = ld_raw8<TX>(r0 + (int64_t)bx.i0 * d.c), q01 = ld_raw8<TX>(r0 + (int64_t)bx.i1 * d.c);
+          const Raw8<TX> q10 = ld_raw8<TX>(r1 + (int64_t)bx.i0 * d.c), q11 = ld_raw8<TX>(r1 + (int64_t)bx.i1 * d.c);
+          float t0[V], t1[V];
+          cvt8(q00, t0);
+          cvt8(q01, t1);
+          float rv[V];
+#pragma unroll
+          for (int e = 0; e < V; ++e) rv[e] = by.l0 * (bx.l0 * t0[e] + bx.l1 * t1[e]);
+          cvt8(q10, t0);
+          cvt8(q11, t1);
 #pragma unroll
           for (int e = 0; e < V; ++e) {
-            const float r = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
+            const float r = rv[e] + by.l1 * (bx.l0 * t0[e] + bx.l1 * t1[e]);
             y[e] += fmaf(r, rav[e], rbv[e]);
           }
         }
 #pragma unroll
-        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
+        for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], post_slope) * post_gain;
       }
-      store_ch<TO, V>(orow + (int64_t)ox * d.out_c_stride, y);
+      store_ch<TO, V>(orow + (int64_t)(ox0 + u * lanes) * d.out_c_stride, y);
     }
   }
 }
@@ -403,9 +446,15 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
                       reinterpret_cast<uintptr_t>(rb)) & 15) == 0;
 #define PPST_APPLY(TX, TO)                                                                                           \
   do {                                                                                                               \
-    if (rows)                                                                                                        \
-      affine_apply_rows_kernel<TX, TO><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, \
-                                                                       ra, rb, d);                                   \
+    if (rows && d.res_mode == 0)                                                                                     \
+      affine_apply_rows_kernel<TX, TO, 0><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b,              \
+                                                                          (const TX*)res, ra, rb, d);                \
+    else if (rows && d.res_mode == 1)                                                                                \
+      affine_apply_rows_kernel<TX, TO, 1><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b,              \
+                                                                          (const TX*)res, ra, rb, d);                \
+    else if (rows)                                                                                                   \
+      affine_apply_rows_kernel<TX, TO, 2><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b,              \
+                                                                          (const TX*)res, ra, rb, d);                \
     else if (vec)                                                                                                    \
       affine_apply_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d); \
     else                                                                                                             \
