@@ -11,7 +11,9 @@
 //     tile i+1.  Epilogue: tcgen05.ld -> + bias + noise -> leaky-ReLU * gain -> bf16 -> 16-byte global stores, plus
 //     per-channel partial sum / sum-of-squares of the stored values (instance-norm statistics for free).
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-//     warps 4-7 = epilogue (TMEM lane quadrant = warp % 4).  Persistent grid: one CTA per SM, static tile striding.
+//     warps 4-7 and 8-11 = two epilogue groups (TMEM lane quadrant = warp % 4), one per accumulator stage, so a tile's
+//     epilogue may take up to two tiles' worth of MMA time before it stalls the tensor pipe.
+//     Persistent grid: one CTA per SM, static tile striding.
 #include <cuda.h>
 
 #include <mutex>
@@ -27,8 +29,9 @@ int validate_conv_desc(const ppst_conv_desc& d, const char* who);
 
 namespace tc {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;           // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kEpiWarp0 = 4;            // first epilogue warp
+constexpr int kBiasSmem = 1024;         // bias values staged in shared memory (larger cout: read from global)
 constexpr int BM = 128;
 
 struct Params {
@@ -46,6 +49,7 @@ struct Params {
   int stats_partials;                   // partial slots per image = tiles_y*tiles_x*phases
   int w_img_rows;                       // weight rows per image (0: one weight matrix for the whole batch)
   int split_seg_kb;                     // 3-term split GEMM: k-blocks per [hi]/[lo] segment (0: plain)
+  int stages, kps;                      // pipeline depth; k-blocks per pipeline stage (one barrier round trip each)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -188,28 +192,36 @@ __device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int BN, int BKC, int STAGES>
+constexpr int kMaxStages = 8;
+template <int BN, int BKC>
 struct Smem {
   static constexpr int kABytes = BM * BKC * 2;
   static constexpr int kBBytes = BN * BKC * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kKblockBytes = kABytes + kBBytes;     // one k-block: A tile then B tile (both 1024-aligned)
   static constexpr int kStatsBytes = 2 /*buf*/ * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
-  static constexpr int kBarOffset = STAGES * kStageBytes + kStatsBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  static constexpr int kBiasBytes = kBiasSmem * 4;
+  static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*align slack*/;
+  static constexpr int kMaxDynamic = 232448 - 1024 /*static*/;
 };
 
-template <int BN, int BKC, int STAGES, bool OUT_F32>
+template <int BN, int BKC, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                void* __restrict__ out_raw, const float* __restrict__ bias, const float* __restrict__ noise,
                float* __restrict__ stats_sum, float* __restrict__ stats_sq, const Params p) {
-  using S = Smem<BN, BKC, STAGES>;
+  using S = Smem<BN, BKC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_stats = reinterpret_cast<float*>(smem + STAGES * S::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  const int STAGES = p.stages;
+  const int stage_bytes = p.kps * S::kKblockBytes;
+  float* s_stats = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + S::kStatsBytes);
+  const bool bias_in_smem = (bias != nullptr) && (p.cout <= kBiasSmem);
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias[i];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + S::kStatsBytes + S::kBiasBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -262,25 +274,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int iy0 = ty * p.th * p.stride + p.off_y + py * p.phase_off_dy;
         const int ix0 = tx * p.tw * p.stride + p.off_x + px * p.phase_off_dx;
         const int brow = img * p.w_img_rows + ph * p.cout + nt * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          int tap, ca, cbk;
-          if (p.split_seg_kb) {
-            const int seg = kb / p.split_seg_kb, r = kb - seg * p.split_seg_kb;
-            tap = 0;
-            ca = ((seg == 2 ? p.split_seg_kb : 0) + r) * BKC;        // A: hi, hi, lo
-            cbk = ((seg == 1 ? p.split_seg_kb : 0) + r) * BKC;       // B: hi, lo, hi
-          } else {
-            tap = kb / p.kblocks_per_tap;
-            ca = (kb - tap * p.kblocks_per_tap) * BKC;
-            cbk = tap * p.cin + ca;
-          }
-          const int ky = tap / p.kw, kx = tap - ky * p.kw;
+        int tap = 0, cb = 0, ky = 0, kx = 0;                 // incremental (tap, channel block) decode: no div/mod
+        for (int kb0 = 0; kb0 < kblocks; kb0 += p.kps) {
+          const int nk = min(p.kps, kblocks - kb0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::kStageBytes;
-          uint8_t* sb = sa + S::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-          tma_load_4d(sa, &map_a, &full_bar[stage], ca, ix0 + kx, iy0 + ky, img);
-          tma_load_2d(sb, &map_b, &full_bar[stage], cbk, brow);
+          uint8_t* sbase = smem + stage * stage_bytes;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(nk * S::kKblockBytes));
+          for (int j = 0; j < nk; ++j) {
+            int ca, cbk;
+            if (p.split_seg_kb) {
+              const int kb = kb0 + j;
+              const int seg = kb / p.split_seg_kb, r = kb - seg * p.split_seg_kb;
+              ca = ((seg == 2 ? p.split_seg_kb : 0) + r) * BKC;        // A: hi, hi, lo
+              cbk = ((seg == 1 ? p.split_seg_kb : 0) + r) * BKC;       // B: hi, lo, hi
+            } else {
+              ca = cb * BKC;
+              cbk = tap * p.cin + ca;
+            }
+            uint8_t* sa = sbase + j * S::kKblockBytes;
+            tma_load_4d(sa, &map_a, &full_bar[stage], ca, ix0 + kx, iy0 + ky, img);
+            tma_load_2d(sa + S::kABytes, &map_b, &full_bar[stage], cbk, brow);
+            if (!p.split_seg_kb && ++cb == p.kblocks_per_tap) {
+              cb = 0; ++tap;
+              if (++kx == p.kw) { kx = 0; ++ky; }
+            }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -298,16 +316,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty[as], aphase ^ 1);          // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb0 = 0; kb0 < kblocks; kb0 += p.kps) {
+          const int nk = min(p.kps, kblocks - kb0);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::kStageBytes);
-          const uint64_t da = make_smem_desc<BKC>(sa);
-          const uint64_t db = make_smem_desc<BKC>(sa + S::kABytes);
+          const uint32_t sbase = smem_u32(smem + stage * stage_bytes);
+          for (int j = 0; j < nk; ++j) {
+            const uint32_t sa = sbase + (uint32_t)(j * S::kKblockBytes);
+            const uint64_t da = make_smem_desc<BKC>(sa);
+            const uint64_t db = make_smem_desc<BKC>(sa + S::kABytes);
 #pragma unroll
-          for (int k = 0; k < BKC / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte address field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BKC / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the 16-byte address field
+              umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, ((kb0 + j) | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);                 // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -318,10 +340,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp >= kEpiWarp0) {
     // ===================== epilogue =====================
     const int q = warp & 3;                              // TMEM lane quadrant
+    const int group = (warp - kEpiWarp0) >> 2;           // epilogue group == accumulator stage it serves
     const int row = q * 32 + lane;                       // row of the 128-pixel tile
     const int ety = row / p.tw, etx = row - ety * p.tw;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
       int nt, ph, tx, ty, img;
       decode(tile, nt, ph, tx, ty, img);
       const int py = ph / p.phases_x, px = ph % p.phases_x;
@@ -346,7 +370,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(r[j]) + (bias ? __ldg(bias + nt * BN + c0 + j) : 0.0f) + nz;
+          const float bj = bias_in_smem ? s_bias[nt * BN + c0 + j] : (bias ? __ldg(bias + nt * BN + c0 + j) : 0.0f);
+          float a = __uint_as_float(r[j]) + bj + nz;
           if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
           v[j] = a * p.gain;
         }
@@ -390,8 +415,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
 
       if (!OUT_F32 && stats_sum != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps
-        const int e = threadIdx.x - kEpiWarp0 * 32;
+        if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 warps of this group
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int e = (threadIdx.x - kEpiWarp0 * 32) & 127;
         const float* b_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN;
         const float* b_sq = s_stats + (size_t)(as * 2 + 1) * 4 * BN;
         const int slot = ((ty * p.tiles_x + tx) * n_phases + ph);
@@ -490,10 +516,10 @@ static void pick_tile(int out_h, int out_w, int& th, int& tw) {
 
 static int g_num_sms = 0;
 
-template <int BN, int BKC, int STAGES, bool OUT_F32>
+template <int BN, int BKC, bool OUT_F32>
 static int launch(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
                   const float* noise, float* stats, cudaStream_t st) {
-  using S = Smem<BN, BKC, STAGES>;
+  using S = Smem<BN, BKC>;
   Params p;
   p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
   p.kh = d.kh; p.kw = d.kw; p.stride = d.stride;
@@ -508,6 +534,19 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_tc: too many tiles");
   p.num_tiles = (int)tiles;
   p.kblocks_per_tap = d.cin / BKC;
+  {
+    // k-blocks per stage: enough bytes per barrier round trip (the single-thread producer / issuer loops cost a few
+    // hundred cycles per iteration whatever the tile size), as few iterations as possible, deepest pipeline that fits
+    const int kblocks = d.split_terms == 3 ? 3 * ((d.cin / 2) / BKC) : d.kh * d.kw * (d.cin / BKC);
+    const int kps_max = 49152 / S::kKblockBytes > 0 ? 49152 / S::kKblockBytes : 1;
+    const int iters = (kblocks + kps_max - 1) / kps_max;
+    p.kps = (kblocks + iters - 1) / iters;
+    const int stage_bytes = p.kps * S::kKblockBytes;
+    int stages = (S::kMaxDynamic - S::kFixedBytes) / stage_bytes;
+    p.stages = stages > kMaxStages ? kMaxStages : stages;
+    PPST_REQUIRE(p.stages >= 2, PPST_ERR_UNSUPPORTED, "conv_tc: pipeline does not fit in shared memory");
+  }
+  const int smem_total = p.stages * p.kps * S::kKblockBytes + S::kFixedBytes;
   p.w_img_rows = d.w_img_rows;
   p.split_seg_kb = d.split_terms == 3 ? (d.cin / 2) / BKC : 0;
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
@@ -539,10 +578,10 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
   }
-  auto kern = conv_tc_kernel<BN, BKC, STAGES, OUT_F32>;
+  auto kern = conv_tc_kernel<BN, BKC, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal),
+    int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kMaxDynamic),
                         "cudaFuncSetAttribute(conv_tc)");
     if (rc) return rc;
     attr_set = true;
@@ -550,7 +589,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   float* ssum = stats;
   float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
-  kern<<<grid, kThreads, S::kTotal, st>>>(map_a, map_b, out, bias, noise, ssum, ssq, p);
+  kern<<<grid, kThreads, smem_total, st>>>(map_a, map_b, out, bias, noise, ssum, ssq, p);
   PPST_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
 }
@@ -596,20 +635,20 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
                PPST_ERR_ARG, "conv_tc: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const bool k64 = (d.cin % 64 == 0);
-#define PPST_TC(BN_, BKC_, ST_)                                                                   \
-  do {                                                                                            \
-    if (d.out_dtype == PPST_F32)                                                                  \
-      return tc::launch<BN_, BKC_, ST_, true>(d, out, in, weight, bias, noise, stats, st);        \
-    return tc::launch<BN_, BKC_, ST_, false>(d, out, in, weight, bias, noise, stats, st);         \
+#define PPST_TC(BN_, BKC_)                                                                   \
+  do {                                                                                       \
+    if (d.out_dtype == PPST_F32)                                                             \
+      return tc::launch<BN_, BKC_, true>(d, out, in, weight, bias, noise, stats, st);        \
+    return tc::launch<BN_, BKC_, false>(d, out, in, weight, bias, noise, stats, st);         \
   } while (0)
   if (k64) {
-    if (d.cout % 256 == 0) PPST_TC(256, 64, 4);
-    if (d.cout % 128 == 0) PPST_TC(128, 64, 6);
-    if (d.cout % 64 == 0) PPST_TC(64, 64, 8);
-    PPST_TC(32, 64, 8);
+    if (d.cout % 256 == 0) PPST_TC(256, 64);
+    if (d.cout % 128 == 0) PPST_TC(128, 64);
+    if (d.cout % 64 == 0) PPST_TC(64, 64);
+    PPST_TC(32, 64);
   } else {
-    if (d.cout % 64 == 0) PPST_TC(64, 32, 8);
-    PPST_TC(32, 32, 8);
+    if (d.cout % 64 == 0) PPST_TC(64, 32);
+    PPST_TC(32, 32);
   }
 #undef PPST_TC
 }
