@@ -25,78 +25,233 @@ struct UpfirdnParams {
 
 constexpr int kMaxTaps = 32 * 32;
 
-// ---- fast path: up = 1, down = 1, minor = 1, kernel <= KMAX x KMAX (modes 1 and 2 of the reference; the
-//      encoder / discriminator blur).  Tile = 32 rows x 128 cols of outputs per 256-thread block.
-template <typename T, int KMAX>
-__global__ void __launch_bounds__(256) upfirdn2d_blur_kernel(T* __restrict__ out, const T* __restrict__ in,
-                                                             const float* __restrict__ kernel, UpfirdnParams p) {
-  constexpr int TH = 32, TW = 128, PER = 4;          // outputs per thread along x
-  constexpr int IH = TH + KMAX - 1, IW = TW + KMAX - 1;
-  constexpr int IWP = 132;                           // row pitch: multiple of 4 floats, >= 124 + 8
-  static_assert(IW <= IWP && PER + KMAX - 1 <= 8, "window must fit two float4 reads");
-  __shared__ float sk[KMAX][KMAX];
-  __shared__ __align__(16) float sx[IH][IWP];
+// ---- mbarrier / bulk-copy primitives (1-D TMA: cp.async.bulk, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+// ---- fast path: up = 1, down = 1, minor = 1, kernel <= 4 x 4 (modes 1 and 2 of the reference: the encoder /
+//      discriminator blur).  One block = one plane x one strip of R output rows x the full width, so the input rows
+//      the strip needs are ONE contiguous span of the plane.  One thread moves the 16-byte-aligned interior of that
+//      span into shared memory with a single bulk copy (no LSU wavefronts, no registers, all bytes in flight at once,
+//      DRAM sees a ~40 KB burst); the <= 2 ragged ends are copied by a few scalar loads.  Shared memory holds the raw
+//      span (element type T, row pitch in_w); the zero padding is applied by predicates, only in threads whose window
+//      touches the image border.  Each thread slides its window down RR rows of one column, lanes on consecutive
+//      columns: conflict-free LDS, and 128-byte coalesced stores whatever the row alignment (2^n+1-wide rows are the
+//      hot case).  KS = 3 / 4: exact square taps in registers; KS = 0: run-time kh, kw <= 4.
+template <typename T, int KS>
+__global__ void __launch_bounds__(256, 4) upfirdn2d_bulk_kernel(T* __restrict__ out, const T* __restrict__ in,
+                                                                const float* __restrict__ kernel, UpfirdnParams p,
+                                                                int R, int nstrips) {
+  constexpr int RR = 8;                              // output rows per thread (vertical sliding window)
+  constexpr int KM = KS ? KS : 4;
+  constexpr int VEC = 16 / sizeof(T);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  T* sm = reinterpret_cast<T*>(smem_raw + 16);
   const int tid = threadIdx.x;
-  const int64_t plane = blockIdx.x;
-  const int oy0 = blockIdx.y * TH, ox0 = blockIdx.z * TW;
-  if (tid < KMAX * KMAX) {
-    const int ky = tid / KMAX, kx = tid % KMAX;
-    // flipped taps, zero-extended to KMAX x KMAX
-    sk[ky][kx] = (ky < p.kh && kx < p.kw) ? kernel[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.0f;
+  const int strip = blockIdx.x % nstrips;
+  const int64_t plane = blockIdx.x / nstrips;
+  const int oy0 = strip * R;
+  const int rows = min(R, p.out_h - oy0);
+  const int kh = KS ? KS : p.kh, kw = KS ? KS : p.kw;
+  // staged input rows [iyA, iyB)
+  const int iyA = max(0, oy0 - p.py0), iyB = min(p.in_h, oy0 - p.py0 + rows + kh - 1);
+  const int64_t n = iyB > iyA ? (int64_t)(iyB - iyA) * p.in_w : 0;
+  const T* g = in + (plane * p.in_h + iyA) * (int64_t)p.in_w;      // first staged element
+  const int mis = (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) & (VEC - 1));
+  // element g[i] lives at sm[mis + i]; the bulk copy covers i in [head, head + body)
+  const int64_t head = n < ((VEC - mis) & (VEC - 1)) ? n : ((VEC - mis) & (VEC - 1));
+  const int64_t body = (n - head) / VEC * VEC;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (uint32_t)(body * sizeof(T)));
+    if (body) bulk_g2s(sm + mis + head, g + head, (uint32_t)(body * sizeof(T)), bar);
+  } else if (tid >= 32 && tid < 32 + 2 * VEC) {
+    const int j = tid - 32;
+    const int64_t i = j < VEC ? j : head + body + (j - VEC);
+    if (j < VEC ? i < head : i < n) sm[mis + i] = g[i];
   }
-  const int iy0 = oy0 - p.py0, ix0 = ox0 - p.px0;
+  // flipped taps in registers
+  float k[KM][KM];
+#pragma unroll
+  for (int ky = 0; ky < KM; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < KM; ++kx)
+      k[ky][kx] = (ky < kh && kx < kw) ? __ldg(kernel + (kh - 1 - ky) * kw + (kw - 1 - kx)) : 0.0f;
+  __syncthreads();          // barrier initialised, ragged ends visible
+  mbar_wait(bar, 0);        // bulk bytes landed
+
+  const int cols = p.out_w;
+  const int nitems = ((rows + RR - 1) / RR) * cols;
+  T* dst = out + plane * (int64_t)p.out_h * p.out_w;
+  for (int idx = tid; idx < nitems; idx += 256) {
+    const int rg = idx / cols, c = idx - rg * cols;
+    const int oyb = oy0 + rg * RR;
+    const int xb = c - p.px0, yb = oyb - p.py0;           // input coordinate of tap (0, 0) of the item's first output
+    const T* sp = sm + mis + (yb - iyA) * p.in_w + xb;   // only dereferenced where the predicates hold
+    float acc[RR];
+#pragma unroll
+    for (int o = 0; o < RR; ++o) acc[o] = 0.0f;
+    const bool interior = xb >= 0 && xb + kw <= p.in_w && yb >= iyA && yb + RR + kh - 1 <= iyB;
+    if (interior) {
+#pragma unroll
+      for (int r = 0; r < RR + KM - 1; ++r) {
+        if (KS == 0 && r >= RR + kh - 1) break;
+        float v[KM];
+#pragma unroll
+        for (int kx = 0; kx < KM; ++kx)
+          if (KS != 0 || kx < kw) v[kx] = Cvt<T>::to_f(sp[r * p.in_w + kx]);
+#pragma unroll
+        for (int o = 0; o < RR; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < KM && (KS != 0 || ky < kh)) {
+#pragma unroll
+            for (int kx = 0; kx < KM; ++kx)
+              if (KS != 0 || kx < kw) acc[o] = fmaf(v[kx], k[ky][kx], acc[o]);
+          }
+        }
+      }
+    } else {
+      bool cok[KM];
+#pragma unroll
+      for (int kx = 0; kx < KM; ++kx) cok[kx] = kx < kw && xb + kx >= 0 && xb + kx < p.in_w;
+#pragma unroll
+      for (int r = 0; r < RR + KM - 1; ++r) {
+        const int y = yb + r;
+        const bool rok = r < RR + kh - 1 && y >= iyA && y < iyB;
+        float v[KM];
+#pragma unroll
+        for (int kx = 0; kx < KM; ++kx) v[kx] = (rok && cok[kx]) ? Cvt<T>::to_f(sp[r * p.in_w + kx]) : 0.0f;
+#pragma unroll
+        for (int o = 0; o < RR; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < KM && (KS != 0 || ky < kh)) {
+#pragma unroll
+            for (int kx = 0; kx < KM; ++kx)
+              if (KS != 0 || kx < kw) acc[o] = fmaf(v[kx], k[ky][kx], acc[o]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < RR; ++o)
+      if (oyb + o < p.out_h) dst[(int64_t)(oyb + o) * p.out_w + c] = Cvt<T>::from_f(acc[o]);
+  }
+}
+
+// ---- register-staged variant of the up = down = 1 path for rows too long for the bulk-copy kernel above
+//      (strip x column-chunk tiles, fp32 tile in shared memory with the zero padding materialised).
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256, 5) upfirdn2d_strip_kernel(T* __restrict__ out, const T* __restrict__ in,
+                                                              const float* __restrict__ kernel, UpfirdnParams p,
+                                                              int R, int CW, int nstrips, int nchunks) {
+  constexpr int RR = 4;                              // output rows per thread (vertical sliding window)
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int UNR = 4;                             // 16-byte loads in flight per lane while staging a row
+  extern __shared__ __align__(16) float sx[];        // (R + KMAX - 1) x P
+  const int P = CW + KMAX - 1;
+  const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+  unsigned b = blockIdx.x;
+  const int strip = b % nstrips; b /= nstrips;
+  const int chunk = b % nchunks;
+  const int64_t plane = b / nchunks;
+  const int oy0 = strip * R, ox0 = chunk * CW;
+  const int rows = min(R, p.out_h - oy0), cols = min(CW, p.out_w - ox0);
+  // flipped taps, zero-extended to KMAX x KMAX, in registers
+  float k[KMAX][KMAX];
+#pragma unroll
+  for (int ky = 0; ky < KMAX; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < KMAX; ++kx)
+      k[ky][kx] = (ky < p.kh && kx < p.kw) ? __ldg(kernel + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)) : 0.0f;
+
+  // ---- stage: smem (r, s) <- input (oy0 - py0 + r, ox0 - px0 + s), zero outside the image / the needed window
   const T* src = in + plane * (int64_t)p.in_h * p.in_w;
-  const int need_h = min(TH, p.out_h - oy0) + p.kh - 1;
-  const int need_w = min(TW, p.out_w - ox0) + p.kw - 1;
-  for (int idx = tid; idx < IH * IWP; idx += 256) {
-    const int ry = idx / IWP, rx = idx - ry * IWP;
-    const int y = iy0 + ry, x = ix0 + rx;
-    float v = 0.0f;
-    if (ry < need_h && rx < need_w && y >= 0 && y < p.in_h && x >= 0 && x < p.in_w)
-      v = Cvt<T>::to_f(src[(int64_t)y * p.in_w + x]);
-    sx[ry][rx] = v;
+  const int need_h = rows + p.kh - 1, need_w = cols + p.kw - 1;
+  const int tile_h = R + KMAX - 1;
+  const int s_lo = max(0, p.px0 - ox0);
+  const int s_hi = min(need_w, p.in_w + p.px0 - ox0);
+  for (int r = wrp; r < tile_h; r += 8) {
+    float* row = sx + r * P;
+    const int y = oy0 - p.py0 + r;
+    if (r >= need_h || y < 0 || y >= p.in_h || s_hi <= s_lo) {
+      for (int s = lane; s < P; s += 32) row[s] = 0.0f;
+      continue;
+    }
+    for (int s = lane; s < s_lo; s += 32) row[s] = 0.0f;
+    for (int s = s_hi + lane; s < P; s += 32) row[s] = 0.0f;
+    const T* rp = src + (int64_t)y * p.in_w + (ox0 - p.px0);        // address of s = 0 (only s in [s_lo, s_hi) is read)
+    const int mis = (int)((reinterpret_cast<uintptr_t>(rp + s_lo) & 15) / sizeof(T));
+    const int sv0 = s_lo - mis;                                     // s of the first 16-byte aligned vector
+    const int nvec = (s_hi - sv0 + VEC - 1) / VEC;
+    for (int v0 = 0; v0 < nvec; v0 += 32 * UNR) {
+      Vec16<T> q[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int s0 = sv0 + (v0 + u * 32 + lane) * VEC;
+        if (s0 >= s_lo && s0 + VEC <= s_hi) {
+          q[u] = ld_vec16_stream(rp + s0);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i)
+            q[u].v[i] = (s0 + i >= s_lo && s0 + i < s_hi) ? rp[s0 + i] : Cvt<T>::from_f(0.0f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int s0 = sv0 + (v0 + u * 32 + lane) * VEC;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (s0 + i >= s_lo && s0 + i < s_hi) row[s0 + i] = Cvt<T>::to_f(q[u].v[i]);
+      }
+    }
   }
   __syncthreads();
-  // thread -> (row group, column quad): 32 quads per row, 8 rows per pass
-  const int qx = (tid & 31) * PER;
-  T* dst = out + plane * (int64_t)p.out_h * p.out_w;
+
+  // ---- compute: item = (row group of RR rows, column); consecutive threads on consecutive columns
+  T* dst = out + plane * (int64_t)p.out_h * p.out_w + ox0;
+  const int nitems = ((rows + RR - 1) / RR) * cols;
+  for (int idx = tid; idx < nitems; idx += 256) {
+    const int rg = idx / cols, c = idx - rg * cols;
+    const float* sp = sx + (rg * RR) * P + c;
+    float acc[RR];
 #pragma unroll
-  for (int pass = 0; pass < TH / 8; ++pass) {
-    const int ry = pass * 8 + (tid >> 5);
-    const int oy = oy0 + ry;
-    float acc[PER] = {0.f, 0.f, 0.f, 0.f};
+    for (int o = 0; o < RR; ++o) acc[o] = 0.0f;
 #pragma unroll
-    for (int ky = 0; ky < KMAX; ++ky) {
-      float win[8];
-      const float4 w0 = *reinterpret_cast<const float4*>(&sx[ry + ky][qx]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&sx[ry + ky][qx + 4]);
-      win[0] = w0.x; win[1] = w0.y; win[2] = w0.z; win[3] = w0.w;
-      win[4] = w1.x; win[5] = w1.y; win[6] = w1.z; win[7] = w1.w;
+    for (int r = 0; r < RR + KMAX - 1; ++r) {
+      float v[KMAX];
 #pragma unroll
-      for (int kx = 0; kx < KMAX; ++kx) {
-        const float w = sk[ky][kx];
+      for (int kx = 0; kx < KMAX; ++kx) v[kx] = sp[r * P + kx];
 #pragma unroll
-        for (int j = 0; j < PER; ++j) acc[j] = fmaf(win[j + kx], w, acc[j]);
-      }
-    }
-    if (oy < p.out_h) {
-      const int ox = ox0 + qx;
-      T* q = dst + (int64_t)oy * p.out_w + ox;
-      if (ox + PER <= p.out_w && (reinterpret_cast<uintptr_t>(q) & (sizeof(T) * PER - 1)) == 0) {
-        if (sizeof(T) == 4) {
-          *reinterpret_cast<float4*>(q) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        } else {
-          union { uint2 u; T t[4]; } pk;
+      for (int o = 0; o < RR; ++o) {
+        const int ky = r - o;
+        if (ky >= 0 && ky < KMAX && ky < p.kh) {
 #pragma unroll
-          for (int j = 0; j < PER; ++j) pk.t[j] = Cvt<T>::from_f(acc[j]);
-          *reinterpret_cast<uint2*>(q) = pk.u;
+          for (int kx = 0; kx < KMAX; ++kx)
+            if (kx < p.kw) acc[o] = fmaf(v[kx], k[ky][kx], acc[o]);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < PER; ++j)
-          if (ox + j < p.out_w) q[j] = Cvt<T>::from_f(acc[j]);
       }
     }
+    const int oy = oy0 + rg * RR;
+#pragma unroll
+    for (int o = 0; o < RR; ++o)
+      if (oy + o < p.out_h) dst[(int64_t)(oy + o) * p.out_w + c] = Cvt<T>::from_f(acc[o]);
   }
 }
 
@@ -193,13 +348,47 @@ template <typename T>
 static int launch_upfirdn2d(T* y, const T* x, const float* k, const UpfirdnParams& p, cudaStream_t st) {
   const bool planes_ok = p.minor == 1 && p.major < (1LL << 31);
   if (planes_ok && p.up_x == 1 && p.up_y == 1 && p.down_x == 1 && p.down_y == 1 && p.kh <= 4 && p.kw <= 4) {
-    dim3 grid((unsigned)p.major, ceil_div(p.out_h, 32), ceil_div(p.out_w, 128));
-    if (grid.y <= 65535 && grid.z <= 65535) {
-      if (p.kh <= 3 && p.kw <= 3)
-        upfirdn2d_blur_kernel<T, 3><<<grid, 256, 0, st>>>(y, x, k, p);
-      else
-        upfirdn2d_blur_kernel<T, 4><<<grid, 256, 0, st>>>(y, x, k, p);
-      PPST_LAUNCH_CHECK("upfirdn2d_blur_kernel");
+    {
+      // bulk-copy kernel: R = the largest multiple of 8 rows whose staged span fits ~44 KB (5 blocks per SM)
+      const int ks = (p.kh == p.kw && (p.kh == 3 || p.kh == 4)) ? p.kh : 0;
+      const size_t row_bytes = sizeof(T) * (size_t)p.in_w;
+      int rows = (int)(45000 / row_bytes) - (p.kh - 1);
+      rows = rows / 8 * 8;
+      rows = rows < 8 ? 8 : (rows > 64 ? 64 : rows);
+      if (rows > (p.out_h + 7) / 8 * 8) rows = (p.out_h + 7) / 8 * 8;
+      const size_t smem = 16 + 16 + row_bytes * (size_t)(rows + p.kh - 1);
+      const int nstrips = ceil_div(p.out_h, rows);
+      const int64_t blocks = p.major * nstrips;
+      if (smem <= 100 * 1024 && blocks < (1LL << 31) && (int64_t)p.in_w * (rows + 8) < (1 << 24)) {
+        auto kern = ks == 3 ? upfirdn2d_bulk_kernel<T, 3> : ks == 4 ? upfirdn2d_bulk_kernel<T, 4>
+                                                                  : upfirdn2d_bulk_kernel<T, 0>;
+        int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+                            "upfirdn2d_bulk_kernel attribute");
+        if (rc) return rc;
+        kern<<<(unsigned)blocks, 256, smem, st>>>(y, x, k, p, rows, nstrips);
+        PPST_LAUNCH_CHECK("upfirdn2d_bulk_kernel");
+        return 0;
+      }
+    }
+    const int kmax = (p.kh <= 3 && p.kw <= 3) ? 3 : 4;
+    const int cw = p.out_w <= 1280 ? p.out_w : 1024;               // full-width strips unless the rows are very long
+    const int pitch = cw + kmax - 1;
+    int rows = (int)(40960 / (sizeof(float) * pitch)) - (kmax - 1);  // ~40 KB of staged input per block
+    rows = rows / 4 * 4;
+    rows = rows < 8 ? 8 : (rows > 32 ? 32 : rows);
+    if (rows > (p.out_h + 3) / 4 * 4) rows = (p.out_h + 3) / 4 * 4;
+    const int nstrips = ceil_div(p.out_h, rows), nchunks = ceil_div(p.out_w, cw);
+    const int64_t blocks = p.major * nstrips * nchunks;
+    const size_t smem = sizeof(float) * (size_t)(rows + kmax - 1) * pitch;
+    if (blocks < (1LL << 31)) {
+      if (kmax == 3) {
+        cudaFuncSetAttribute(upfirdn2d_strip_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        upfirdn2d_strip_kernel<T, 3><<<(unsigned)blocks, 256, smem, st>>>(y, x, k, p, rows, cw, nstrips, nchunks);
+      } else {
+        cudaFuncSetAttribute(upfirdn2d_strip_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        upfirdn2d_strip_kernel<T, 4><<<(unsigned)blocks, 256, smem, st>>>(y, x, k, p, rows, cw, nstrips, nchunks);
+      }
+      PPST_LAUNCH_CHECK("upfirdn2d_strip_kernel");
       return 0;
     }
   }

@@ -107,6 +107,49 @@ def test_upfirdn2d_hot_path_sizes_and_dtypes():
         assert got.shape == want.shape and (got - want).abs().max() <= 2e-6
 
 
+def test_upfirdn2d_strip_path_edge_cases():
+    """up = down = 1 fast path: cropping (negative) and oversized pads, non-square / short taps, rows long enough to be
+    split into column chunks, one-row strips, and a base pointer that is not 16-byte aligned."""
+    from ppst_b200.stylegan2_op import upfirdn2d
+    cases = [
+        ((1, 2, 37, 41), torch.randn(3, 3, generator=gen(1)), (-1, -2)),
+        ((1, 2, 37, 41), torch.randn(2, 2, generator=gen(2)), (5, 6)),
+        ((2, 1, 9, 1400), torch.randn(4, 3, generator=gen(3)), (2, 1)),     # out_w > 1280 -> two column chunks
+        ((1, 3, 33, 2600), torch.randn(3, 3, generator=gen(4)), (0, 0)),
+        ((3, 1, 3, 3), torch.randn(3, 3, generator=gen(5)), (0, 0)),       # single output element per plane
+        ((1, 1, 70, 1027), torch.randn(1, 4, generator=gen(6)), (1, 2)),
+    ]
+    for shape, k, pad in cases:
+        x = torch.randn(*shape, generator=gen(shape[3]))
+        want = O.upfirdn2d(x, k, pad=pad)
+        got = upfirdn2d(x.to(DEV), k.to(DEV), pad=pad).cpu()
+        assert got.shape == want.shape, (shape, pad)
+        assert (got - want).abs().max() <= 2e-5, (shape, pad)
+        for dt in (torch.bfloat16, torch.float16):
+            g16 = upfirdn2d(x.to(DEV, dt), k.to(DEV), pad=pad).float().cpu()
+            w16 = O.upfirdn2d(x.to(dt).float(), k, pad=pad)
+            assert (g16 - w16).abs().max() <= 2e-2 * max(1.0, float(w16.abs().max())), (shape, pad, dt)
+    # contiguous view at an odd element offset into its storage
+    k = O.make_kernel([1, 2, 1])
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 2e-2)):
+        flat = torch.randn(2 * 5 * 131 * 67 + 3, generator=gen(9)).to(DEV, dt)
+        x = flat[3:].view(2, 5, 131, 67)
+        assert x.is_contiguous() and x.data_ptr() % 16 != 0
+        got = upfirdn2d(x, k.to(DEV)).float().cpu()
+        assert (got - O.upfirdn2d(x.float().cpu(), k)).abs().max() <= tol
+    # Inf in the input reaches exactly the outputs whose kh x kw window covers it (no 0 * Inf through padded taps)
+    for kk, pad in ((torch.ones(2, 2), (0, -1)), (torch.ones(1, 3), (1, 1)), (torch.ones(3, 3), (0, 0)),
+                    (torch.ones(4, 2), (2, 2))):
+        x = torch.randn(1, 2, 40, 40, generator=gen(10))
+        x[0, 0, -1, :] = float("inf")
+        x[0, 1, 17, 23] = float("inf")
+        want = O.upfirdn2d(x, kk, pad=pad)
+        got = upfirdn2d(x.to(DEV), kk.to(DEV), pad=pad).cpu()
+        fin = torch.isfinite(want)
+        assert (torch.isfinite(got) == fin).all(), (tuple(kk.shape), pad)
+        assert (got[fin] - want[fin]).abs().max() <= 1e-5
+
+
 def test_upfirdn2d_backward_and_double_backward():
     from ppst_b200.stylegan2_op import upfirdn2d
     k = O.make_kernel([1, 3, 3, 1])
