@@ -55,7 +55,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 //      columns: conflict-free LDS, and 128-byte coalesced stores whatever the row alignment (2^n+1-wide rows are the
 //      hot case).  KS = 3 / 4: exact square taps in registers; KS = 0: run-time kh, kw <= 4.
 template <typename T, int KS>
-__global__ void __launch_bounds__(256, 4) upfirdn2d_bulk_kernel(T* __restrict__ out, const T* __restrict__ in,
+__global__ void __launch_bounds__(256, 5) upfirdn2d_bulk_kernel(T* __restrict__ out, const T* __restrict__ in,
                                                                 const float* __restrict__ kernel, UpfirdnParams p,
                                                                 int R, int nstrips) {
   constexpr int RR = 8;                              // output rows per thread (vertical sliding window)
@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(256, 4) upfirdn2d_bulk_kernel(T* __restrict__ 
   const int cols = p.out_w;
   const int nitems = ((rows + RR - 1) / RR) * cols;
   T* dst = out + plane * (int64_t)p.out_h * p.out_w;
+  // item = (row group rg, column c), walked 256 items at a time without a division per item
+  int rg = tid / cols, c = tid - rg * cols;
   for (int idx = tid; idx < nitems; idx += 256) {
-    const int rg = idx / cols, c = idx - rg * cols;
     const int oyb = oy0 + rg * RR;
     const int xb = c - p.px0, yb = oyb - p.py0;           // input coordinate of tap (0, 0) of the item's first output
     const T* sp = sm + mis + (yb - iyA) * p.in_w + xb;   // only dereferenced where the predicates hold
@@ -149,9 +150,15 @@ __global__ void __launch_bounds__(256, 4) upfirdn2d_bulk_kernel(T* __restrict__ 
         }
       }
     }
+    T* q = dst + (int64_t)oyb * p.out_w + c;
+    const int nvalid = p.out_h - oyb;
 #pragma unroll
-    for (int o = 0; o < RR; ++o)
-      if (oyb + o < p.out_h) dst[(int64_t)(oyb + o) * p.out_w + c] = Cvt<T>::from_f(acc[o]);
+    for (int o = 0; o < RR; ++o) {
+      if (o < nvalid) *q = Cvt<T>::from_f(acc[o]);
+      q += p.out_w;
+    }
+    c += 256;
+    while (c >= cols) { c -= cols; ++rg; }
   }
 }
 
@@ -354,8 +361,8 @@ static int launch_upfirdn2d(T* y, const T* x, const float* k, const UpfirdnParam
       const size_t row_bytes = sizeof(T) * (size_t)p.in_w;
       int rows = (int)(45000 / row_bytes) - (p.kh - 1);
       rows = rows / 8 * 8;
-      rows = rows < 8 ? 8 : (rows > 64 ? 64 : rows);
-      if (rows > (p.out_h + 7) / 8 * 8) rows = (p.out_h + 7) / 8 * 8;
+      rows = rows < 8 ? 8 : (rows > 128 ? 128 : rows);
+      rows = (ceil_div(p.out_h, ceil_div(p.out_h, rows)) + 7) / 8 * 8;   // balance the strips of a plane
       const size_t smem = 16 + 16 + row_bytes * (size_t)(rows + p.kh - 1);
       const int nstrips = ceil_div(p.out_h, rows);
       const int64_t blocks = p.major * nstrips;

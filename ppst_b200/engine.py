@@ -285,7 +285,13 @@ class Engine:
             wf = ops.resample(wf, (wf.shape[1] * scale, wf.shape[2] * scale), 0)
         return wf
 
-    def encoder_col(self, image_nchw, corr=None, labels=None, taps=None):
+    def encoder_col_warp(self, levels, corr):
+        """The correlation branch of E2 alone (encoder_col.py:168-178, 100-138) on trunk features kept from an earlier
+        encoder_col(..., levels_out=[]) pass over the same images: the warped codes without re-running the trunk."""
+        return [self._pooled_head(lvl, self._e2_warp(levels[li], corr, resize=(li < 3), scale=2 ** (3 - li)))
+                for li, lvl in enumerate(LEVELS)]
+
+    def encoder_col(self, image_nchw, corr=None, labels=None, taps=None, levels_out=None):
         """E2: StyleGAN2ResnetEncodercol.forward (encoder_col.py:150-251).
         corr: f32 [n,4096,4096], or its [hi | lo] bf16 split [n,4096,8192] (ops.split_bf16 / corrm(split_out=True)),
         or None.  labels: uint8 [n,h,w] region map or None (training-path mask branch;
@@ -300,6 +306,8 @@ class Engine:
                 x = self._res_block(P["res%d" % (2 ** (li - 1))], x, False)
             if taps is not None:
                 taps["level" + lvl] = x
+            if levels_out is not None:
+                levels_out.append(x)
             vectors.append(self._pooled_head(lvl, x))
             xx = None
             if corr is not None:

@@ -42,6 +42,14 @@ class SwapModel:
             k: v.to(self.device, torch.float32).contiguous() for k, v in value.items()}
         self._graphs.clear()
 
+    def _noises_for(self, rows):
+        """The noise dict for a pass over `rows` samples: the user's [B,...] maps repeated when the content and style
+        rows are batched together (rows = 2B)."""
+        if self._noises is None:
+            return None
+        return {k: (v if v.shape[0] == rows else v.repeat(rows // v.shape[0], 1, 1, 1))
+                for k, v in self._noises.items()}
+
     @classmethod
     def from_model_state_dict(cls, sd, **kw):
         return cls(*split_state_dict(sd), **kw)
@@ -155,12 +163,19 @@ class SwapModel:
         e = self.engine
         xc, xs = self._in(content), self._in(style)
         n = xc.shape[0]
-        sp_c = e.encoder_con(xc)
-        gl_c, _ = e.encoder_col(xc)
-        _, fea_c, fea_c1 = e.generator(sp_c, gl_c, extract_features=True, noises=self.noises)
-        sp_s = e.encoder_con(xs)
-        gl_s, _ = e.encoder_col(xs)
-        _, fea_s, fea_s1 = e.generator(sp_s, gl_s, extract_features=True, noises=self.noises)
+        if xc.shape != xs.shape:
+            raise ValueError("swap: content %s and style %s must have the same shape" % (tuple(xc.shape), tuple(xs.shape)))
+        # content and style rows go through E1 / E2 / G.extract as ONE batch of 2n (every normalisation on the path is
+        # per sample, so each row's result is bit-identical to a separate pass); E2's trunk features of the style rows
+        # are kept for the correlation branch, which the reference recomputes from the image (encode2).
+        x2 = torch.cat([xc, xs], 0)
+        noises2 = self._noises_for(2 * n)
+        sp2 = e.encoder_con(x2)
+        levels = []
+        gl2, _ = e.encoder_col(x2, levels_out=levels)
+        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=noises2)
+        sp_c, gl_c = sp2[:n], [v[:n] for v in gl2]
+        fea_c, fea_s, fea_c1, fea_s1 = fea2[:n], fea2[n:], fea21[:n], fea21[n:]
         fc = torch.empty((n, 64, 64, 512), device=self.device, dtype=torch.float32)
         fs = torch.empty_like(fc)
         ops.affine_apply(fea_c, 256, out=fc, out_c_off=0)
@@ -168,9 +183,9 @@ class SwapModel:
         ops.rselfcorr(fea_c1, out=fc, out_c_off=256)
         ops.rselfcorr(fea_s1, out=fs, out_c_off=256)
         corr = e.corrm(fs, fc, split_out=e.use_tc)
-        _, gl_w = e.encoder_col(xs, corr=corr)
+        gl_w = e.encoder_col_warp([x[n:] for x in levels], corr)
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
-        rgb = e.generator(sp_c, codes, noises=self.noises)
+        rgb = e.generator(sp_c, codes, noises=self._noises_for(n))
         return rgb if return_nhwc else self._out(rgb)
 
     def swap_graph(self, content, style, alpha=1.0):
