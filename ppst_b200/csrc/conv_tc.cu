@@ -20,6 +20,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -50,6 +51,10 @@ struct Params {
   int w_img_rows;                       // weight rows per image (0: one weight matrix for the whole batch)
   int split_seg_kb;                     // 3-term split GEMM: k-blocks per [hi]/[lo] segment (0: plain)
   int stages, kps;                      // pipeline depth; k-blocks per pipeline stage (one barrier round trip each)
+  // halo kernel only
+  int tiles_ys;                         // super-tile rows per image = ceil(tiles_y / MT)
+  int a_rows, a_slot_bytes;             // rows of one A box (MT*th + kh - 1) and its 1024-aligned slot size
+  int na, nb, bps;                      // A slots, B slots, taps per B slot (1 or kh)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -192,6 +197,94 @@ __device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
   return v[0];
 }
 
+
+// ---------------------------------------------------------------- bf16 epilogue shared by both kernels
+constexpr int kEpiStageBytes = 2048;     // per epilogue warp: 32 rows x 64 bytes of packed bf16 (one 32-column chunk)
+
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// One warp's share of the epilogue of a 128 x BN accumulator sub-tile: TMEM lanes [32q, 32q+32) = pixel rows, BN
+// columns = output channels.  Per 32-column chunk:
+//   tcgen05.ld -> (+ bias + noise, leaky-ReLU, gain) -> bf16 -> the warp's 2 KB staging buffer (16-byte pieces XOR-
+//   swizzled by row pair so that both the row-wise writes and the column-wise reads below are bank-conflict free)
+//   -> per-channel sum / sum of squares of the STORED values by walking the staged columns (lane = channel pair x row
+//      parity: 16 LDS.32 + FMAs per lane instead of a 31-step shuffle transpose per statistic)
+//   -> global stores with 4 lanes per pixel: every store instruction writes 8 pixels x 64 contiguous bytes (whole
+//      32-byte sectors) instead of 32 scattered 16-byte pieces.
+// soff[i] / bit i of svalid describe row 8i + lane/4 of this warp's 32 rows (element offset of the pixel's channel
+// slice + 8 * (lane % 4), and whether that pixel exists); nz / valid describe row `lane`.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows_bf16(uint32_t taddr, uint32_t bias_u32, uint32_t stage_u32, float* st_sum,
+                                                   float* st_sq, __nv_bfloat16* __restrict__ out,
+                                                   const int64_t (&soff)[4], uint32_t svalid, float nz, bool valid,
+                                                   float gain, float slope_eff, int lane) {
+  const uint32_t my_row = stage_u32 + (uint32_t)lane * 64u;
+  const uint32_t wsw = (uint32_t)(lane >> 1) & 3u;                 // swizzle of the row this lane writes
+  const int rpar = lane >> 4, cp = lane & 15;                     // statistics: row parity, channel pair
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + (uint32_t)c0, r);
+    uint32_t bb[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lds128(bias_u32 + (uint32_t)(c0 + 4 * j) * 4u, *reinterpret_cast<uint32_t(*)[4]>(&bb[4 * j]));
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float a = (__uint_as_float(r[2 * j + h]) + __uint_as_float(bb[2 * j + h])) + nz;
+        v[h] = fmaxf(a, a * slope_eff) * gain;                     // leaky-ReLU for slope_eff in (0, 1]; 1 = identity
+      }
+      pk[j] = valid ? pack_bf16(v[0], v[1]) : 0u;                  // rows outside the image count as 0 in the statistics
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(my_row + (((uint32_t)j ^ wsw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    __syncwarp();
+    if (st_sum != nullptr) {
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t word = ((((uint32_t)cp >> 2) ^ (uint32_t)(i & 3)) << 2) | ((uint32_t)cp & 3u);
+        const uint32_t w = lds32(stage_u32 + (uint32_t)(2 * i + rpar) * 64u + word * 4u);
+        const float fx = __uint_as_float(w << 16), fy = __uint_as_float(w & 0xffff0000u);
+        s1a += fx; s1b += fy;
+        s2a = fmaf(fx, fx, s2a); s2b = fmaf(fy, fy, s2b);
+      }
+      s1a += __shfl_xor_sync(0xffffffffu, s1a, 16);
+      s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+      s2a += __shfl_xor_sync(0xffffffffu, s2a, 16);
+      s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+      if (lane < 16) {
+        *reinterpret_cast<float2*>(st_sum + c0 + 2 * cp) = make_float2(s1a, s1b);
+        *reinterpret_cast<float2*>(st_sq + c0 + 2 * cp) = make_float2(s2a, s2b);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = 8 * i + (lane >> 2);
+      uint32_t q4[4];
+      lds128(stage_u32 + (uint32_t)rr * 64u + ((((uint32_t)lane & 3u) ^ ((uint32_t)(rr >> 1) & 3u)) << 4), q4);
+      if ((svalid >> i) & 1u)
+        *reinterpret_cast<uint4*>(out + soff[i] + c0) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
+    }
+    __syncwarp();
+  }
+}
+
 constexpr int kMaxStages = 8;
 template <int BN, int BKC>
 struct Smem {
@@ -200,7 +293,8 @@ struct Smem {
   static constexpr int kKblockBytes = kABytes + kBBytes;     // one k-block: A tile then B tile (both 1024-aligned)
   static constexpr int kStatsBytes = 2 /*buf*/ * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
   static constexpr int kBiasBytes = kBiasSmem * 4;
-  static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*align slack*/;
+  static constexpr int kEpiBytes = 8 * kEpiStageBytes;        // per-warp staging of the bf16 epilogue
+  static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*align slack*/;
   static constexpr int kMaxDynamic = 232448 - 1024 /*static*/;
 };
 
@@ -216,10 +310,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int stage_bytes = p.kps * S::kKblockBytes;
   float* s_stats = reinterpret_cast<float*>(smem + STAGES * stage_bytes);
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + S::kStatsBytes);
-  const bool bias_in_smem = (bias != nullptr) && (p.cout <= kBiasSmem);
+  const bool bias_in_smem = (p.cout <= kBiasSmem);        // always true for bf16 output (checked on the host)
   if (bias_in_smem)
-    for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias[i];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes + S::kStatsBytes + S::kBiasBytes);
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias ? bias[i] : 0.0f;
+  uint8_t* s_epi = smem + STAGES * stage_bytes + S::kStatsBytes + S::kBiasBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_epi + S::kEpiBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
@@ -362,52 +457,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if constexpr (OUT_F32) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float bj = bias_in_smem ? s_bias[nt * BN + c0 + j] : (bias ? __ldg(bias + nt * BN + c0 + j) : 0.0f);
-          float a = __uint_as_float(r[j]) + bj + nz;
-          if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
-          v[j] = a * p.gain;
-        }
-        if (OUT_F32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
           if (valid) {
             float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_raw) + obase + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              float v[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int c = nt * BN + c0 + 4 * j + h;
+                const float bj = bias ? (bias_in_smem ? s_bias[c] : __ldg(bias + c)) : 0.0f;
+                float a = __uint_as_float(r[4 * j + h]) + bj + nz;
+                if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
+                v[h] = a * p.gain;
+              }
+              dst[j] = make_float4(v[0], v[1], v[2], v[3]);
+            }
           }
-          continue;
         }
-        uint32_t pk[16];
+      } else {
+        // store-side view of this warp's rows: lane -> rows 8i + lane/4, 16-byte piece lane%4
+        int64_t soff[4];
+        uint32_t svalid = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-        if (valid) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out_raw) + obase + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        for (int i = 0; i < 4; ++i) {
+          const int srow = q * 32 + 8 * i + (lane >> 2);
+          const int sy = srow / p.tw, sx = srow - sy * p.tw;
+          const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
+          if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
+          const int64_t spix = ((int64_t)img * p.full_h + (soy * p.phases_y + py)) * p.full_w + (sox * p.phases_x + px);
+          soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
         }
-        if (stats_sum != nullptr) {
-          // statistics of the values as stored (bf16-rounded), fp32 accumulate
-          float s1[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
-            const float2 f = __bfloat1622float2(h);
-            s1[2 * j] = valid ? f.x : 0.0f;
-            s1[2 * j + 1] = valid ? f.y : 0.0f;
-            s2[2 * j] = s1[2 * j] * s1[2 * j];
-            s2[2 * j + 1] = s1[2 * j + 1] * s1[2 * j + 1];
-          }
-          const float cs = warp_col_reduce(s1, lane);
-          const float cq = warp_col_reduce(s2, lane);
-          st_sum[c0 + lane] = cs;
-          st_sq[c0 + lane] = cq;
-        }
+        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
+                               stats_sum ? st_sum : nullptr, st_sq, reinterpret_cast<__nv_bfloat16*>(out_raw), soff,
+                               svalid, nz, valid, p.gain, p.has_act ? p.slope : 1.0f, lane);
       }
       // all TMEM reads of this warp are complete (wait::ld above): hand the accumulator stage back
       tc_fence_before();
@@ -427,6 +515,240 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int64_t o = ((int64_t)img * p.stats_partials + slot) * p.cout + nt * BN + c;
           stats_sum[o] = s;
           stats_sq[o] = qv;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// =====================================================================================================================
+// Halo variant: stride-1 convolutions with kh > 1 (the 3x3 layers and the 2x2 phase kernels of the transposed convs).
+//
+// The plain kernel above fetches one A box per tap, so a 3x3 layer pulls its input tile into the SM nine times and the
+// layers with cout <= 128 are bound by the SM's L2 read port (ncu: 13 TB/s of L2->SM traffic at 0.43 of the tensor
+// peak).  Here
+//   * ONE A box of (MT*th + kh - 1) rows serves the kh taps of a kernel column: tap (ky, kx) is the same box read from
+//     row ky on -- a descriptor start address ky * tw * BKC*2 bytes further, a whole number of swizzle atoms because
+//     tw >= 8 -- so A is fetched kw * (1 + (kh-1)/(MT*th)) times instead of kh*kw times;
+//   * a work item is MT = 2 vertically stacked 128-pixel sub-tiles that share every B tile (two accumulators of BN
+//     columns per TMEM stage), halving the weight traffic per FLOP when BN <= 128.
+// A and B travel through separate rings (A slots live for kh taps, B slots for one tap or one kernel column).
+// K order: channel block, kernel column, kernel row -- fixed, so results do not depend on batch or grid.
+// =====================================================================================================================
+constexpr int kMaxA = 4, kMaxB = 8;
+
+template <int BN, int MT>
+struct HaloSmem {
+  static constexpr int kStatsBytes = 2 /*acc stage*/ * MT * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
+  static constexpr int kBiasBytes = kBiasSmem * 4;
+  static constexpr int kBarBytes = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16;
+  static constexpr int kEpiBytes = 8 * kEpiStageBytes;
+  static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kMaxDynamic = 232448 - 1024;
+};
+
+template <int BN, int BKC, int MT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ noise,
+                    float* __restrict__ stats_sum, float* __restrict__ stats_sq, const Params p) {
+  using S = HaloSmem<BN, MT>;
+  constexpr int kBBytes = BN * BKC * 2;
+  constexpr int kSubBytes = BM * BKC * 2;            // one 128-pixel sub-tile of an A box
+  constexpr int kAccCols = MT * BN;                  // TMEM columns per accumulator stage
+  constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                 : (2 * kAccCols <= 256) ? 256 : 512;
+  static_assert(2 * kAccCols <= 512, "accumulators exceed tensor memory");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_slot_bytes = p.bps * kBBytes;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + p.na * p.a_slot_bytes;
+  uint8_t* fixed = b_ring + p.nb * b_slot_bytes;
+  float* s_stats = reinterpret_cast<float*>(fixed);
+  float* s_bias = reinterpret_cast<float*>(fixed + S::kStatsBytes);
+  uint8_t* s_epi = fixed + S::kStatsBytes + S::kBiasBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_epi + S::kEpiBytes);
+  uint64_t* a_empty = a_full + kMaxA;
+  uint64_t* b_full = a_empty + kMaxA;
+  uint64_t* b_empty = b_full + kMaxB;
+  uint64_t* tmem_full = b_empty + kMaxB;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias ? bias[i] : 0.0f;   // cout <= kBiasSmem (host)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_phases = p.phases_y * p.phases_x;
+
+  // work item -> (n-tile, phase, tile column, super-tile row, image)
+  auto decode = [&](int tile, int& nt, int& ph, int& tx, int& tys, int& img) {
+    nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+    ph = tile % n_phases; tile /= n_phases;
+    tx = tile % p.tiles_x; tile /= p.tiles_x;
+    tys = tile % p.tiles_ys; img = tile / p.tiles_ys;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      const uint32_t a_box_bytes = (uint32_t)(p.a_rows * p.tw * BKC * 2);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int nt, ph, tx, tys, img;
+        decode(tile, nt, ph, tx, tys, img);
+        const int py = ph / p.phases_x, px = ph % p.phases_x;
+        const int iy0 = tys * MT * p.th + p.off_y + py * p.phase_off_dy;
+        const int ix0 = tx * p.tw + p.off_x + px * p.phase_off_dx;
+        const int brow = ph * p.cout + nt * BN;
+        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+          for (int kx = 0; kx < p.kw; ++kx) {
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            mbar_arrive_expect_tx(&a_full[sa], a_box_bytes);
+            tma_load_4d(a_ring + sa * p.a_slot_bytes, &map_a, &a_full[sa], cb * BKC, ix0 + kx, iy0, img);
+            if (++sa == p.na) { sa = 0; pha ^= 1; }
+            for (int ky0 = 0; ky0 < p.kh; ky0 += p.bps) {
+              mbar_wait(&b_empty[sb], phb ^ 1);
+              mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_slot_bytes);
+              for (int j = 0; j < p.bps; ++j)
+                tma_load_2d(b_ring + sb * b_slot_bytes + j * kBBytes, &map_b, &b_full[sb],
+                            ((ky0 + j) * p.kw + kx) * p.cin + cb * BKC, brow);
+              if (++sb == p.nb) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc<BN>();
+      const uint32_t dy_bytes = (uint32_t)(p.tw * BKC * 2);
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccCols);
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+          for (int kx = 0; kx < p.kw; ++kx) {
+            mbar_wait(&a_full[sa], pha);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(a_ring + sa * p.a_slot_bytes);
+            for (int ky0 = 0; ky0 < p.kh; ky0 += p.bps) {
+              mbar_wait(&b_full[sb], phb);
+              tc_fence_after();
+              const uint32_t b_base = smem_u32(b_ring + sb * b_slot_bytes);
+              for (int j = 0; j < p.bps; ++j) {
+                const uint64_t db = make_smem_desc<BKC>(b_base + (uint32_t)(j * kBBytes));
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t da = make_smem_desc<BKC>(a_base + (uint32_t)(ky0 + j) * dy_bytes + (uint32_t)(m * kSubBytes));
+#pragma unroll
+                  for (int k = 0; k < BKC / 16; ++k)
+                    umma_bf16(tmem_d + (uint32_t)(m * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (accumulate | (uint32_t)k) != 0 ? 1u : 0u);
+                }
+                accumulate = 1;
+              }
+              umma_commit(&b_empty[sb]);
+              if (++sb == p.nb) { sb = 0; phb ^= 1; }
+            }
+            umma_commit(&a_empty[sa]);
+            if (++sa == p.na) { sa = 0; pha ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int row = q * 32 + lane;
+    const int ety = row / p.tw, etx = row - ety * p.tw;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != group) continue;
+      int nt, ph, tx, tys, img;
+      decode(tile, nt, ph, tx, tys, img);
+      const int py = ph / p.phases_x, px = ph % p.phases_x;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int ty = tys * MT + m;
+        const int oy = ty * p.th + ety, ox = tx * p.tw + etx;
+        const bool valid = (oy < p.out_h) && (ox < p.out_w);
+        const int64_t pix = ((int64_t)img * p.full_h + (oy * p.phases_y + py)) * p.full_w + (ox * p.phases_x + px);
+        const float nz = (noise != nullptr && valid) ? p.noise_w * noise[pix] : 0.0f;
+        float* b_sum = s_stats + (size_t)((as * MT + m) * 2 + 0) * 4 * BN;
+        float* b_sq = s_stats + (size_t)((as * MT + m) * 2 + 1) * 4 * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN);
+        int64_t soff[4];
+        uint32_t svalid = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int srow = q * 32 + 8 * i + (lane >> 2);
+          const int sy = srow / p.tw, sx = srow - sy * p.tw;
+          const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
+          if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
+          const int64_t spix = ((int64_t)img * p.full_h + (soy * p.phases_y + py)) * p.full_w + (sox * p.phases_x + px);
+          soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
+        }
+        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
+                               stats_sum ? b_sum + q * BN : nullptr, b_sq + q * BN, out, soff, svalid, nz, valid, p.gain,
+                               p.has_act ? p.slope : 1.0f, lane);
+        if (m == MT - 1) {
+          // every TMEM read of this warp has completed (wait::ld above): hand the accumulator stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        if (stats_sum != nullptr) {
+          if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (ty < p.tiles_y) {
+            const int e = (threadIdx.x - kEpiWarp0 * 32) & 127;
+            const int slot = ((ty * p.tiles_x + tx) * n_phases + ph);
+            for (int c = e; c < BN; c += 128) {
+              const float s = (b_sum[c] + b_sum[BN + c]) + (b_sum[2 * BN + c] + b_sum[3 * BN + c]);
+              const float qv = (b_sq[c] + b_sq[BN + c]) + (b_sq[2 * BN + c] + b_sq[3 * BN + c]);
+              const int64_t o = ((int64_t)img * p.stats_partials + slot) * p.cout + nt * BN + c;
+              stats_sum[o] = s;
+              stats_sq[o] = qv;
+            }
+          }
+          if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // staging buffer free for its next use
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
     }
@@ -515,6 +837,15 @@ static void pick_tile(int out_h, int out_w, int& th, int& tw) {
 }
 
 static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
 
 template <int BN, int BKC, bool OUT_F32>
 static int launch(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
@@ -572,12 +903,6 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     int rc = encode_map(&map_b, weight, 2, dims, strides, box, est, BKC);
     if (rc) return rc;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
   auto kern = conv_tc_kernel<BN, BKC, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -586,12 +911,100 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     if (rc) return rc;
     attr_set = true;
   }
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   float* ssum = stats;
   float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
   kern<<<grid, kThreads, smem_total, st>>>(map_a, map_b, out, bias, noise, ssum, ssq, p);
   PPST_LAUNCH_CHECK("conv_tc_kernel");
   return 0;
+}
+
+
+template <int BN, int BKC, int MT>
+static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
+                       const float* noise, float* stats, cudaStream_t st) {
+  using S = HaloSmem<BN, MT>;
+  Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
+  p.kh = d.kh; p.kw = d.kw; p.stride = 1;
+  p.off_y = d.off_y; p.off_x = d.off_x; p.phases_y = d.phases_y; p.phases_x = d.phases_x;
+  p.phase_off_dy = d.phase_off_dy; p.phase_off_dx = d.phase_off_dx;
+  p.full_h = d.full_h; p.full_w = d.full_w; p.cout_stride = d.cout_stride; p.c_off = d.c_off;
+  pick_tile(d.out_h, d.out_w, p.th, p.tw);
+  p.tiles_y = ceil_div(d.out_h, p.th); p.tiles_x = ceil_div(d.out_w, p.tw);
+  p.tiles_ys = ceil_div(p.tiles_y, MT);
+  p.n_tiles_n = d.cout / BN;
+  const int n_phases = d.phases_y * d.phases_x;
+  const int64_t tiles = (int64_t)d.n * p.tiles_ys * p.tiles_x * n_phases * p.n_tiles_n;
+  PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_tc: too many tiles");
+  p.num_tiles = (int)tiles;
+  p.kblocks_per_tap = d.cin / BKC;
+  p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
+  p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
+  p.a_rows = MT * p.th + d.kh - 1;
+  p.a_slot_bytes = (p.a_rows * p.tw * BKC * 2 + 1023) / 1024 * 1024;
+  constexpr int kBBytes = BN * BKC * 2;
+  p.bps = (d.kh * kBBytes <= 24576) ? d.kh : 1;
+  const int b_slot = p.bps * kBBytes;
+  const int avail = S::kMaxDynamic - S::kFixedBytes;
+  p.na = p.a_slot_bytes <= 24576 ? 4 : 3;
+  while (p.na > 2 && avail - p.na * p.a_slot_bytes < 3 * b_slot) --p.na;
+  p.nb = (avail - p.na * p.a_slot_bytes) / b_slot;
+  if (p.nb > kMaxB) p.nb = kMaxB;
+  PPST_REQUIRE(p.nb >= 2 && p.na >= 2, PPST_ERR_UNSUPPORTED, "conv_tc(halo): rings do not fit in shared memory");
+  const int smem_total = p.na * p.a_slot_bytes + p.nb * b_slot + S::kFixedBytes;
+
+  CUtensorMap map_a, map_b;
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)d.n};
+    const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
+    const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
+    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)p.tw, (uint32_t)p.a_rows, 1};
+    const uint32_t est[4] = {1, 1, 1, 1};
+    int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
+    const uint64_t dims[2] = {K, (uint64_t)d.cout * n_phases};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)BN};
+    const uint32_t est[2] = {1, 1};
+    int rc = encode_map(&map_b, weight, 2, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  auto kern = conv_tc_halo_kernel<BN, BKC, MT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kMaxDynamic),
+                        "cudaFuncSetAttribute(conv_tc_halo)");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  float* ssum = stats;
+  float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
+  kern<<<grid, kThreads, smem_total, st>>>(map_a, map_b, reinterpret_cast<__nv_bfloat16*>(out), bias, noise, ssum, ssq, p);
+  PPST_LAUNCH_CHECK("conv_tc_halo_kernel");
+  return 0;
+}
+
+// 0: plain kernel; else MT (1 or 2) of the halo kernel for this layer
+static int halo_mode(const ppst_conv_desc& d, int bn) {
+  static const int env_halo = [] { const char* e = getenv("PPST_CONV_TC_HALO"); return e ? atoi(e) : 1; }();
+  static const int env_mt = [] { const char* e = getenv("PPST_CONV_TC_MT"); return e ? atoi(e) : 0; }();
+  if (!env_halo || d.stride != 1 || d.kh < 2 || d.kh > 4 || d.split_terms != 0 || d.w_img_rows != 0 ||
+      d.out_dtype != PPST_BF16)
+    return 0;
+  int th, tw;
+  pick_tile(d.out_h, d.out_w, th, tw);
+  if (tw < 8 || tw * th != BM) return 0;       // tap row offsets must be whole swizzle atoms
+  if (bn > 128) return 1;
+  if (env_mt == 1 || env_mt == 2) return env_mt;
+  const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * ceil_div(d.out_w, tw) * d.phases_y * d.phases_x * (d.cout / bn);
+  return (ceil_div(d.out_h, th) >= 2 && tiles >= 4LL * num_sms()) ? 2 : 1;
 }
 
 }  // namespace tc
@@ -628,6 +1041,8 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
   PPST_REQUIRE(d.out_dtype == PPST_BF16 || stats == nullptr, PPST_ERR_UNSUPPORTED, "conv_tc: statistics need bf16 output");
   PPST_REQUIRE(d.cin % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cin=%d must be a multiple of 32", d.cin);
   PPST_REQUIRE(d.cout % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cout=%d must be a multiple of 32", d.cout);
+  PPST_REQUIRE(d.out_dtype == PPST_F32 || d.cout <= tc::kBiasSmem, PPST_ERR_UNSUPPORTED,
+               "conv_tc: bf16 output supports cout <= %d (got %d)", tc::kBiasSmem, d.cout);
   PPST_REQUIRE(d.stride == 1 || d.stride == 2, PPST_ERR_UNSUPPORTED, "conv_tc: stride %d", d.stride);
   PPST_REQUIRE(d.in_row_pitch % 8 == 0 && d.in_img_pitch % 8 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: input pitches must be 16-byte multiples");
   PPST_REQUIRE(d.cout_stride % 8 == 0 && d.c_off % 8 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: output channel slice must be 16-byte aligned");
@@ -637,6 +1052,10 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
   const bool k64 = (d.cin % 64 == 0);
 #define PPST_TC(BN_, BKC_)                                                                   \
   do {                                                                                       \
+    const int hm = tc::halo_mode(d, BN_);                                                    \
+    if (hm == 2 && BN_ <= 128)                                                               \
+      return tc::launch_halo<BN_, BKC_, (BN_ <= 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
+    if (hm >= 1) return tc::launch_halo<BN_, BKC_, 1>(d, out, in, weight, bias, noise, stats, st);         \
     if (d.out_dtype == PPST_F32)                                                             \
       return tc::launch<BN_, BKC_, true>(d, out, in, weight, bias, noise, stats, st);        \
     return tc::launch<BN_, BKC_, false>(d, out, in, weight, bias, noise, stats, st);         \

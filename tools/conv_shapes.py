@@ -19,6 +19,12 @@ SHAPES = [  # n, h, w, cin, cout, k, stride, phases
     (8, 512, 512, 32, 32, 3, 1, 1),
     (8, 512, 512, 128, 64, 1, 1, 1),
     (8, 256, 256, 32, 64, 5, 2, 1),
+    (8, 512, 512, 256, 128, 2, 1, 4),
+    (8, 256, 256, 512, 256, 2, 1, 4),
+    (8, 256, 256, 64, 64, 3, 1, 1),
+    (8, 256, 256, 256, 128, 3, 1, 1),
+    (8, 128, 128, 128, 128, 3, 1, 1),
+    (8, 64, 64, 512, 512, 3, 1, 1),
 ]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
