@@ -82,6 +82,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// warp-level transposing reduction: on entry lane L holds v[c] for columns c = 0..31 of ITS row;
+// on exit v[0] of lane L = sum over the 32 lanes (rows) of column L.  31 shuffles.
+__device__ __forceinline__ float warp_col_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = hi ? v[i] : v[i + off];
+      const float keep = hi ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 inline size_t dtype_size(int dtype) { return dtype == PPST_F32 ? 4 : 2; }

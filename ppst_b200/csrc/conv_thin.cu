@@ -6,25 +6,44 @@
 
 namespace ppst {
 
-// out NHWC [n, hw, cout_stride] (slice c_off..c_off+COUT), x NCHW f32 [n, cin, hw]; one thread per pixel.
+// out NHWC [n, hw, cout_stride] (slice c_off..c_off+COUT), x NCHW f32 [n, cin, hw].
+// A block stages kPixBlock consecutive pixels of each input plane in shared memory (coalesced 16-byte loads when the
+// plane length allows), then thread -> (pixel, group of 8 output channels): COUT/8 consecutive lanes write one pixel's
+// channel vector, so a warp store covers 8 pixels x 64 contiguous bytes (bf16) instead of 32 scattered pieces.
+constexpr int kPixBlock = 1024;
 template <typename TO, int COUT>
 __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ out, const float* __restrict__ x,
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               int64_t n, int cin, int64_t hw, int cout_stride, int c_off,
                                                               int has_act, float slope, float gain) {
+  constexpr int G = COUT / 8;                     // channel groups (= lanes) per pixel
   __shared__ float sw[COUT * 4];
   __shared__ float sb[COUT];
+  __shared__ __align__(16) float sx[4][kPixBlock];
   for (int i = threadIdx.x; i < COUT * cin; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
-  __syncthreads();
-  const int64_t total = n * hw;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t ni = p / hw, pix = p - ni * hw;
-    float xin[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < cin; ++ci) xin[ci] = x[(ni * cin + ci) * hw + pix];
-    TO* o = out + p * cout_stride + c_off;
+  const int64_t blocks_per_img = (hw + kPixBlock - 1) / kPixBlock;
+  const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t blk = blockIdx.x; blk < n * blocks_per_img; blk += gridDim.x) {
+    const int64_t ni = blk / blocks_per_img, p0 = (blk - ni * blocks_per_img) * kPixBlock;
+    const int np = (int)((hw - p0) < kPixBlock ? (hw - p0) : kPixBlock);
+    __syncthreads();                              // previous tile consumed (and sw / sb visible on the first pass)
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = x + (ni * cin + ci) * hw + p0;
+      if (vec) {
+        const int i = threadIdx.x * 4;
+        if (i < np) *reinterpret_cast<float4*>(&sx[ci][i]) = *reinterpret_cast<const float4*>(src + i);
+      } else {
+        for (int i = threadIdx.x; i < np; i += 256) sx[ci][i] = src[i];
+      }
+    }
+    __syncthreads();
+    TO* obase = out + (ni * hw + p0) * cout_stride + c_off;
+    for (int item = threadIdx.x; item < np * G; item += 256) {
+      const int pix = item / G, g = item - pix * G;
+      float xin[4];
 #pragma unroll
-    for (int g = 0; g < COUT / 8; ++g) {
+      for (int ci = 0; ci < 4; ++ci) xin[ci] = ci < cin ? sx[ci][pix] : 0.0f;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -34,13 +53,14 @@ __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ o
         if (has_act) acc = (acc > 0.f) ? acc : acc * slope;
         v[e] = acc * gain;
       }
+      TO* o = obase + (int64_t)pix * cout_stride + g * 8;
       if (sizeof(TO) == 2) {
         Vec16<TO> r;
 #pragma unroll
         for (int e = 0; e < 8; ++e) r.v[e] = Cvt<TO>::from_f(v[e]);
-        st_vec16(o + g * 8, r);
+        st_vec16(o, r);
       } else {
-        float* of = reinterpret_cast<float*>(o) + g * 8;
+        float* of = reinterpret_cast<float*>(o);
         *reinterpret_cast<float4*>(of) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(of + 4) = make_float4(v[4], v[5], v[6], v[7]);
       }
@@ -64,33 +84,51 @@ __global__ void __launch_bounds__(256) conv1x1_thin_out_kernel(float* __restrict
     for (int e = 0; e < 8; ++e) wr[co][e] = w[co * cin + cg * 8 + e];
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t p0 = warp * per_warp; p0 < pixels; p0 += nwarps * per_warp) {
-    const int64_t p = p0 + sub;
-    float acc[COUT];
+  constexpr int U = 4;                           // pixel groups per iteration: U 16-byte loads in flight per lane
+  for (int64_t p0 = warp * per_warp * U; p0 < pixels; p0 += nwarps * per_warp * U) {
+    Vec16<TI> rv[U][sizeof(TI) == 2 ? 1 : 2];
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-    if (p < pixels) {
-      float xv[8];
-      if (sizeof(TI) == 2) {
-        Vec16<TI> r = ld_vec16_stream(x + p * cin + cg * 8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) xv[e] = Cvt<TI>::to_f(r.v[e]);
-      } else {
-        const float* xf = reinterpret_cast<const float*>(x) + p * cin + cg * 8;
-        const float4 f0 = *reinterpret_cast<const float4*>(xf), f1 = *reinterpret_cast<const float4*>(xf + 4);
-        xv[0] = f0.x; xv[1] = f0.y; xv[2] = f0.z; xv[3] = f0.w; xv[4] = f1.x; xv[5] = f1.y; xv[6] = f1.z; xv[7] = f1.w;
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * per_warp + sub;
+      if (p < pixels) {
+        if (sizeof(TI) == 2) {
+          rv[u][0] = ld_vec16_stream(x + p * cin + cg * 8);
+        } else {
+          rv[u][0] = ld_vec16_stream(x + p * cin + cg * 8);
+          rv[u][sizeof(TI) == 2 ? 0 : 1] = ld_vec16_stream(x + p * cin + cg * 8 + 4);
+        }
       }
-#pragma unroll
-      for (int co = 0; co < COUT; ++co)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[co] = fmaf(xv[e], wr[co][e], acc[co]);
     }
-    for (int o = L >> 1; o > 0; o >>= 1)
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    if (cg == 0 && p < pixels) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * per_warp + sub;
+      float acc[COUT];
 #pragma unroll
-      for (int co = 0; co < COUT; ++co) out[p * COUT + co] = acc[co] + (bias ? bias[co] : 0.f);
+      for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+      if (p < pixels) {
+        float xv[8];
+        if (sizeof(TI) == 2) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) xv[e] = Cvt<TI>::to_f(rv[u][0].v[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            xv[e] = Cvt<TI>::to_f(rv[u][0].v[e]);
+            xv[4 + e] = Cvt<TI>::to_f(rv[u][sizeof(TI) == 2 ? 0 : 1].v[e]);
+          }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[co] = fmaf(xv[e], wr[co][e], acc[co]);
+      }
+      for (int o = L >> 1; o > 0; o >>= 1)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+      if (cg == 0 && p < pixels) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) out[p * COUT + co] = acc[co] + (bias ? bias[co] : 0.f);
+      }
     }
   }
 }
@@ -105,8 +143,8 @@ extern "C" int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, c
   PPST_REQUIRE(cout == 32, PPST_ERR_UNSUPPORTED, "conv1x1_in_nchw: cout=%d (32 supported: FromRGB)", cout);
   PPST_REQUIRE(c_off % 8 == 0 && cout_stride % 8 == 0 && c_off + cout <= cout_stride, PPST_ERR_ARG,
                "conv1x1_in_nchw: channel slice");
-  const int64_t total = n * hw;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int64_t tiles = n * ((hw + kPixBlock - 1) / kPixBlock);
+  const int blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == PPST_BF16)
     conv1x1_in_nchw_kernel<__nv_bfloat16, 32><<<blocks, 256, 0, st>>>((__nv_bfloat16*)out, x, w, bias, n, cin, hw,
@@ -128,7 +166,7 @@ extern "C" int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, 
   const int L = cin / 8;
   PPST_REQUIRE(cin % 8 == 0 && L >= 1 && L <= 32 && (32 % L) == 0, PPST_ERR_UNSUPPORTED,
                "conv1x1_thin_out: cin=%d must be 8*L with L dividing 32", cin);
-  const int per_warp = 32 / L;
+  const int per_warp = 4 * (32 / L);             // pixels per warp iteration (4 groups in flight)
   const int64_t warps = (pixels + per_warp - 1) / per_warp;
   const int blocks = (int)((warps + 7) / 8 < 148 * 8 ? (warps + 7) / 8 : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;

@@ -147,7 +147,71 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(__nv_bfloat16* __rest
   }
 }
 
-// softmax(x / divisor) per row, written as [hi | lo] bf16 halves; one block per row
+// block-wide max / sum over 256 threads (result broadcast); `sm` holds 8 partials + the result
+__device__ __forceinline__ float block256_reduce(float v, bool is_max, float* sm) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = sm[0];
+    for (int i = 1; i < 8; ++i) t = is_max ? fmaxf(t, sm[i]) : t + sm[i];
+    sm[8] = t;
+  }
+  __syncthreads();
+  return sm[8];
+}
+
+// softmax(x / divisor) per row as [hi | lo] bf16 halves, rows of <= 4096 values (the 64x64 correlation rows): the row
+// lives in registers (4 float4 per thread), so the logits are read from HBM exactly once and the two halves leave as
+// 8-byte stores.  One block per row.
+__global__ void __launch_bounds__(256) softmax_rows_split_reg_kernel(__nv_bfloat16* __restrict__ out,
+                                                                     const float* __restrict__ x, int64_t cols,
+                                                                     float divisor) {
+  const float* xr = x + (int64_t)blockIdx.x * cols;
+  __nv_bfloat16* o = out + (int64_t)blockIdx.x * 2 * cols;
+  __shared__ float sm[9];
+  const int nvec = (int)(cols >> 2);
+  float4 v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < nvec) {
+      const Vec16<float> r = ld_vec16_stream(xr + 4 * i);
+      v[j] = make_float4(r.v[0] / divisor, r.v[1] / divisor, r.v[2] / divisor, r.v[3] / divisor);
+    } else {
+      v[j] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    }
+  }
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mx = fmaxf(fmaxf(fmaxf(mx, v[j].x), fmaxf(v[j].y, v[j].z)), v[j].w);
+  mx = block256_reduce(mx, true, sm);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool on = threadIdx.x + 256 * j < nvec;
+    v[j].x = on ? expf(v[j].x - mx) : 0.f; v[j].y = on ? expf(v[j].y - mx) : 0.f;
+    v[j].z = on ? expf(v[j].z - mx) : 0.f; v[j].w = on ? expf(v[j].w - mx) : 0.f;
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float tot = block256_reduce(s, false, sm);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i = threadIdx.x + 256 * j;
+    if (i < nvec) {
+      union { uint2 u; __nv_bfloat16 h[4]; } hi, lo;
+      split2(v[j].x / tot, hi.h[0], lo.h[0]);
+      split2(v[j].y / tot, hi.h[1], lo.h[1]);
+      split2(v[j].z / tot, hi.h[2], lo.h[2]);
+      split2(v[j].w / tot, hi.h[3], lo.h[3]);
+      *reinterpret_cast<uint2*>(o + 4 * i) = hi.u;
+      *reinterpret_cast<uint2*>(o + cols + 4 * i) = lo.u;
+    }
+  }
+}
+
+// general row length: three passes over the row (the re-reads hit L1 / L2); one block per row
 __global__ void __launch_bounds__(256) softmax_rows_split_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ x,
                                                                  int64_t cols, float divisor) {
   const float* xr = x + (int64_t)blockIdx.x * cols;
@@ -223,7 +287,10 @@ extern "C" int ppst_softmax_rows_split(void* out, const float* x, int64_t rows, 
                                        void* stream) {
   using namespace ppst;
   PPST_REQUIRE(out && x && rows > 0 && cols > 0 && divisor != 0.0f, PPST_ERR_ARG, "softmax_rows_split: bad args");
-  softmax_rows_split_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, cols, divisor);
+  if (cols % 4 == 0 && cols <= 4096 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    softmax_rows_split_reg_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, cols, divisor);
+  else
+    softmax_rows_split_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out, x, cols, divisor);
   PPST_LAUNCH_CHECK("softmax_rows_split_kernel");
   return 0;
 }

@@ -5,52 +5,77 @@
 
 namespace ppst {
 
-// ---- skinny linear: one warp per output column, up to 8 rows of x per pass --------------------------------
-// Weight-bandwidth bound (m = batch is tiny): every weight row is read once per 8 batch rows with 128-bit loads.
-constexpr int kLinRows = 8;
+// ---- skinny linear: y[m, n] = x[m, k] . w[n, k]^T (+ bias), m = batch is tiny ------------------------------------
+// Weight-bandwidth bound.  A block owns 4 output columns x 16 batch rows; its 8 warps split K (split-K inside the block
+// keeps >= n/4 blocks in flight even for the 512-column style layers), each lane streaming 128-bit weight loads with all
+// of its loads issued before the first use.  Partials are combined in a fixed order (lane chain, transposing warp
+// butterfly, warps 0..7), so a row's result does not depend on the batch it is in.
+constexpr int kLinRows = 16, kLinCols = 4;
+__device__ __forceinline__ float dot4(const float4& x, const float4& w, float acc) {
+  acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc);
+  acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+  return acc;
+}
 __global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, const float* __restrict__ x,
                                                      const float* __restrict__ w, const float* __restrict__ b,
                                                      int64_t m, int64_t n, int64_t k, int64_t ldx, float w_scale,
                                                      float b_scale, int relu_in) {
-  const int lane = threadIdx.x & 31;
-  const int64_t col = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float part[8][kLinCols * kLinRows];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c0 = (int64_t)blockIdx.x * kLinCols;
   const int64_t m0 = (int64_t)blockIdx.y * kLinRows;
-  if (col >= n) return;
-  const float* wr = w + col * k;
-  float acc[kLinRows];
+  const int rows = (int)((m - m0) < kLinRows ? (m - m0) : kLinRows);
+  const float* wp[kLinCols];
 #pragma unroll
-  for (int r = 0; r < kLinRows; ++r) acc[r] = 0.0f;
+  for (int c = 0; c < kLinCols; ++c) wp[c] = w + (c0 + c < n ? c0 + c : c0) * k;
+  float acc[kLinCols * kLinRows];
+#pragma unroll
+  for (int i = 0; i < kLinCols * kLinRows; ++i) acc[i] = 0.0f;
   const bool vec = (k % 4 == 0) && (ldx % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
   if (vec) {
-    for (int64_t kk = lane * 4; kk < k; kk += 128) {
-      const float4 wv = *reinterpret_cast<const float4*>(wr + kk);
+    // warp `warp` owns k in [warp*128 + 1024*j, +128): consecutive warps read consecutive 512-byte weight segments
+    for (int64_t kk = warp * 128 + lane * 4; kk < k; kk += 1024) {
+      float4 wv[kLinCols];
+#pragma unroll
+      for (int c = 0; c < kLinCols; ++c) wv[c] = *reinterpret_cast<const float4*>(wp[c] + kk);
 #pragma unroll
       for (int r = 0; r < kLinRows; ++r) {
-        if (m0 + r < m) {
+        if (r < rows) {
           float4 xv = *reinterpret_cast<const float4*>(x + (m0 + r) * ldx + kk);
           if (relu_in) { xv.x = fmaxf(xv.x, 0.f); xv.y = fmaxf(xv.y, 0.f); xv.z = fmaxf(xv.z, 0.f); xv.w = fmaxf(xv.w, 0.f); }
-          acc[r] = fmaf(xv.x, wv.x, acc[r]); acc[r] = fmaf(xv.y, wv.y, acc[r]);
-          acc[r] = fmaf(xv.z, wv.z, acc[r]); acc[r] = fmaf(xv.w, wv.w, acc[r]);
+#pragma unroll
+          for (int c = 0; c < kLinCols; ++c) acc[c * kLinRows + r] = dot4(xv, wv[c], acc[c * kLinRows + r]);
         }
       }
     }
   } else {
-    for (int64_t kk = lane; kk < k; kk += 32) {
-      const float wv = wr[kk];
+    for (int64_t kk = warp * 32 + lane; kk < k; kk += 256) {
+      float wv[kLinCols];
+#pragma unroll
+      for (int c = 0; c < kLinCols; ++c) wv[c] = wp[c][kk];
 #pragma unroll
       for (int r = 0; r < kLinRows; ++r)
-        if (m0 + r < m) {
+        if (r < rows) {
           float xv = x[(m0 + r) * ldx + kk];
           if (relu_in) xv = fmaxf(xv, 0.f);
-          acc[r] = fmaf(xv, wv, acc[r]);
+#pragma unroll
+          for (int c = 0; c < kLinCols; ++c) acc[c * kLinRows + r] = fmaf(xv, wv[c], acc[c * kLinRows + r]);
         }
     }
   }
+  // lane L ends up with the warp totals of acc[L] and acc[32 + L]
+  const float t0 = warp_col_reduce(*reinterpret_cast<float(*)[32]>(&acc[0]), lane);
+  const float t1 = warp_col_reduce(*reinterpret_cast<float(*)[32]>(&acc[32]), lane);
+  part[warp][lane] = t0;
+  part[warp][32 + lane] = t1;
+  __syncthreads();
+  if (threadIdx.x < kLinCols * kLinRows) {
+    const int c = threadIdx.x / kLinRows, r = threadIdx.x % kLinRows;
+    float s = part[0][threadIdx.x];
 #pragma unroll
-  for (int r = 0; r < kLinRows; ++r) {
-    const float s = warp_sum(acc[r]);
-    if (lane == 0 && m0 + r < m) y[(m0 + r) * n + col] = s * w_scale + (b ? b[col] * b_scale : 0.0f);
+    for (int i = 1; i < 8; ++i) s += part[i][threadIdx.x];
+    if (r < rows && c0 + c < n) y[(m0 + r) * n + c0 + c] = s * w_scale + (b ? b[c0 + c] * b_scale : 0.0f);
   }
 }
 
@@ -217,7 +242,7 @@ extern "C" int ppst_linear(float* y, const float* x, const float* w, const float
                            int64_t ldx, float w_scale, float b_scale, int relu_in, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(y && x && w && m > 0 && n > 0 && k > 0 && ldx >= k, PPST_ERR_ARG, "linear: bad args");
-  dim3 grid(ceil_div(n, 8), ceil_div(m, kLinRows));
+  dim3 grid(ceil_div(n, kLinCols), ceil_div(m, kLinRows));
   PPST_REQUIRE(grid.y <= 65535, PPST_ERR_ARG, "linear: too many rows");
   linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, x, w, b, m, n, k, ldx, w_scale, b_scale, relu_in);
   PPST_LAUNCH_CHECK("linear_kernel");

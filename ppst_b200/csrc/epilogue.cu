@@ -238,12 +238,12 @@ __device__ __forceinline__ void cvt8(const Raw8<float>& r, float (&f)[8]) {
 // before any use, data kept packed) and the residual mode is a template parameter so that the common no-residual
 // instance stays small enough for 3+ resident blocks per SM.
 template <typename TX, typename TO, int RES>
-__global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
+__global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
                                                                    const float* __restrict__ a, const float* __restrict__ b,
                                                                    const TX* __restrict__ res, const float* __restrict__ ra,
                                                                    const float* __restrict__ rb, ppst_apply_desc d) {
   constexpr int V = 8;
-  constexpr int U = 4;
+  constexpr int U = RES == 2 ? 2 : 4;        // RES == 2 also keeps 4 bilinear neighbours per pixel in flight
   const int cv = d.c / V;
   const int lanes = 256 / cv;
   const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(TO* __restric
   }
   const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
   for (int ox0 = lane; ox0 < ow; ox0 += U * lanes) {
-    Raw8<TX> xr[U], rr[RES == 1 ? U : 1];
+    Raw8<TX> xr[U], rr[RES == 1 ? U : 1], qq[RES == 2 ? U : 1][4];
+    Bilin2 bxs[RES == 2 ? U : 1];
     int uxs[U];
     unsigned live = 0, zero = 0;
 #pragma unroll
@@ -295,6 +296,14 @@ __global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(TO* __restric
       if (ox < ow && !z) {
         xr[u] = ld_raw8<TX>(xrow + (int64_t)(uxs[u] / d.up) * d.c);
         if (RES == 1) rr[u] = ld_raw8<TX>(r0 + (int64_t)uxs[u] * d.c);
+        if (RES == 2) {
+          const Bilin2 bx = bilin_x2(uxs[u], lw);
+          bxs[u] = bx;
+          qq[u][0] = ld_raw8<TX>(r0 + (int64_t)bx.i0 * d.c);
+          qq[u][1] = ld_raw8<TX>(r0 + (int64_t)bx.i1 * d.c);
+          qq[u][2] = ld_raw8<TX>(r1 + (int64_t)bx.i0 * d.c);
+          qq[u][3] = ld_raw8<TX>(r1 + (int64_t)bx.i1 * d.c);
+        }
       }
     }
 #pragma unroll
@@ -314,17 +323,15 @@ __global__ void __launch_bounds__(256, 3) affine_apply_rows_kernel(TO* __restric
 #pragma unroll
           for (int e = 0; e < V; ++e) y[e] += fmaf(rv[e], rav[e], rbv[e]);
         } else if (RES == 2) {
-          const Bilin2 bx = bilin_x2(uxs[u], lw);
-          const Raw8<TX> q00 = ld_raw8<TX>(r0 + (int64_t)bx.i0 * d.c), q01 = ld_raw8<TX>(r0 + (int64_t)bx.i1 * d.c);
-          const Raw8<TX> q10 = ld_raw8<TX>(r1 + (int64_t)bx.i0 * d.c), q11 = ld_raw8<TX>(r1 + (int64_t)bx.i1 * d.c);
+          const Bilin2 bx = bxs[RES == 2 ? u : 0];
           float t0[V], t1[V];
-          cvt8(q00, t0);
-          cvt8(q01, t1);
+          cvt8(qq[RES == 2 ? u : 0][0], t0);
+          cvt8(qq[RES == 2 ? u : 0][1], t1);
           float rv[V];
 #pragma unroll
           for (int e = 0; e < V; ++e) rv[e] = by.l0 * (bx.l0 * t0[e] + bx.l1 * t1[e]);
-          cvt8(q10, t0);
-          cvt8(q11, t1);
+          cvt8(qq[RES == 2 ? u : 0][2], t0);
+          cvt8(qq[RES == 2 ? u : 0][3], t1);
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             const float r = rv[e] + by.l1 * (bx.l0 * t0[e] + bx.l1 * t1[e]);

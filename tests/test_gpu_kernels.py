@@ -535,6 +535,10 @@ def test_split_gemm_on_tensor_cores_is_fp32_accurate():
     sp = ops.softmax_rows_split(logits.to(DEV), 0.01).float().cpu()
     rec = sp[:, :4096] + sp[:, 4096:]
     assert (rec - F.softmax(logits / 0.01, -1)).abs().max() <= 1e-5
+    for cols in (1000, 5000, 4098):          # short rows (register path), long rows and odd lengths (three-pass path)
+        logits = torch.randn(5, cols, generator=g) * 0.3
+        sp = ops.softmax_rows_split(logits.to(DEV), 0.01).float().cpu()
+        assert (sp[:, :cols] + sp[:, cols:] - F.softmax(logits / 0.01, -1)).abs().max() <= 1e-5
     x = torch.randn(1, 8, 8, 512, generator=g)
     sp = ops.corr_prepare_split(x.to(DEV), 256).float().cpu().view(64, 1024)
     ref = ops.corr_prepare(x.to(DEV), 256).cpu().view(64, 512)
