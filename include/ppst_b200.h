@@ -277,6 +277,18 @@ PPST_API int ppst_gemm_f32(float* c, const float* a, const float* b, int64_t bat
 /* in-place row softmax of (x / divisor), f32 [rows, cols]  (F.softmax(logits / 0.01, dim=-1), ppst_model.py:363) */
 PPST_API int ppst_softmax_rows(float* x, int64_t rows, int64_t cols, float divisor, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * decode(target=...) post-process
+ * ------------------------------------------------------------------------------------------- */
+/* Guided-filter smoothing of a decoded image against the content image, entirely on the device: replaces
+ * PPSTModel.decode's target branch (models/ppst_model.py:288-306) = util.tensor2im (util/util.py:98-131) ->
+ * photo_gif.GIFSmoothing(r, eps).process (photo_gif.py:13-46: cv2.ximgproc.guidedFilter(guide=target, src=out)) ->
+ * ToTensor -> (x - 0.5) * 2.  src / guide / out: NCHW f32 [n, 3, h, w] with values in [-1, 1]; radius < min(h, w).
+ * workspace: device scratch of at least ppst_guided_smooth_workspace_bytes(n, h, w) bytes, owned by the caller. */
+PPST_API int64_t ppst_guided_smooth_workspace_bytes(int64_t n, int h, int w);
+PPST_API int ppst_guided_smooth(float* out, const float* src, const float* guide, int64_t n, int h, int w, int radius,
+                       float eps, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

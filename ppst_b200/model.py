@@ -106,12 +106,14 @@ class SwapModel:
         return self.engine.encoder_col(self._in(image), corr=corr, labels=labels)
 
     def decode(self, spatial_code, global_code, target=None):
-        """ppst_model.py:288-306 with target=None (the guided-filter post-process is SURVEY 8(f) 'next')."""
-        if target is not None:
-            raise NotImplementedError("decode(target=...) post-processing (photo_gif.GIFSmoothing) is out of scope")
+        """ppst_model.py:288-306.  With `target` (the content image, as the grid evaluator passes it) the decoded image
+        goes through the guided-filter smoothing of photo_gif.GIFSmoothing(r=30, eps=(0.02*255)**2) -- on the device,
+        without the reference's host round trip."""
         sp = self.engine.to_nhwc(spatial_code)
-        rgb = self.engine.generator(sp, global_code, noises=self.noises)
-        return self._out(rgb)
+        rgb = self._out(self.engine.generator(sp, global_code, noises=self._noises_for(sp.shape[0])))
+        if target is not None:
+            rgb = ops.guided_smooth(rgb, self._in(target))
+        return rgb
 
     def extract_feat(self, spatial_code, global_code):
         """ppst_model.py:308-309 -> (rgb, fea, fea1)."""
@@ -187,6 +189,50 @@ class SwapModel:
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
         rgb = e.generator(sp_c, codes, noises=self._noises_for(n))
         return rgb if return_nhwc else self._out(rgb)
+
+    def plain_swap(self, content, style, return_nhwc=False):
+        """G(E1(content), E2(style)) without the correlation branch: the only swap the reference can run away from
+        512^2 (its correlation path is hard-wired to 64x64 / 256x256 feature maps) -- the
+        1024^2 configuration of BASELINE.json."""
+        e = self.engine
+        sp = e.encoder_con(self._in(content))
+        gl, _ = e.encoder_col(self._in(style))
+        rgb = e.generator(sp, gl, noises=self._noises_for(sp.shape[0]))
+        return rgb if return_nhwc else self._out(rgb)
+
+    def swap_grid(self, contents, styles, cell_batch=8, smooth=False):
+        """Every (content i, style j) cell of evaluation/content_style_grid_generation_evaluator.py:57-91 in one call:
+        contents [Nc,3,512,512], styles [Ns,3,512,512] -> [Nc, Ns, 3, 512, 512].
+        Per-image work (E1, E2 trunk, G.extract, Rselfcorr) runs ONCE per image instead of once per cell (the
+        reference re-encodes the style image for every content); per-cell work {corrm, E2 correlation branch,
+        G.decode} is batched `cell_batch` cells at a time.  Each cell is bit-identical to swap(content_i, style_j).
+        smooth=True applies decode(target=content_i)'s guided-filter post-process (photo_gif.py) on the device."""
+        e = self.engine
+        xc, xs = self._in(contents), self._in(styles)
+        nc, ns = xc.shape[0], xs.shape[0]
+        x2 = torch.cat([xc, xs], 0)
+        sp2 = e.encoder_con(x2)
+        levels = []
+        gl2, _ = e.encoder_col(x2, levels_out=levels)
+        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=self._noises_for(nc + ns))
+        f2 = torch.empty((nc + ns, 64, 64, 512), device=self.device, dtype=torch.float32)
+        ops.affine_apply(fea2, 256, out=f2, out_c_off=0)
+        ops.rselfcorr(fea21, out=f2, out_c_off=256)
+        sp_c = sp2[:nc]
+        lv_s = [x[nc:] for x in levels]
+        out = torch.empty((nc, ns, 3) + tuple(xc.shape[2:]), device=self.device, dtype=torch.float32)
+        cells = [(i, j) for i in range(nc) for j in range(ns)]
+        for k0 in range(0, len(cells), cell_batch):
+            chunk = cells[k0:k0 + cell_batch]
+            ci = torch.tensor([c[0] for c in chunk], device=self.device)
+            sj = torch.tensor([c[1] for c in chunk], device=self.device)
+            corr = e.corrm(f2.index_select(0, sj + nc), f2.index_select(0, ci), split_out=e.use_tc)
+            gl_w = e.encoder_col_warp([x.index_select(0, sj) for x in lv_s], corr)
+            rgb = self._out(e.generator(sp_c.index_select(0, ci), gl_w, noises=self._noises_for(len(chunk))))
+            if smooth:
+                rgb = ops.guided_smooth(rgb, xc.index_select(0, ci))
+            out.view(nc * ns, *out.shape[2:])[k0:k0 + len(chunk)] = rgb
+        return out
 
     def swap_graph(self, content, style, alpha=1.0):
         """swap() replayed from a CUDA graph: the ~600 kernel launches of one step are captured once per

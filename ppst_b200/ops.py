@@ -367,6 +367,23 @@ def softmax_rows_split(logits, divisor):
     return out
 
 
+def guided_smooth(out_img, target, radius=30, eps=(0.02 * 255) ** 2):
+    """PPSTModel.decode's target branch (ppst_model.py:288-306; photo_gif.py:13-46) on the device: both images NCHW f32
+    [n,3,h,w] in [-1,1]; returns the guided-filtered image in the same convention."""
+    require_cuda(out_img, target)
+    assert out_img.shape == target.shape and out_img.shape[1] == 3, (out_img.shape, target.shape)
+    src = out_img.to(torch.float32).contiguous()
+    guide = target.to(torch.float32).contiguous()
+    n, _, h, w = src.shape
+    ws_bytes = int(_L().ppst_guided_smooth_workspace_bytes(n, h, w))
+    ws = torch.empty(ws_bytes, device=src.device, dtype=torch.uint8)
+    y = torch.empty_like(src)
+    with _Prof("guided_smooth", 2 * src.numel() * 4):
+        check(_L().ppst_guided_smooth(ptr(y), ptr(src), ptr(guide), n, h, w, int(radius), float(eps), ptr(ws), ws_bytes,
+                                      stream()))
+    return y
+
+
 def gemm_split_tc(a_split, b_split, m_hw, out=None):
     """C[b] = A[b] . B[b]^T with fp32-level accuracy on the tensor cores (3-term bf16 split).
     a_split: bf16 [b, M, 2K] ([hi | lo]), M = m_hw[0] * m_hw[1];  b_split: bf16 [b, N, 2K];  -> f32 [b, M, N].

@@ -286,6 +286,41 @@ def test_batch_rows_are_independent(world, model_bf16):
         m.noises = saved
 
 
+def test_swap_grid_cells_equal_pairwise_swaps(world, model_bf16):
+    """swap_grid (grid evaluator, content_style_grid_generation_evaluator.py:57-91, with per-image work done once):
+    every cell is bit-identical to swap(content_i, style_j); a ragged last chunk of cells is covered."""
+    m = model_bf16
+    contents = torch.cat([world["c"], world["s"].flip(3)], 0)
+    styles = torch.cat([world["s"], world["c"].flip(2), world["c"]], 0)
+    grid = m.swap_grid(contents, styles, cell_batch=4)
+    assert grid.shape == (2, 3, 3, 512, 512)
+    for i in range(2):
+        for j in range(3):
+            one = m.swap(contents[i:i + 1], styles[j:j + 1])
+            assert torch.equal(grid[i, j], one[0]), (i, j)
+    assert psnr(grid[0, 0].cpu()[None], world["swap"]) >= 45.0
+
+
+def test_plain_swap_1024_matches_oracle(world):
+    """BASELINE config 4: the plain swap G(E1(c), E2(s)) is the only one defined away from 512^2.  Checked at
+    1024 x 512 (the oracle needs ~20 s per full 1024^2 generator pass; the kernels are size-agnostic)."""
+    from ppst_b200 import SwapModel
+    sdE1, sdE2, sdG = world["sd"]
+    c = O.make_portraits(1, 1024, 512, seed=77)
+    s = O.make_portraits(1, 1024, 512, seed=78, smooth=True)
+    noises = O.make_noises(1, 1024, 512)
+    with torch.no_grad():
+        want = O.generator(sdG, O.encoder_con(sdE1, c), O.encoder_col(sdE2, s)[0], noises=noises)
+    m = SwapModel(sdE1, sdE2, sdG, mode="bf16")
+    m.noises = noises
+    got = m.plain_swap(c, s)
+    assert got.shape == want.shape == (1, 3, 1024, 512)
+    assert psnr(got.cpu(), want) >= 45.0
+    m32 = SwapModel(sdE1, sdE2, sdG, mode="fp32")
+    m32.noises = noises
+    assert (m32.plain_swap(c, s).cpu() - want).abs().max() <= 2e-3
+
+
 def test_evaluator_sequence_through_command_dispatch(world, model_fp32):
     """evaluation/simple_swapping_evaluator.py:44-59, verbatim call sequence, through model(..., command=)."""
     model = model_fp32

@@ -543,3 +543,21 @@ def test_split_gemm_on_tensor_cores_is_fp32_accurate():
     sp = ops.corr_prepare_split(x.to(DEV), 256).float().cpu().view(64, 1024)
     ref = ops.corr_prepare(x.to(DEV), 256).cpu().view(64, 512)
     assert (sp[:, :512] + sp[:, 512:] - ref).abs().max() <= 1e-6
+
+
+def test_guided_smooth_matches_oracle():
+    """decode(target=...) post-process (ppst_model.py:288-306, photo_gif.py:13-46) on the device vs the numpy restatement:
+    the integer window sums are exact and every fp32 step is order-matched, so at most a handful of pixels (double-
+    precision sums landing on a rounding boundary) may differ, and then by one uint8 level."""
+    from oracle import guided_oracle as G
+    from ppst_b200 import ops
+    for (n, h, w, r) in ((2, 96, 130, 30), (1, 512, 512, 30), (1, 70, 64, 5)):
+        out = O.make_portraits(n, h, w, seed=5, smooth=True) * 1.2        # values outside [-1, 1] exercise the clip
+        tgt = O.make_portraits(n, h, w, seed=6, smooth=True) * 0.7 + 0.2 * O.make_portraits(n, h, w, seed=7)
+        want = G.guided_smooth(out.numpy(), tgt.numpy(), r=r)
+        got = ops.guided_smooth(out.to(DEV), tgt.to(DEV), radius=r).cpu().numpy()
+        lv = np.abs(np.rint((got - want) * 127.5))
+        assert lv.max() <= 1, (n, h, w, lv.max())
+        assert (lv > 0).mean() <= 1e-4, (n, h, w, float((lv > 0).mean()))
+    with pytest.raises(RuntimeError):
+        ops.guided_smooth(torch.zeros(1, 3, 20, 20, device=DEV), torch.zeros(1, 3, 20, 20, device=DEV), radius=30)

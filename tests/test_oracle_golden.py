@@ -201,3 +201,32 @@ def test_plain_path_non_square(golden, full_nets):
         gl2, _ = O.encoder_col(sdE2, c2)
         check_summary(g, "plain256x384/sp", sp2, atol=1e-4)
         check_summary(g, "plain256x384/rec", O.generator(sdG, sp2, gl2, noises=n2), atol=1e-4)
+
+
+def test_guided_oracle_box_means_match_opencv_boxfilter():
+    """oracle/guided_oracle.py is parity-unpinned (opencv-contrib absent); what CAN be pinned is its box mean, against
+    plain OpenCV's cv2.boxFilter with BORDER_REFLECT (the primitive ximgproc's guided filter is built on)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import guided_oracle as G
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 65026, (97, 120)).astype(np.int64)
+    f = (rng.standard_normal((97, 120)) * 100).astype(np.float32)
+    for r in (1, 7, 30):
+        k = (2 * r + 1, 2 * r + 1)
+        want = cv2.boxFilter(a.astype(np.float32), cv2.CV_32F, k, borderType=cv2.BORDER_REFLECT)
+        assert np.array_equal(G.box_mean_int(a, r), want)
+        want = cv2.boxFilter(f, cv2.CV_32F, k, borderType=cv2.BORDER_REFLECT)
+        assert np.abs(G.box_mean_f32(f, r) - want).max() <= 2e-5
+
+
+def test_guided_oracle_properties():
+    """Known properties of the guided filter: a constant source stays constant; filtering an image with itself as the
+    guide at eps -> 0 reproduces it; quantisation follows tensor2im (truncation)."""
+    from oracle import guided_oracle as G
+    rng = np.random.default_rng(1)
+    guide = rng.integers(0, 256, (80, 96, 3)).astype(np.uint8)
+    const = np.full((80, 96, 3), 77, np.uint8)
+    assert np.array_equal(G.guided_filter_u8(guide, const, 9, np.float32(26.01)), const)
+    out = G.guided_filter_u8(guide, guide, 9, np.float32(1e-3))
+    assert np.abs(out.astype(int) - guide.astype(int)).max() <= 1
+    assert G.quantize_u8(np.array([-1.0, 0.0, 0.999, 1.0, 1.5])).tolist() == [0, 127, 254, 255, 255]
