@@ -182,6 +182,12 @@ PPST_API int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, con
 PPST_API int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, const float* bias, int64_t pixels, int cin,
                           int cout, int in_dtype, void* stream);
 
+/* Per-sample input-channel scaling of packed weights (StyleGAN2-style weight modulation) for ppst_conv_tc with
+ * w_img_rows = rows:  out bf16 [n][rows][taps*cin] = w f32 [rows][taps*cin] * a f32 [n][cin].  Folds the InstanceNorm
+ * that PRECEDES the first convolution of the generator's feature heads (generator.py:180-231) into that convolution. */
+PPST_API int ppst_scale_weights(void* out, const float* w, const float* a, int64_t n, int64_t rows, int taps, int cin,
+                       void* stream);
+
 /* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
 PPST_API int ppst_conv_tc_available(void);
 

@@ -53,6 +53,7 @@ _SIGS = {
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_available": (c_int, []),
+    "ppst_scale_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_conv1x1_in_nchw": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_float, c_float,
                                                      c_int, c_void_p]),
     "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),

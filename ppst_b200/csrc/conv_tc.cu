@@ -606,7 +606,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int py = ph / p.phases_x, px = ph % p.phases_x;
         const int iy0 = tys * MT * p.th + p.off_y + py * p.phase_off_dy;
         const int ix0 = tx * p.tw + p.off_x + px * p.phase_off_dx;
-        const int brow = ph * p.cout + nt * BN;
+        const int brow = img * p.w_img_rows + ph * p.cout + nt * BN;
         for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
           for (int kx = 0; kx < p.kw; ++kx) {
             mbar_wait(&a_empty[sa], pha ^ 1);
@@ -951,13 +951,14 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   }
   {
     const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
-    const uint64_t dims[2] = {K, (uint64_t)d.cout * n_phases};
+    const uint64_t dims[2] = {K, d.w_img_rows ? (uint64_t)d.w_img_rows * d.n : (uint64_t)d.cout * n_phases};
     const uint64_t strides[1] = {K * 2};
     const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)BN};
     const uint32_t est[2] = {1, 1};
     int rc = encode_map(&map_b, weight, 2, dims, strides, box, est, BKC);
     if (rc) return rc;
   }
+  p.w_img_rows = d.w_img_rows;
   auto kern = conv_tc_halo_kernel<BN, BKC, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -978,8 +979,7 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
 static int halo_mode(const ppst_conv_desc& d, int bn) {
   static const int env_halo = [] { const char* e = getenv("PPST_CONV_TC_HALO"); return e ? atoi(e) : 1; }();
   static const int env_mt = [] { const char* e = getenv("PPST_CONV_TC_MT"); return e ? atoi(e) : 0; }();
-  if (!env_halo || d.stride != 1 || d.kh < 2 || d.kh > 4 || d.split_terms != 0 || d.w_img_rows != 0 ||
-      d.out_dtype != PPST_BF16)
+  if (!env_halo || d.stride != 1 || d.kh < 2 || d.kh > 4 || d.split_terms != 0 || d.out_dtype != PPST_BF16)
     return 0;
   int th, tw;
   pick_tile(d.out_h, d.out_w, th, tw);

@@ -17,17 +17,24 @@ __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ o
                                                               int64_t n, int cin, int64_t hw, int cout_stride, int c_off,
                                                               int has_act, float slope, float gain) {
   constexpr int G = COUT / 8;                     // channel groups (= lanes) per pixel
-  __shared__ float sw[COUT * 4];
-  __shared__ float sb[COUT];
   __shared__ __align__(16) float sx[4][kPixBlock];
-  for (int i = threadIdx.x; i < COUT * cin; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias ? bias[i] : 0.0f;
+  static_assert(256 % G == 0, "a thread must keep its channel group");
+  const int g = threadIdx.x % G;
+  float rw[8][4], rb[8];                          // this thread's 8 output channels: weights (zero beyond cin), bias
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    rb[e] = bias ? bias[g * 8 + e] : 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) rw[e][ci] = ci < cin ? w[(g * 8 + e) * cin + ci] : 0.0f;
+  }
   const int64_t blocks_per_img = (hw + kPixBlock - 1) / kPixBlock;
   const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   for (int64_t blk = blockIdx.x; blk < n * blocks_per_img; blk += gridDim.x) {
     const int64_t ni = blk / blocks_per_img, p0 = (blk - ni * blocks_per_img) * kPixBlock;
     const int np = (int)((hw - p0) < kPixBlock ? (hw - p0) : kPixBlock);
-    __syncthreads();                              // previous tile consumed (and sw / sb visible on the first pass)
+    __syncthreads();                              // previous tile consumed
+    for (int ci = cin; ci < 4; ++ci)
+      for (int i = threadIdx.x; i < kPixBlock; i += 256) sx[ci][i] = 0.0f;
     for (int ci = 0; ci < cin; ++ci) {
       const float* src = x + (ni * cin + ci) * hw + p0;
       if (vec) {
@@ -39,17 +46,18 @@ __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ o
     }
     __syncthreads();
     TO* obase = out + (ni * hw + p0) * cout_stride + c_off;
+    // 256 % G == 0: a thread always serves the same channel group, whose weights / bias live in registers
     for (int item = threadIdx.x; item < np * G; item += 256) {
-      const int pix = item / G, g = item - pix * G;
+      const int pix = item / G;
       float xin[4];
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) xin[ci] = ci < cin ? sx[ci][pix] : 0.0f;
+      for (int ci = 0; ci < 4; ++ci) xin[ci] = sx[ci][pix];
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int co = g * 8 + e;
-        float acc = sb[co];
-        for (int ci = 0; ci < cin; ++ci) acc = fmaf(xin[ci], sw[co * cin + ci], acc);
+        float acc = rb[e];
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) acc = fmaf(xin[ci], rw[e][ci], acc);
         if (has_act) acc = (acc > 0.f) ? acc : acc * slope;
         v[e] = acc * gain;
       }

@@ -74,3 +74,41 @@ extern "C" int ppst_nhwc_to_nchw(void* dst, const void* src, int64_t n, int64_t 
   PPST_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return 0;
 }
+
+// Per-sample input-channel scaling of packed conv weights: out[n][r][t*cin + c] = bf16(w[r][t*cin + c] * a[n][c]).
+// InstanceNorm in FRONT of a convolution whose output is instance-normalised again (the generator's feature heads,
+// generator.py:180-231: [ReplPad] -> IN -> conv -> IN) needs no pass over the activation: the scale folds into the
+// weights per sample -- StyleGAN2's weight modulation -- and the shift, a per-(sample, output channel) constant because
+// nothing is zero-padded after it, is removed by the second normalisation.
+namespace ppst {
+__global__ void __launch_bounds__(256) scale_weights_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ w,
+                                                            const float* __restrict__ a, int64_t n, int64_t rows,
+                                                            int taps, int cin) {
+  const int64_t K = (int64_t)taps * cin, per = rows * K, total = n * per;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (int64_t)gridDim.x * blockDim.x * 4) {
+    const int64_t ni = i / per, r = i - ni * per;
+    const int c = (int)(r % cin);                       // cin % 4 == 0: the 4 elements share a tap
+    const float4 wv = *reinterpret_cast<const float4*>(w + r);
+    const float4 av = *reinterpret_cast<const float4*>(a + ni * cin + c);
+    union { uint2 u; __nv_bfloat16 h[4]; } o;
+    o.h[0] = __float2bfloat16_rn(wv.x * av.x); o.h[1] = __float2bfloat16_rn(wv.y * av.y);
+    o.h[2] = __float2bfloat16_rn(wv.z * av.z); o.h[3] = __float2bfloat16_rn(wv.w * av.w);
+    *reinterpret_cast<uint2*>(out + i) = o.u;
+  }
+}
+}  // namespace ppst
+
+extern "C" int ppst_scale_weights(void* out, const float* w, const float* a, int64_t n, int64_t rows, int taps, int cin,
+                                  void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && w && a && n > 0 && rows > 0 && taps > 0 && cin > 0 && cin % 4 == 0, PPST_ERR_ARG,
+               "scale_weights: bad args (cin must be a multiple of 4)");
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(a)) & 15) == 0,
+               PPST_ERR_ARG, "scale_weights: buffers must be 16-byte aligned");
+  const int64_t total = n * rows * taps * cin;
+  const int64_t blocks = (total / 4 + 255) / 256;
+  scale_weights_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)out, w, a, n, rows, taps, cin);
+  PPST_LAUNCH_CHECK("scale_weights_kernel");
+  return 0;
+}

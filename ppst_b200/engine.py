@@ -152,8 +152,9 @@ class Engine:
         return G
 
     # ------------------------------------------------------------------------------------------ primitives
-    def conv(self, x, spec, noise=None, out=None, c_off=0, out_dtype=None, want_stats=False):
-        """x: dense NHWC.  Returns (y, stats) with stats = None | dict(partials...) for in_coeffs."""
+    def conv(self, x, spec, noise=None, out=None, c_off=0, out_dtype=None, want_stats=False, w_per_image=None):
+        """x: dense NHWC.  Returns (y, stats) with stats = None | dict(partials...) for in_coeffs.
+        w_per_image: bf16 [n, cout, K] per-sample weights (ops.scale_weights) instead of spec.w16 (tensor-core path)."""
         n, h, w, cin = x.shape
         assert cin == spec.cin, (cin, spec.cin)
         oh, ow = spec.out_hw(h, w)
@@ -168,13 +169,14 @@ class Engine:
                           out_hw=(oh, ow), phases=spec.phases, phase_off=spec.phase_off, full_hw=(fh, fw),
                           cout_stride=out.shape[3], c_off=c_off, act=spec.act, slope=0.2,
                           gain=SQRT2 if spec.act else 1.0, noise_w=spec.noise_w if noise is not None else 0.0,
-                          in_dtype=code_in, out_dtype=code_out)
+                          in_dtype=code_in, out_dtype=code_out, w_img_rows=spec.cout if w_per_image is not None else 0)
         stats = None
+        assert w_per_image is None or tc, "per-sample weights need the tensor-core path"
         if tc:
             sbuf = None
             if want_stats:
                 sbuf = torch.empty(ops.conv_tc_stats_elems(d), device=x.device, dtype=torch.float32)
-            ops.conv_tc(out, x, spec.w16, spec.bias, noise, sbuf, d)
+            ops.conv_tc(out, x, spec.w16 if w_per_image is None else w_per_image, spec.bias, noise, sbuf, d)
             if want_stats:
                 half = sbuf.numel() // 2
                 stats = {"sum": sbuf[:half], "sumsq": sbuf[half:], "n_partials": half // (n * spec.cout),
@@ -353,8 +355,15 @@ class Engine:
         pad = (1, 1, 1, 1) if P["k"] == 3 else (0, 0, 0, 0)
         xp = self.apply(x, pad=pad, pad_mode=2) if P["k"] == 3 else x
         a, b = self.coeffs(xp)
-        xn = self.apply(xp, a, b)
-        c1, st = self.conv(xn, P["c1"], want_stats=True)
+        if self.use_tc and xp.dtype == torch.bfloat16:
+            # IN -> conv -> IN: the first normalisation's scale goes into per-sample weights, its shift is a constant
+            # per (sample, output channel) that the second normalisation removes -- no pass over the activation
+            spec = P["c1"]
+            wn = ops.scale_weights(spec.w32, a, spec.kh * spec.kw, spec.cin)
+            c1, st = self.conv(xp, spec, want_stats=True, w_per_image=wn)
+        else:
+            xn = self.apply(xp, a, b)
+            c1, st = self.conv(xn, P["c1"], want_stats=True)
         a, b = self.coeffs(c1, st)
         h = self.apply(c1, a, b, pre_slope=P["a1"], pad=pad, pad_mode=2)
         c2, st = self.conv(h, P["c2"], want_stats=True)

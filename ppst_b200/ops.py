@@ -367,6 +367,17 @@ def softmax_rows_split(logits, divisor):
     return out
 
 
+def scale_weights(w32, a, taps, cin):
+    """Per-sample modulated weights: w32 f32 [rows, taps*cin] (packed), a f32 [n, cin] -> bf16 [n, rows, taps*cin]."""
+    require_cuda(w32, a)
+    assert w32.dtype == torch.float32 and a.dtype == torch.float32 and w32.is_contiguous()
+    a = a.contiguous()
+    rows = w32.numel() // (taps * cin)
+    out = torch.empty((a.shape[0], rows, taps * cin), device=w32.device, dtype=torch.bfloat16)
+    check(_L().ppst_scale_weights(ptr(out), ptr(w32), ptr(a), a.shape[0], rows, int(taps), int(cin), stream()))
+    return out
+
+
 def guided_smooth(out_img, target, radius=30, eps=(0.02 * 255) ** 2):
     """PPSTModel.decode's target branch (ppst_model.py:288-306; photo_gif.py:13-46) on the device: both images NCHW f32
     [n,3,h,w] in [-1,1]; returns the guided-filtered image in the same convention."""

@@ -338,3 +338,28 @@ def test_evaluator_sequence_through_command_dispatch(world, model_fp32):
     assert (output_image.cpu() - world["swap"]).abs().max() <= 2e-3
     with pytest.raises(ValueError):
         model(structure_image)
+
+
+def test_grid_evaluator_sequence_with_guided_filter_target(world, model_fp32):
+    """evaluation/content_style_grid_generation_evaluator.py:57-88, verbatim call sequence for one (content, style)
+    cell, including decode(..., target=structure_image): the guided-filter post-process of ppst_model.py:288-306."""
+    from oracle import guided_oracle as G
+    model = model_fp32
+    style_image, structure_image = world["s"], world["c"]
+    f0, f1 = model(style_image, command="extract_feat_from_image")
+    fea_ss, fea_ss1 = [f0], [f1]
+    sps = [model(structure_image, command="encode")[0]]
+    f0, f1 = model(structure_image, command="extract_feat_from_image")
+    fea_s, fea_s1 = [f0], [f1]
+    fea_s[0] = torch.cat((fea_s[0], model(fea_s1[0], command="Rselfcorr")), dim=1)
+    if fea_ss[0].size(1) == 256:
+        fea_ss[0] = torch.cat((fea_ss[0], model(fea_ss1[0], command="Rselfcorr")), dim=1)
+    corrmatrix = model(fea_ss[0], fea_s[0], command="corrm")
+    gl, gl_w = model(style_image.cuda(), corrmatrix, command="encode2")
+    out = model(sps[0], gl_w, command="decode", target=structure_image)[0]
+    assert out.shape == (3, 512, 512)
+    want = G.guided_smooth(world["swap"].numpy(), structure_image.numpy())[0]
+    lv = np.abs(out.cpu().numpy() - want) * 127.5                       # in uint8 levels
+    assert lv.max() <= 3.0 and lv.mean() <= 0.05, (float(lv.max()), float(lv.mean()))
+    # every value is an exact uint8 level mapped back to [-1, 1]
+    assert np.abs(np.rint((out.cpu().numpy() + 1) * 127.5) - (out.cpu().numpy() + 1) * 127.5).max() <= 1e-4

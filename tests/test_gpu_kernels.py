@@ -344,6 +344,9 @@ TC_CASES = [  # ci, co, k, stride, pad, h, w, batch
     (32, 64, 5, 2, 0, 35, 35, 1),       # stride 2 via tensor-map element strides
     (64, 96, 3, 1, 1, 9, 70, 1),        # cout = 3*32, odd sizes
     (256, 384, 3, 1, 1, 16, 16, 1),     # BN=128 x 3
+    (64, 128, 3, 1, 1, 200, 190, 2),    # >= 4 x 148 tiles: halo kernel, 2 stacked sub-tiles; odd tile-row count
+    (32, 32, 3, 1, 1, 200, 190, 2),     # same with 64B-swizzled 32-channel blocks
+    (64, 64, 3, 1, 1, 203, 97, 3),      # BN=64, ragged bottom / right edges
 ]
 
 
@@ -378,6 +381,34 @@ def test_conv_tc_matches_reference():
     ref = O.fused_leaky_relu(F.conv2d(x.bfloat16().float(), wt.bfloat16().float(), None, padding=1) + 0.3 * nz[:, None], b)
     got = run_conv("tc", x, wt, b, 1, (-1, -1), (16, 16), act=True, noise=nz, noise_w=0.3, dtype=torch.bfloat16)
     assert (got.float().permute(0, 3, 1, 2).cpu() - ref).abs().max() <= 3e-2
+
+
+def test_conv_tc_per_sample_scaled_weights():
+    """ops.scale_weights + w_img_rows: conv(W * a_n, x_n) per sample (the feature heads' folded InstanceNorm), on the
+    3x3 halo kernel and on the 1x1 plain kernel."""
+    from ppst_b200 import ops
+    from ppst_b200._lib import BF16
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    for ci, co, k, h, w, n in ((64, 128, 3, 40, 48, 3), (128, 64, 1, 32, 32, 2)):
+        g = gen(ci + k)
+        x = torch.randn(n, ci, h, w, generator=g)
+        wt = torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)
+        a = torch.rand(n, ci, generator=g) + 0.5
+        w32 = pack_w(wt).to(DEV).contiguous()
+        wn = ops.scale_weights(w32, a.to(DEV), k * k, ci)
+        assert wn.shape == (n, co, k * k * ci) and wn.dtype == torch.bfloat16
+        want_w = (pack_w(wt).view(co, k * k, ci) * a[:, None, None, :]).view(n, co, -1)
+        assert (wn.float().cpu() - want_w.bfloat16().float()).abs().max() == 0.0
+        d = ops.conv_desc((n, h, w, ci), co, k, k, off=(-(k // 2), -(k // 2)), out_hw=(h, w), in_dtype=BF16,
+                          out_dtype=BF16, w_img_rows=co)
+        out = torch.empty((n, h, w, co), device=DEV, dtype=torch.bfloat16)
+        ops.conv_tc(out, ops.nchw_to_nhwc(x.to(DEV), dtype=torch.bfloat16), wn, None, None, None, d)
+        for i in range(n):
+            wi = (wt * a[i].view(1, ci, 1, 1)).bfloat16().float()
+            ref = F.conv2d(x[i:i + 1].bfloat16().float(), wi, None, padding=k // 2)
+            err = (out[i:i + 1].float().permute(0, 3, 1, 2).cpu() - ref).abs().max()
+            assert err <= 2e-2 * max(1.0, float(ref.abs().max())), (ci, co, k, i, float(err))
 
 
 def test_conv_reads_interior_of_padded_buffer():
