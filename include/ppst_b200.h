@@ -103,6 +103,16 @@ PPST_API int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const void
                       const float* shift, float* scratch, int64_t n, int64_t c, int64_t hw, int n_regions,
                       int label_mode, int channels_last, int dtype, void* stream);
 
+/* GAP / GMP of a bilinear (align_corners=False) x`scale` upsampling of an f32 NHWC map without materialising it:
+ * the correlation branch of the colour encoder interpolates the warped 64x64 features back to the level's resolution
+ * and then only pools them (encoder_col.py:119-130 followed by :160-166).  x: f32 [n, lh, lw, c_stride], channel slice
+ * [c_off, c_off + c).  sum / vmax: f32 [n, c] over the (lh*scale) x (lw*scale) virtual map (either may be NULL).
+ * scale in {1, 2, 4, 8}; scratch: f32 workspace of ppst_upsample_reduce_scratch_elems(n, lh, c) elements.
+ * Deterministic; the reduction split does not depend on n. */
+PPST_API int64_t ppst_upsample_reduce_scratch_elems(int64_t n, int lh, int c);
+PPST_API int ppst_upsample_reduce(float* sum, float* vmax, const float* x, int64_t n, int lh, int lw, int c_stride,
+                         int c_off, int c, int scale, float* scratch, void* stream);
+
 /* uint8 label map [n, hw] -> one-hot f32 [n, n_labels, hw]  (CelebAMaskDataset._mask_labels,
  * data/CelebAMask_dataset.py:54-60; bit-exact membership test label == i). */
 PPST_API int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64_t n, int64_t hw, int n_labels, void* stream);
@@ -229,9 +239,13 @@ PPST_API int ppst_affine_apply(void* out, const void* x, const float* a, const f
 /* Resampling into a channel slice of an NHWC tensor.
  * mode 0: bilinear, align_corners=False (F.interpolate, generator.py:274,277; encoder_col.py:130)
  * mode 1: adaptive average pool with integer window (nn.AdaptiveAvgPool2d, generator.py:257,276;
- *         F.adaptive_avg_pool2d encoder_col.py:119-122) -- requires in % out == 0 */
+ *         F.adaptive_avg_pool2d encoder_col.py:119-122) -- requires in % out == 0
+ * a, b: NULL, or f32 [n, c] (b may be NULL = 0): every SOURCE sample is first mapped to lrelu(x*a + b, slope) -- the
+ *       InstanceNorm + PReLU that ends a feature head (generator.py:180-231) applied on load, so the normalised map
+ *       that generator.py:272-278 pools and interpolates is never written to memory. */
 PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
-                  int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, void* stream);
+                  int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
+                  const float* b, float slope, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * small dense layers and vector normalisation (f32)

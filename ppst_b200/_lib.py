@@ -45,6 +45,8 @@ _SIGS = {
     "ppst_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 14 + [c_void_p]),
     "ppst_plane_reduce_scratch_elems": (c_i64, [c_i64, c_i64, c_i64, c_int]),
     "ppst_plane_reduce": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_upsample_reduce_scratch_elems": (c_i64, [c_i64, c_int, c_int]),
+    "ppst_upsample_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 6 + [c_void_p, c_void_p]),
     "ppst_labels_pool_or": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_labels_to_onehot": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_void_p]),
     "ppst_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),
@@ -59,7 +61,7 @@ _SIGS = {
     "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),
     "ppst_in_coeffs": (c_int, [c_void_p] * 6 + [c_i64, c_void_p, c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),
-    "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p]),
+    "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p, c_void_p, c_float, c_void_p]),
     "ppst_linear": (c_int, [c_void_p] * 4 + [c_i64] * 4 + [c_float, c_float, c_int, c_void_p]),
     "ppst_l2_normalize": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_float, c_int, c_void_p]),
     "ppst_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p]),

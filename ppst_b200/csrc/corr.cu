@@ -56,6 +56,86 @@ __global__ void __launch_bounds__(256) rselfcorr_kernel(TO* __restrict__ out, co
   out[((ni * ph + py) * pw + px) * (int64_t)out_c_stride + c_off + threadIdx.x] = Cvt<TO>::from_f(acc);
 }
 
+// c == 64 (the only width PPSTModel.Rselfcorr is called with): HALF A WARP per patch, 8 patches per 128-thread block.
+// Thread `pos` of a patch owns pixel `pos` of the 4x4 patch: it loads the pixel's 64 channels with 16-byte loads, centres
+// and normalises them in registers (no shuffles), parks them in shared memory as [channel][position], and then computes a
+// 4x4 register tile of the 16x16 Gram matrix with two LDS.128 per 16 FMAs (the one-block-per-patch kernel below spends
+// two LDS.32 per FMA and 32768 blocks per batch of 8).
+template <typename TO> __device__ __forceinline__ void store4(TO* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&v)[4]) {
+  __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(128) rselfcorr64_kernel(TO* __restrict__ out, const TI* __restrict__ fea,
+                                                          int64_t patches, int h, int w, int out_c_stride, int c_off) {
+  constexpr int C = 64;
+  __shared__ __align__(16) float sp[8][C][16];
+  const int slot = threadIdx.x >> 4, pos = threadIdx.x & 15;
+  const int64_t patch = (int64_t)blockIdx.x * 8 + slot;
+  const bool live = patch < patches;
+  const int pw = w / 4, ph = h / 4;
+  if (live) {
+    const int px = (int)(patch % pw), py = (int)((patch / pw) % ph);
+    const int64_t ni = patch / ((int64_t)pw * ph);
+    const int yy = py * 4 + (pos >> 2), xx = px * 4 + (pos & 3);
+    const TI* src = fea + ((ni * h + yy) * w + xx) * (int64_t)C;
+    float v[C];
+    constexpr int VN = Vec16<TI>::N;
+#pragma unroll
+    for (int k = 0; k < C / VN; ++k) {
+      const Vec16<TI> r = ld_vec16(src + k * VN);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) v[k * VN + e] = Cvt<TI>::to_f(r.v[e]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) s += v[ch];
+    const float mu = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) { v[ch] -= mu; q = fmaf(v[ch], v[ch], q); }
+    const float inv = 1.0f / (sqrtf(q) + (float)DBL_EPSILON);
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) sp[slot][ch][pos] = v[ch] * inv;
+  }
+  __syncwarp();
+  if (!live) return;
+  const int ti = pos >> 2, tj = pos & 3;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[r][e] = 0.f;
+#pragma unroll 8
+  for (int ch = 0; ch < C; ++ch) {
+    const float4 a = *reinterpret_cast<const float4*>(&sp[slot][ch][4 * ti]);
+    const float4 b = *reinterpret_cast<const float4*>(&sp[slot][ch][4 * tj]);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[r][e] = fmaf(av[r], bv[e], acc[r][e]);
+  }
+  TO* o = out + patch * (int64_t)out_c_stride + c_off;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) store4<TO>(o + (4 * ti + r) * 16 + 4 * tj, acc[r]);
+}
+
 // One warp per pixel row of c channels: centre the first c_center channels, then L2-normalise all of them.
 template <typename TI>
 __global__ void __launch_bounds__(256) corr_prepare_kernel(float* __restrict__ out, const TI* __restrict__ in,
@@ -306,8 +386,17 @@ extern "C" int ppst_rselfcorr(void* out, const void* fea, int64_t n, int h, int 
   const size_t smem = sizeof(float) * 16 * (c + 1);
   PPST_REQUIRE(smem <= 48 * 1024, PPST_ERR_UNSUPPORTED, "rselfcorr: too many channels (%d)", c);
   cudaStream_t st = (cudaStream_t)stream;
-#define PPST_RSC(TI, TO) \
-  rselfcorr_kernel<TI, TO><<<(unsigned)patches, 256, smem, st>>>((TO*)out, (const TI*)fea, h, w, c, out_c_stride, c_off)
+  const bool fast = (c == 64) && out_c_stride % 4 == 0 && c_off % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(fea) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+#define PPST_RSC(TI, TO)                                                                                              \
+  do {                                                                                                                \
+    if (fast)                                                                                                         \
+      rselfcorr64_kernel<TI, TO><<<(unsigned)((patches + 7) / 8), 128, 0, st>>>((TO*)out, (const TI*)fea, patches, h, \
+                                                                                 w, out_c_stride, c_off);             \
+    else                                                                                                              \
+      rselfcorr_kernel<TI, TO><<<(unsigned)patches, 256, smem, st>>>((TO*)out, (const TI*)fea, h, w, c, out_c_stride, \
+                                                                     c_off);                                          \
+  } while (0)
   if (in_dtype == PPST_F32 && out_dtype == PPST_F32) PPST_RSC(float, float);
   else if (in_dtype == PPST_BF16 && out_dtype == PPST_BF16) PPST_RSC(__nv_bfloat16, __nv_bfloat16);
   else if (in_dtype == PPST_BF16 && out_dtype == PPST_F32) PPST_RSC(__nv_bfloat16, float);

@@ -218,6 +218,19 @@ __device__ __forceinline__ Raw8<T> ld_raw8(const T* p) {
   }
   return r;
 }
+// same, but allocating in L1: the bilinear-skip neighbours are re-read by the next pixel and the next output row
+template <typename T>
+__device__ __forceinline__ Raw8<T> ld_raw8_cached(const T* p) {
+  Raw8<T> r;
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 2); ++i) {
+    const uint4* src = reinterpret_cast<const uint4*>(p) + i;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.q[i].x), "=r"(r.q[i].y), "=r"(r.q[i].z), "=r"(r.q[i].w)
+                 : "l"(src));
+  }
+  return r;
+}
 __device__ __forceinline__ void cvt8(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
   const uint32_t w[4] = {r.q[0].x, r.q[0].y, r.q[0].z, r.q[0].w};
 #pragma unroll
@@ -299,10 +312,10 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
         if (RES == 2) {
           const Bilin2 bx = bilin_x2(uxs[u], lw);
           bxs[u] = bx;
-          qq[u][0] = ld_raw8<TX>(r0 + (int64_t)bx.i0 * d.c);
-          qq[u][1] = ld_raw8<TX>(r0 + (int64_t)bx.i1 * d.c);
-          qq[u][2] = ld_raw8<TX>(r1 + (int64_t)bx.i0 * d.c);
-          qq[u][3] = ld_raw8<TX>(r1 + (int64_t)bx.i1 * d.c);
+          qq[u][0] = ld_raw8_cached<TX>(r0 + (int64_t)bx.i0 * d.c);
+          qq[u][1] = ld_raw8_cached<TX>(r0 + (int64_t)bx.i1 * d.c);
+          qq[u][2] = ld_raw8_cached<TX>(r1 + (int64_t)bx.i0 * d.c);
+          qq[u][3] = ld_raw8_cached<TX>(r1 + (int64_t)bx.i1 * d.c);
         }
       }
     }
@@ -350,7 +363,9 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
 template <typename TX, typename TO, int V>
 __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, const TX* __restrict__ x, int64_t n,
                                                        int in_h, int in_w, int out_h, int out_w, int c,
-                                                       int out_c_stride, int out_c_off, int mode) {
+                                                       int out_c_stride, int out_c_off, int mode,
+                                                       const float* __restrict__ a, const float* __restrict__ b,
+                                                       float slope) {
   const int cv = c / V;
   const int64_t total = n * out_h * out_w * cv;
   const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
@@ -363,6 +378,20 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
     const int ch = cg * V;
     const TX* base = x + ni * in_h * in_w * (int64_t)c + ch;
     float y[V];
+    // optional per-(n, c) affine + leaky/PReLU slope applied to every SOURCE sample (the normalisation + activation of
+    // the tensor being resampled, so that it never has to be materialised)
+    float av[V], bv[V];
+    const bool tf = (a != nullptr);
+    if (tf) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) { av[e] = a[ni * c + ch + e]; bv[e] = b ? b[ni * c + ch + e] : 0.0f; }
+    }
+    auto xf = [&](float (&v)[V]) {
+      if (tf) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = lrelu_slope(fmaf(v[e], av[e], bv[e]), slope);
+      }
+    };
     if (mode == 0) {
       float sy = sh * ((float)oy + 0.5f) - 0.5f, sx = sw * ((float)ox + 0.5f) - 0.5f;
       if (sy < 0.f) sy = 0.f;
@@ -375,6 +404,7 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
       load_ch<TX, V>(v01, base + ((int64_t)y0 * in_w + x1) * c);
       load_ch<TX, V>(v10, base + ((int64_t)y1 * in_w + x0) * c);
       load_ch<TX, V>(v11, base + ((int64_t)y1 * in_w + x1) * c);
+      xf(v00); xf(v01); xf(v10); xf(v11);
 #pragma unroll
       for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
     } else {
@@ -385,6 +415,7 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
         for (int dx = 0; dx < fw; ++dx) {
           float v[V];
           load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_w + (ox * fw + dx)) * c);
+          xf(v);
 #pragma unroll
           for (int e = 0; e < V; ++e) y[e] += v[e];
         }
@@ -478,7 +509,8 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
 }
 
 extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
-                             int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, void* stream) {
+                             int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
+                             const float* b, float slope, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(out && x && n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && c > 0, PPST_ERR_ARG,
                "resample: bad args");
@@ -494,10 +526,10 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
   do {                                                                                                         \
     if (vec)                                                                                                   \
       resample_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
-                                                       out_c_stride, out_c_off, mode);                         \
+                                                       out_c_stride, out_c_off, mode, a, b, slope);            \
     else                                                                                                       \
       resample_kernel<TX, TO, 1><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
-                                                       out_c_stride, out_c_off, mode);                         \
+                                                       out_c_stride, out_c_off, mode, a, b, slope);            \
   } while (0)
   if (in_dtype == PPST_F32 && out_dtype == PPST_F32) PPST_RS(float, float);
   else if (in_dtype == PPST_BF16 && out_dtype == PPST_BF16) PPST_RS(__nv_bfloat16, __nv_bfloat16);

@@ -251,6 +251,86 @@ static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, cons
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// GAP / GMP of a bilinear x-scale upsampled map WITHOUT materialising it (encoder_col.py:119-130: the warped 64x64
+// features are F.interpolate'd by 8 / 4 / 2 and then only ever pooled).  f32 NHWC input slice [n, lh, lw, c_off:c_off+c]
+// of a tensor with channel stride c_stride.  A "cell" is the square between four neighbouring source samples: the
+// scale^2 outputs that fall into it share the four corner loads; the half cells along the border (clamped source
+// coordinate) hold scale/2 outputs per axis.  Every output value is evaluated with the resample kernel's formula
+// (src = (o + 0.5) / scale - 0.5, clamped at 0), so it equals the materialised path value for value.
+// grid = (cell rows, n); block = (c/4 channel vectors) x (256 / (c/4) cell lanes); partials per cell row, then
+// plane_reduce_nhwc_final<1> combines them in a fixed order.
+__global__ void __launch_bounds__(256) upsample_reduce_kernel(float* __restrict__ scratch, const float* __restrict__ x,
+                                                              int lh, int lw, int c_stride, int c_off, int c, int scale,
+                                                              int rows) {
+  extern __shared__ float red[];                       // [lanes][c][2]
+  const int cv = c >> 2;
+  const int lanes = 256 / cv;
+  const int col = threadIdx.x % cv, lane = threadIdx.x / cv;
+  const int ni = blockIdx.y;
+  const int half = scale >> 1;
+  const float inv = 1.0f / (float)scale;
+  // cell row -> its output rows [oy_beg, oy_beg + ny)
+  const int cy = (int)blockIdx.x - (scale > 1 ? 1 : 0);
+  int oy_beg, ny;
+  if (scale == 1) { oy_beg = cy; ny = 1; }
+  else if (cy < 0) { oy_beg = 0; ny = half; }
+  else if (cy == lh - 1) { oy_beg = scale * lh - half; ny = half; }
+  else { oy_beg = half + cy * scale; ny = scale; }
+  const int y0 = max(cy, 0), y1 = min(y0 + 1, lh - 1);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (lane < lanes) {
+    const float* base = x + ((int64_t)ni * lh * lw) * c_stride + c_off + col * 4;
+    const int ncx = (scale > 1) ? lw + 1 : lw;
+    for (int k = lane; k < ncx; k += lanes) {
+      const int cx = k - (scale > 1 ? 1 : 0);
+      int ox_beg, nx;
+      if (scale == 1) { ox_beg = cx; nx = 1; }
+      else if (cx < 0) { ox_beg = 0; nx = half; }
+      else if (cx == lw - 1) { ox_beg = scale * lw - half; nx = half; }
+      else { ox_beg = half + cx * scale; nx = scale; }
+      const int x0 = max(cx, 0), x1 = min(x0 + 1, lw - 1);
+      const float4 v00 = *reinterpret_cast<const float4*>(base + ((int64_t)y0 * lw + x0) * c_stride);
+      const float4 v01 = *reinterpret_cast<const float4*>(base + ((int64_t)y0 * lw + x1) * c_stride);
+      const float4 v10 = *reinterpret_cast<const float4*>(base + ((int64_t)y1 * lw + x0) * c_stride);
+      const float4 v11 = *reinterpret_cast<const float4*>(base + ((int64_t)y1 * lw + x1) * c_stride);
+      const float a00[4] = {v00.x, v00.y, v00.z, v00.w}, a01[4] = {v01.x, v01.y, v01.z, v01.w};
+      const float a10[4] = {v10.x, v10.y, v10.z, v10.w}, a11[4] = {v11.x, v11.y, v11.z, v11.w};
+      for (int jy = 0; jy < ny; ++jy) {
+        float sy = inv * ((float)(oy_beg + jy) + 0.5f) - 0.5f;
+        if (sy < 0.f) sy = 0.f;
+        const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+        for (int jx = 0; jx < nx; ++jx) {
+          float sx = inv * ((float)(ox_beg + jx) + 0.5f) - 0.5f;
+          if (sx < 0.f) sx = 0.f;
+          const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = ly0 * (lx0 * a00[e] + lx1 * a01[e]) + ly1 * (lx0 * a10[e] + lx1 * a11[e]);
+            s[e] += v;
+            m[e] = fmaxf(m[e], v);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      red[((int64_t)lane * c + col * 4 + e) * 2 + 0] = s[e];
+      red[((int64_t)lane * c + col * 4 + e) * 2 + 1] = m[e];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float a = 0.f, mm = -FLT_MAX;
+    for (int l = 0; l < lanes; ++l) {
+      a += red[((int64_t)l * c + ch) * 2 + 0];
+      mm = fmaxf(mm, red[((int64_t)l * c + ch) * 2 + 1]);
+    }
+    float* o = scratch + (((int64_t)ni * rows + blockIdx.x) * c + ch) * 3;     // plane_reduce_nhwc_final<1> layout
+    o[0] = a; o[1] = 0.f; o[2] = mm;
+  }
+}
+
 __global__ void labels_to_onehot_kernel(float* __restrict__ onehot, const uint8_t* __restrict__ labels, int64_t n,
                                         int64_t hw, int n_labels) {
   const int64_t total = n * n_labels * hw;
@@ -322,6 +402,34 @@ extern "C" int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const vo
     default: PPST_RED(4);
   }
 #undef PPST_RED
+  return 0;
+}
+
+extern "C" int64_t ppst_upsample_reduce_scratch_elems(int64_t n, int lh, int c) {
+  if (n <= 0 || lh <= 0 || c <= 0) return 0;
+  return n * (int64_t)(lh + 1) * c * 3;
+}
+
+extern "C" int ppst_upsample_reduce(float* sum, float* vmax, const float* x, int64_t n, int lh, int lw, int c_stride,
+                                    int c_off, int c, int scale, float* scratch, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(x && scratch && (sum || vmax) && n > 0 && lh > 0 && lw > 0 && c > 0, PPST_ERR_ARG, "upsample_reduce: bad args");
+  PPST_REQUIRE(scale == 1 || scale == 2 || scale == 4 || scale == 8, PPST_ERR_UNSUPPORTED,
+               "upsample_reduce: scale %d (1, 2, 4 or 8)", scale);
+  PPST_REQUIRE(c % 4 == 0 && c <= 1024 && c_stride % 4 == 0 && c_off % 4 == 0 && c_off >= 0 && c_off + c <= c_stride &&
+               (reinterpret_cast<uintptr_t>(x) & 15) == 0, PPST_ERR_UNSUPPORTED,
+               "upsample_reduce: channel slice must be 16-byte aligned, c a multiple of 4 and <= 1024");
+  PPST_REQUIRE(n <= 65535, PPST_ERR_ARG, "upsample_reduce: batch too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = scale > 1 ? lh + 1 : lh;
+  const int cv = c / 4;
+  const int lanes = 256 / cv > 0 ? 256 / cv : 1;
+  PPST_REQUIRE(cv <= 256, PPST_ERR_UNSUPPORTED, "upsample_reduce: c too large");
+  const size_t smem = sizeof(float) * 2 * (size_t)lanes * c;
+  upsample_reduce_kernel<<<dim3(rows, (unsigned)n), 256, smem, st>>>(scratch, x, lh, lw, c_stride, c_off, c, scale, rows);
+  PPST_LAUNCH_CHECK("upsample_reduce_kernel");
+  plane_reduce_nhwc_final<1><<<ceil_div(n * c, 256), 256, 0, st>>>(sum, nullptr, vmax, scratch, n, c, rows);
+  PPST_LAUNCH_CHECK("plane_reduce_nhwc_final");
   return 0;
 }
 

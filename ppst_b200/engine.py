@@ -289,9 +289,41 @@ class Engine:
 
     def encoder_col_warp(self, levels, corr):
         """The correlation branch of E2 alone (encoder_col.py:168-178, 100-138) on trunk features kept from an earlier
-        encoder_col(..., levels_out=[]) pass over the same images: the warped codes without re-running the trunk."""
-        return [self._pooled_head(lvl, self._e2_warp(levels[li], corr, resize=(li < 3), scale=2 ** (3 - li)))
-                for li, lvl in enumerate(LEVELS)]
+        encoder_col(..., levels_out=[]) pass over the same images: the warped codes without re-running the trunk.
+        Tensor-core mode: the four levels' pooled features sit side by side in ONE B operand, so `corr` (the 537 MB
+        operand at batch 8) is read by one split GEMM instead of four, and the bilinear x8/x4/x2 maps that the
+        reference interpolates and then only pools are reduced on the fly (ops.upsample_reduce)."""
+        n = levels[0].shape[0]
+        sizes = []
+        for li, x in enumerate(levels):
+            h, w = x.shape[1:3]
+            sizes.append(((int(64 * h / w), 64) if h > w else (64, int(64 * w / h))) if li < 3 else (h, w))
+        chans = [x.shape[3] for x in levels]
+        fused = corr.dtype == torch.bfloat16 and len(set(sizes)) == 1 and sum(chans) <= 512 and \
+            all(c % 8 == 0 for c in chans) and all(x.shape[1] == sizes[0][0] * 2 ** (3 - li) for li, x in enumerate(levels))
+        if not fused:
+            return [self._pooled_head(lvl, self._e2_warp(levels[li], corr, resize=(li < 3), scale=2 ** (3 - li)))
+                    for li, lvl in enumerate(LEVELS)]
+        ph, pw = sizes[0]
+        pooled = torch.empty((n, ph, pw, 512), device=self.device, dtype=torch.float32)
+        off, offs = 0, []
+        for li, x in enumerate(levels):
+            if li < 3:
+                ops.resample(x, (ph, pw), 1, out=pooled, out_c_off=off)
+            else:
+                ops.affine_apply(x, x.shape[3], out=pooled, out_c_off=off)
+            offs.append(off)
+            off += chans[li]
+        if off < 512:
+            pooled[..., off:].zero_()                      # unused B rows (their output columns are never read)
+        bsp = ops.split_bf16(pooled.view(n, ph * pw, 512), transpose=True)                 # [n, 512, 2L]
+        wf = ops.gemm_split_tc(corr, bsp, (corr.shape[1] // 64, 64)).view(n, ph, pw, 512)
+        out = []
+        for li, lvl in enumerate(LEVELS):
+            scale = 2 ** (3 - li)
+            r = ops.upsample_reduce(wf, offs[li], chans[li], scale)
+            out.append(self._code_head(lvl, r["sum"], r["max"], ph * pw * scale * scale))
+        return out
 
     def encoder_col(self, image_nchw, corr=None, labels=None, taps=None, levels_out=None):
         """E2: StyleGAN2ResnetEncodercol.forward (encoder_col.py:150-251).
@@ -428,9 +460,9 @@ class Engine:
         feat = torch.empty((n, pool_hw[0], pool_hw[1], 256), device=x.device, dtype=self.adt)
         feat1 = torch.empty((n, 256, 256, 256), device=x.device, dtype=self.adt)
         for i, (c2, a, b, slope) in enumerate(feas):
-            f = self.apply(c2, a, b, pre_slope=slope)
-            ops.resample(f, pool_hw, 1, out=feat, out_c_off=64 * i)       # nn.AdaptiveAvgPool2d((h, w))
-            ops.resample(f, (256, 256), 0, out=feat1, out_c_off=64 * i)
+            # IN + PReLU of the head output applied on load: the normalised map itself is never materialised
+            ops.resample(c2, pool_hw, 1, out=feat, out_c_off=64 * i, a=a, b=b, slope=slope)   # nn.AdaptiveAvgPool2d((h, w))
+            ops.resample(c2, (256, 256), 0, out=feat1, out_c_off=64 * i, a=a, b=b, slope=slope)
         if taps is not None:
             taps["feat_cat"], taps["feat1_cat"] = feat, feat1
         for i in range(3):

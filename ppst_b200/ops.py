@@ -121,6 +121,21 @@ def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift
     return outs
 
 
+def upsample_reduce(x, c_off, c, scale, want=("sum", "max")):
+    """GAP / GMP operands of the bilinear x`scale` upsampling of x[..., c_off:c_off+c] (f32 NHWC [n,lh,lw,cs]) without
+    materialising it.  Returns dict of f32 [n, c] ("sum" over the (lh*scale)x(lw*scale) virtual map, "max")."""
+    require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, lh, lw, cs = x.shape
+    L = _L()
+    scratch = _get_scratch(x.device, L.ppst_upsample_reduce_scratch_elems(n, lh, c))
+    outs = {k: torch.empty((n, c), device=x.device, dtype=torch.float32) for k in want}
+    with _Prof("upsample_reduce", n * lh * lw * c * 4, "n%d %dx%d c%d x%d" % (n, lh, lw, c, scale)):
+        check(L.ppst_upsample_reduce(ptr(outs.get("sum")), ptr(outs.get("max")), ptr(x), n, lh, lw, cs, c_off, c, scale,
+                                     ptr(scratch), stream()))
+    return outs
+
+
 def labels_to_onehot(labels, n_labels=3):
     require_cuda(labels)
     n, h, w = labels.shape
@@ -252,15 +267,20 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
     return out
 
 
-def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0):
-    """mode 0 bilinear (align_corners False), 1 adaptive average.  x NHWC dense."""
-    require_cuda(x)
+def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0, a=None, b=None, slope=1.0):
+    """mode 0 bilinear (align_corners False), 1 adaptive average.  x NHWC dense.
+    a / b (f32 [n, c]) + slope: every source sample is first mapped to lrelu(x*a + b, slope)."""
+    require_cuda(x, a, b)
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty((n, out_hw[0], out_hw[1], c), device=x.device, dtype=out_dtype or x.dtype)
-    with _Prof("resample", x.numel() * x.element_size() + n * out_hw[0] * out_hw[1] * c * out.element_size()):
+    if a is not None:
+        assert a.dtype == torch.float32 and a.is_contiguous() and a.shape == (n, c)
+        assert b is None or (b.dtype == torch.float32 and b.is_contiguous() and b.shape == (n, c))
+    with _Prof("resample", x.numel() * x.element_size() + n * out_hw[0] * out_hw[1] * c * out.element_size(),
+               "n%d %dx%d->%dx%d c%d m%d" % (n, h, w, out_hw[0], out_hw[1], c, mode)):
         check(_L().ppst_resample(ptr(out), ptr(x), n, h, w, out_hw[0], out_hw[1], c, out.shape[3], out_c_off, mode,
-                                 dt(x), dt(out), stream()))
+                                 dt(x), dt(out), ptr(a), ptr(b), float(slope), stream()))
     return out
 
 

@@ -222,6 +222,27 @@ def test_plane_reduce_layouts_and_regions():
         assert torch.equal(r["max"][:, i].cpu(), xm.amax((2, 3)))
 
 
+def test_upsample_reduce_matches_interpolate_then_pool():
+    """encoder_col.py:119-130 + :160-166: F.interpolate(bilinear, align_corners=False) followed by GAP / GMP, fused."""
+    from ppst_b200 import ops
+    for (n, lh, lw, cs, c_off, c, scale) in [(2, 64, 64, 512, 0, 32, 8), (2, 64, 64, 512, 32, 64, 4),
+                                             (3, 64, 64, 512, 96, 128, 2), (2, 64, 64, 512, 224, 256, 1),
+                                             (1, 5, 7, 16, 4, 8, 4), (2, 3, 3, 8, 0, 8, 2), (1, 1, 1, 4, 0, 4, 8)]:
+        x = torch.randn(n, lh, lw, cs, generator=gen(lh * 31 + scale))
+        r = ops.upsample_reduce(x.to(DEV), c_off, c, scale)
+        xs = x[..., c_off:c_off + c].permute(0, 3, 1, 2).contiguous()
+        up = F.interpolate(xs, scale_factor=scale, mode="bilinear", align_corners=False) if scale > 1 else xs
+        ref_sum, ref_max = up.sum(dim=(2, 3)), up.amax(dim=(2, 3))
+        tol = 1e-5 * max(1.0, float(ref_sum.abs().max()))
+        assert (r["sum"].cpu() - ref_sum).abs().max() <= max(tol, 2e-3), (lh, lw, c, scale)
+        assert (r["max"].cpu() - ref_max).abs().max() <= 1e-5, (lh, lw, c, scale)
+    # a sample's result does not depend on the batch it is reduced in
+    x = torch.randn(4, 64, 64, 512, generator=gen(5)).to(DEV)
+    a = ops.upsample_reduce(x, 32, 64, 4)
+    b = ops.upsample_reduce(x[1:2].contiguous(), 32, 64, 4)
+    assert torch.equal(a["sum"][1:2], b["sum"]) and torch.equal(a["max"][1:2], b["max"])
+
+
 def test_layout_roundtrip():
     from ppst_b200 import ops
     x = torch.randn(2, 19, 13, 21, generator=gen(31))
@@ -489,6 +510,14 @@ def test_resample():
     dst = torch.zeros(2, 8, 8, 64, device=DEV)
     ops.resample(xin, (8, 8), 1, out=dst, out_c_off=32)
     assert (dst[..., 32:48].permute(0, 3, 1, 2).cpu() - F.adaptive_avg_pool2d(x, 8)).abs().max() <= 1e-5
+    # normalisation + PReLU of the source applied on load (the feature-head tails, generator.py:272-278)
+    a, b = torch.randn(2, 16, generator=gen(62)), torch.randn(2, 16, generator=gen(63))
+    xt = F.leaky_relu(x * a[:, :, None, None] + b[:, :, None, None], 0.25)
+    for xi, xr in ((xin, xt), (xin.bfloat16(), F.leaky_relu(x.bfloat16().float() * a[:, :, None, None] + b[:, :, None, None], 0.25))):
+        y = ops.resample(xi, (16, 16), 0, a=a.to(DEV), b=b.to(DEV), slope=0.25, out_dtype=torch.float32)
+        assert (y.permute(0, 3, 1, 2).cpu() - F.interpolate(xr, (16, 16), mode="bilinear")).abs().max() <= 1e-5
+        y = ops.resample(xi, (4, 4), 1, a=a.to(DEV), b=b.to(DEV), slope=0.25, out_dtype=torch.float32)
+        assert (y.permute(0, 3, 1, 2).cpu() - F.adaptive_avg_pool2d(xr, 4)).abs().max() <= 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ dense / corr
@@ -535,6 +564,21 @@ def test_rselfcorr_and_corr_prepare():
     want = torch.einsum("bcli,bclj->blij", p, p).reshape(b, h // 4, w // 4, 256)
     got = ops.rselfcorr(ops.nchw_to_nhwc(fea.to(DEV)))
     assert (got.cpu() - want).abs().max() <= 1e-5
+    # bf16 input written into an f32 channel slice (the swap path), and a width that takes the generic kernel
+    fb = fea.bfloat16()
+    pb = fb.float().reshape(b, c, h // 4, 4, w // 4, 4).permute(0, 1, 2, 4, 3, 5).reshape(b, c, -1, 16)
+    pb = pb - pb.mean(1, keepdim=True)
+    pb = pb / (pb.pow(2).sum(1, keepdim=True).sqrt() + 2.220446049250313e-16)
+    wantb = torch.einsum("bcli,bclj->blij", pb, pb).reshape(b, h // 4, w // 4, 256)
+    slab = torch.full((b, h // 4, w // 4, 512), 7.0, device=DEV)
+    ops.rselfcorr(ops.nchw_to_nhwc(fb.to(DEV)), out=slab, out_c_off=256)
+    assert (slab[..., 256:].cpu() - wantb).abs().max() <= 1e-5 and bool((slab[..., :256] == 7.0).all())
+    f32c = torch.randn(1, 32, 8, 8, generator=g)
+    p32 = f32c.reshape(1, 32, 2, 4, 2, 4).permute(0, 1, 2, 4, 3, 5).reshape(1, 32, -1, 16)
+    p32 = p32 - p32.mean(1, keepdim=True)
+    p32 = p32 / (p32.pow(2).sum(1, keepdim=True).sqrt() + 2.220446049250313e-16)
+    want32 = torch.einsum("bcli,bclj->blij", p32, p32).reshape(1, 2, 2, 256)
+    assert (ops.rselfcorr(ops.nchw_to_nhwc(f32c.to(DEV))).cpu() - want32).abs().max() <= 1e-5
     f = torch.randn(1, 512, 8, 8, generator=g)
     rows = ops.nchw_to_nhwc(f.to(DEV))
     prep = ops.corr_prepare(rows, 256).cpu().reshape(64, 512)
