@@ -130,8 +130,10 @@ PPST_API int ppst_labels_pool_or(uint8_t* out, const uint8_t* in, int64_t n, int
  * written at channel offset c_off (used to build concatenated feature maps, generator.py:272-278). */
 PPST_API int ppst_nchw_to_nhwc(void* dst, const void* src, int64_t n, int64_t c, int64_t hw, int64_t dst_c, int64_t c_off,
                       int src_dtype, int dst_dtype, void* stream);
+/* nhwc_to_nchw: a, b = NULL, or f32 [n, c] (b may be NULL): dst = src * a + b per (sample, channel) -- the InstanceNorm +
+ * StyleMod of ToRGB (stylegan2_layers.py:477-495) folded into the conversion to the reference's NCHW image layout. */
 PPST_API int ppst_nhwc_to_nchw(void* dst, const void* src, int64_t n, int64_t c, int64_t hw, int64_t src_c, int64_t c_off,
-                      int src_dtype, int dst_dtype, void* stream);
+                      int src_dtype, int dst_dtype, const float* a, const float* b, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * convolution (NHWC activations, weights packed [phase][cout][kh*kw*cin])
@@ -235,6 +237,15 @@ typedef struct {
 /* out: [n, h*up + pad_t + pad_b, w*up + pad_l + pad_r, out_c_stride]; a,b,ra,rb: f32 [n, c] or NULL (1 / 0). */
 PPST_API int ppst_affine_apply(void* out, const void* x, const float* a, const float* b, const void* res,
                       const float* ra, const float* rb, const ppst_apply_desc* d, void* stream);
+
+/* ppst_affine_apply with a bilinear-x2 skip (the end of UpsamplingResBlock64, generator.py:63-77) fused with the ToRGB
+ * 1x1 convolution that follows it (stylegan2_layers.py:477-495, conv only: 128 -> 3 channels + bias):
+ *   rgb_out f32 [n, h, w, 3] = conv1x1(bf16(apply(x, a, b, res)), rgb_w [3, 128]) + rgb_bias [3]
+ * out: the bf16 activation itself [n, h, w, out_c_stride], or NULL when nothing else reads it (plain decode).
+ * d: c == 128, res_mode == 2, up == 1, no padding, bf16 in / out, h even, w % 64 == 0. */
+PPST_API int ppst_affine_apply_torgb(void* out, float* rgb_out, const void* x, const float* a, const float* b,
+                            const void* res, const float* rgb_w, const float* rgb_bias, const ppst_apply_desc* d,
+                            void* stream);
 
 /* Resampling into a channel slice of an NHWC tensor.
  * mode 0: bilinear, align_corners=False (F.interpolate, generator.py:274,277; encoder_col.py:130)

@@ -50,7 +50,9 @@ _SIGS = {
     "ppst_labels_pool_or": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_labels_to_onehot": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_void_p]),
     "ppst_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),
-    "ppst_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),
+    "ppst_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p]),
+    "ppst_affine_apply_torgb": (c_int, [c_void_p] * 8 + [ctypes.POINTER(ApplyDesc), c_void_p]),
     "ppst_conv_simt": (c_int, [c_void_p] * 5 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),

@@ -359,6 +359,142 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
   }
 }
 
+// Bilinear-x2 skip variant of the row kernel (generator.py:75, the end of every UpsamplingResnetBlock), no padding / no
+// nearest upsampling.  A thread owns 8 channels and a run of FOUR consecutive output pixels = two low-res columns: the
+// 2 x 4 low-res samples around them are loaded once (8 loads instead of 16), blended vertically in fp32, and every
+// output takes two of the four blended columns.  4 independent 16-byte loads of x per thread x 512 threads per SM keep
+// ~32 KB of the HBM stream in flight (the generic RES == 2 instance above holds 16 KB and reaches 0.45 of HBM).
+//
+// RGB != 0 (c == 128 only): the ToRGB 1x1 convolution (stylegan2_layers.py:477-495, 128 -> 3) of the tensor being written
+// is computed on the fly from the ROUNDED values -- 24 FMAs per thread, then a 15-shuffle reduction of the 4 pixels x 3
+// outputs over the 16 lanes that share a pixel -- so ToRGB never re-reads the 512^2 x 128 activation; RGB == 2 does not
+// even write it (plain decode: nothing else consumes the last block's output).
+template <typename TX, typename TO, bool RAB, int RGB>
+__global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
+                                                                         const float* __restrict__ a, const float* __restrict__ b,
+                                                                         const TX* __restrict__ res, const float* __restrict__ ra,
+                                                                         const float* __restrict__ rb, ppst_apply_desc d,
+                                                                         float* __restrict__ rgb_out,
+                                                                         const float* __restrict__ rgb_w,
+                                                                         const float* __restrict__ rgb_bias) {
+  constexpr int V = 8;
+  const int cv = d.c / V;
+  const int lanes = 256 / cv;
+  const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
+  if (RGB == 0 && lane >= lanes) return;              // RGB: cv == 16, every thread is live (warp shuffles below)
+  const int oy = blockIdx.x, ni = blockIdx.y;
+  const int ch = cg * V;
+  const int h = d.h, w = d.w, lh = h / 2, lw = w / 2;
+  float av[V], bv[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; }
+  if (a) load_ch<float, V>(av, a + (int64_t)ni * d.c + ch);
+  if (b) load_ch<float, V>(bv, b + (int64_t)ni * d.c + ch);
+  float rav[RAB ? V : 1], rbv[RAB ? V : 1];
+  if (RAB) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { rav[e] = 1.0f; rbv[e] = 0.0f; }
+    if (ra) load_ch<float, V>(*reinterpret_cast<float(*)[V]>(rav), ra + (int64_t)ni * d.c + ch);
+    if (rb) load_ch<float, V>(*reinterpret_cast<float(*)[V]>(rbv), rb + (int64_t)ni * d.c + ch);
+  }
+  const Bilin2 by = bilin_x2(oy, lh);
+  const TX* xrow = x + (((int64_t)ni * h + oy) * w) * d.c + ch;
+  TO* orow = out + (((int64_t)ni * h + oy) * w) * d.out_c_stride + d.out_c_off + ch;
+  const TX* r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
+  const TX* r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
+  const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
+  float wr[RGB ? 3 : 1][RGB ? V : 1];
+  float* rgb_row = nullptr;
+  if (RGB) {
+#pragma unroll
+    for (int co = 0; co < 3; ++co) load_ch<float, V>(*reinterpret_cast<float(*)[V]>(wr[RGB ? co : 0]), rgb_w + co * d.c + ch);
+    rgb_row = rgb_out + (((int64_t)ni * h + oy) * w) * 3;
+  }
+  const int sweeps = (lw + 2 * lanes - 1) / (2 * lanes);       // uniform trip count (the RGB reduction shuffles)
+  for (int sw = 0; sw < sweeps; ++sw) {
+    const int j0 = 2 * lane + sw * 2 * lanes;
+    if (j0 >= lw) continue;                                    // never taken with RGB (w % 64 == 0, host-checked)
+    // low-res columns j0-1 .. j0+2 (clamped) serve output pixels 2*j0 .. 2*j0+3
+    int col[4];
+    col[0] = max(j0 - 1, 0); col[1] = j0; col[2] = min(j0 + 1, lw - 1); col[3] = min(j0 + 2, lw - 1);
+    const int ox0 = 2 * j0;
+    Raw8<TX> xr[4], q0[4], q1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ox0 + u < w) xr[u] = ld_raw8<TX>(xrow + (int64_t)(ox0 + u) * d.c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q0[k] = ld_raw8_cached<TX>(r0 + (int64_t)col[k] * d.c);
+      q1[k] = ld_raw8_cached<TX>(r1 + (int64_t)col[k] * d.c);
+    }
+    float t[4][V];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f0[V], f1[V];
+      cvt8(q0[k], f0);
+      cvt8(q1[k], f1);
+#pragma unroll
+      for (int e = 0; e < V; ++e) t[k][e] = by.l0 * f0[e] + by.l1 * f1[e];
+    }
+    float part[RGB ? 12 : 1];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (RGB) { part[RGB ? 3 * u : 0] = 0.f; part[RGB ? 3 * u + 1 : 0] = 0.f; part[RGB ? 3 * u + 2 : 0] = 0.f; }
+      if (ox0 + u >= w) continue;
+      const Bilin2 bx = bilin_x2(ox0 + u, lw);
+      const int kl = (u + 1) >> 1;                 // u = 0: columns (0,1); 1, 2: (1,2); 3: (2,3)
+      float y[V];
+      cvt8(xr[u], y);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        y[e] = lrelu_slope(fmaf(y[e], av[e], bv[e]), pre_slope) * pre_gain;
+        const float r = bx.l0 * t[kl][e] + bx.l1 * t[kl + 1][e];
+        y[e] += RAB ? fmaf(r, rav[RAB ? e : 0], rbv[RAB ? e : 0]) : r;
+        y[e] = lrelu_slope(y[e], post_slope) * post_gain;
+      }
+      if (RGB != 2) store_ch<TO, V>(orow + (int64_t)(ox0 + u) * d.out_c_stride, y);
+      if (RGB) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float yq = Cvt<TO>::to_f(Cvt<TO>::from_f(y[e]));            // what a reader of `out` would see
+#pragma unroll
+          for (int co = 0; co < 3; ++co)
+            part[RGB ? 3 * u + co : 0] = fmaf(yq, wr[RGB ? co : 0][RGB ? e : 0], part[RGB ? 3 * u + co : 0]);
+        }
+      }
+    }
+    if (RGB) {
+      // 12 partial sums x 16 lanes -> lane quad q = 2*b3 + b2 ends up with the 3 channel totals of pixel q
+      const bool b3 = (threadIdx.x & 8) != 0, b2 = (threadIdx.x & 4) != 0;
+      float q6[6], r3[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float mine = b3 ? part[RGB ? 6 + i : 0] : part[RGB ? i : 0];
+        const float other = b3 ? part[RGB ? i : 0] : part[RGB ? 6 + i : 0];
+        q6[i] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float mine = b2 ? q6[3 + i] : q6[i];
+        const float other = b2 ? q6[i] : q6[3 + i];
+        r3[i] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        r3[i] += __shfl_xor_sync(0xffffffffu, r3[i], 2);
+        r3[i] += __shfl_xor_sync(0xffffffffu, r3[i], 1);
+      }
+      const int u = (b3 ? 2 : 0) + (b2 ? 1 : 0);
+      if ((threadIdx.x & 3) == 0 && ox0 + u < w) {
+        float* o = rgb_row + (int64_t)(ox0 + u) * 3;
+        o[0] = r3[0] + (rgb_bias ? rgb_bias[0] : 0.f);
+        o[1] = r3[1] + (rgb_bias ? rgb_bias[1] : 0.f);
+        o[2] = r3[2] + (rgb_bias ? rgb_bias[2] : 0.f);
+      }
+    }
+  }
+}
+
 // mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows)
 template <typename TX, typename TO, int V>
 __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, const TX* __restrict__ x, int64_t n,
@@ -482,6 +618,7 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
   const bool rows = vec && (d.c / 8) <= 256 && d.n <= 65535 &&
                     ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ra) |
                       reinterpret_cast<uintptr_t>(rb)) & 15) == 0;
+  const bool bilin_fast = d.res_mode == 2 && d.up == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 && d.pad_r == 0;
 #define PPST_APPLY(TX, TO)                                                                                           \
   do {                                                                                                               \
     if (rows && d.res_mode == 0)                                                                                     \
@@ -490,6 +627,12 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
     else if (rows && d.res_mode == 1)                                                                                \
       affine_apply_rows_kernel<TX, TO, 1><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b,              \
                                                                           (const TX*)res, ra, rb, d);                \
+    else if (rows && bilin_fast && !(ra || rb))                                                                      \
+      affine_apply_bilin_rows_kernel<TX, TO, false, 0><<<dim3(oh_, d.n), 256, 0, st>>>(                              \
+          (TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d, nullptr, nullptr, nullptr);                       \
+    else if (rows && bilin_fast)                                                                                     \
+      affine_apply_bilin_rows_kernel<TX, TO, true, 0><<<dim3(oh_, d.n), 256, 0, st>>>(                               \
+          (TO*)out, (const TX*)x, a, b, (const TX*)res, ra, rb, d, nullptr, nullptr, nullptr);                       \
     else if (rows)                                                                                                   \
       affine_apply_rows_kernel<TX, TO, 2><<<dim3(oh_, d.n), 256, 0, st>>>((TO*)out, (const TX*)x, a, b,              \
                                                                           (const TX*)res, ra, rb, d);                \
@@ -505,6 +648,35 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
   else PPST_REQUIRE(false, PPST_ERR_DTYPE, "affine_apply: dtype combination %d -> %d", d.x_dtype, d.out_dtype);
 #undef PPST_APPLY
   PPST_LAUNCH_CHECK("affine_apply_kernel");
+  return 0;
+}
+
+extern "C" int ppst_affine_apply_torgb(void* out, float* rgb_out, const void* x, const float* a, const float* b,
+                                       const void* res, const float* rgb_w, const float* rgb_bias,
+                                       const ppst_apply_desc* dp, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(rgb_out && x && res && rgb_w && dp, PPST_ERR_ARG, "affine_apply_torgb: null argument");
+  const ppst_apply_desc d = *dp;
+  PPST_REQUIRE(d.n > 0 && d.n <= 65535 && d.h > 0 && d.w > 0 && d.h % 2 == 0 && d.w % 64 == 0, PPST_ERR_ARG,
+               "affine_apply_torgb: bad geometry (h even, w a multiple of 64: whole warps stay converged)");
+  PPST_REQUIRE(d.c == 128 && d.res_mode == 2 && d.up == 1 && d.pad_t == 0 && d.pad_b == 0 && d.pad_l == 0 && d.pad_r == 0,
+               PPST_ERR_UNSUPPORTED, "affine_apply_torgb: c must be 128 with a bilinear-x2 skip and no padding / upsampling");
+  PPST_REQUIRE(d.x_dtype == PPST_BF16 && d.res_dtype == PPST_BF16 && d.out_dtype == PPST_BF16, PPST_ERR_DTYPE,
+               "affine_apply_torgb: bf16 activations");
+  PPST_REQUIRE(out == nullptr || (d.out_c_stride % 8 == 0 && d.out_c_off % 8 == 0 && d.out_c_off + d.c <= d.out_c_stride),
+               PPST_ERR_ARG, "affine_apply_torgb: channel slice");
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res) |
+                 reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(rgb_w)) & 15) == 0,
+               PPST_ERR_ARG, "affine_apply_torgb: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 T;
+  if (out)
+    affine_apply_bilin_rows_kernel<T, T, false, 1><<<dim3(d.h, d.n), 256, 0, st>>>(
+        (T*)out, (const T*)x, a, b, (const T*)res, nullptr, nullptr, d, rgb_out, rgb_w, rgb_bias);
+  else
+    affine_apply_bilin_rows_kernel<T, T, false, 2><<<dim3(d.h, d.n), 256, 0, st>>>(
+        nullptr, (const T*)x, a, b, (const T*)res, nullptr, nullptr, d, rgb_out, rgb_w, rgb_bias);
+  PPST_LAUNCH_CHECK("affine_apply_bilin_rows_kernel(torgb)");
   return 0;
 }
 

@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(TD* __restrict__ dst,
 // src [n, hw, src_c] (channel offset c_off) -> dst [n, c, hw]
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(TD* __restrict__ dst, const TS* __restrict__ src, int64_t c,
-                                                           int64_t hw, int64_t src_c, int64_t c_off) {
+                                                           int64_t hw, int64_t src_c, int64_t c_off,
+                                                           const float* __restrict__ a, const float* __restrict__ b) {
   __shared__ float tile[32][33];
   const int64_t n = blockIdx.z;
   const int64_t p0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
@@ -38,7 +39,11 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(TD* __restrict__ dst,
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
     const int64_t ch = c0 + j, p = p0 + tx;
-    if (ch < c && p < hw) dst[(n * c + ch) * hw + p] = Cvt<TD>::from_f(tile[tx][j]);
+    if (ch < c && p < hw) {
+      float v = tile[tx][j];
+      if (a) v = fmaf(v, a[n * c + ch], b ? b[n * c + ch] : 0.0f);       // per-(n, c) affine (ToRGB's IN + StyleMod)
+      dst[(n * c + ch) * hw + p] = Cvt<TD>::from_f(v);
+    }
   }
 }
 
@@ -62,7 +67,8 @@ extern "C" int ppst_nchw_to_nhwc(void* dst, const void* src, int64_t n, int64_t 
 }
 
 extern "C" int ppst_nhwc_to_nchw(void* dst, const void* src, int64_t n, int64_t c, int64_t hw, int64_t src_c,
-                                 int64_t c_off, int src_dtype, int dst_dtype, void* stream) {
+                                 int64_t c_off, int src_dtype, int dst_dtype, const float* a, const float* b,
+                                 void* stream) {
   using namespace ppst;
   PPST_REQUIRE(dst && src && n > 0 && c > 0 && hw > 0 && c_off >= 0 && c_off + c <= src_c, PPST_ERR_ARG,
                "nhwc_to_nchw: bad args");
@@ -70,7 +76,7 @@ extern "C" int ppst_nhwc_to_nchw(void* dst, const void* src, int64_t n, int64_t 
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), (unsigned)n);
   cudaStream_t st = (cudaStream_t)stream;
   PPST_DISPATCH2(src_dtype, dst_dtype, TS, TD,
-                 nhwc_to_nchw_kernel<TS, TD><<<grid, 256, 0, st>>>((TD*)dst, (const TS*)src, c, hw, src_c, c_off));
+                 nhwc_to_nchw_kernel<TS, TD><<<grid, 256, 0, st>>>((TD*)dst, (const TS*)src, c, hw, src_c, c_off, a, b));
   PPST_LAUNCH_CHECK("nhwc_to_nchw_kernel");
   return 0;
 }

@@ -412,10 +412,11 @@ class Engine:
         a, b = self.coeffs(c2, st)
         return self.apply(c2, a, b, res=x, res_mode=1, post_slope=P["a"])
 
-    def generator(self, sp, codes, extract_features=False, noises=None, taps=None):
+    def generator(self, sp, codes, extract_features=False, noises=None, taps=None, nchw_out=False):
         """StyleGAN2ResnetGenerator.forward (generator.py:244-281).  sp NHWC [n,h,w,256] (engine dtype),
-        codes: 4 x f32 [n,2048].  Returns rgb NHWC f32 [n,8h,8w,3] (and fea NHWC [n,64,64,256], fea1 NHWC
-        [n,256,256,64] when extract_features)."""
+        codes: 4 x f32 [n,2048].  Returns rgb NHWC f32 [n,8h,8w,3] (nchw_out: NCHW f32 [n,3,8h,8w], ToRGB's affine
+        folded into the layout conversion) (and fea NHWC [n,64,64,256], fea1 NHWC [n,256,256,64] when
+        extract_features)."""
         G = self.G
         noises = noises or {}          # device f32 [n,1,H,W] tensors (SwapModel.set_noises moves them once)
         codes = [ops.l2_normalize(c.to(self.device, torch.float32), 1e-8, 0) for c in codes]   # util.normalize
@@ -444,16 +445,25 @@ class Engine:
             y, a, b = self._styled(B["conv1"], x, st["up%d.conv1" % res], noises.get(name + ".conv1"), upsample=True)
             h = self.apply(y, a, b)
             y, a, b = self._styled(B["conv2"], h, st["up%d.conv2" % res], noises.get(name + ".conv2"))
-            x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2)     # bilinear x2 skip, generator.py:75
+            yrgb = None
+            last = j == len(UP_CH) - 1
+            if (last and self.use_tc and taps is None and y.dtype == torch.bfloat16 and y.shape[3] == 128
+                    and y.shape[2] % 64 == 0 and y.shape[1] % 2 == 0):
+                # last block: ToRGB's 1x1 conv rides on the pass that writes x; plain decode does not write x at all
+                x, yrgb = ops.affine_apply_torgb(y, a, b, skip, G["rgb"].w32[0], G["rgb"].bias, post_gain=INV_SQRT2,
+                                                 write_out=extract_features)
+            else:
+                x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2)     # bilinear x2 skip, generator.py:75
             if taps is not None:
                 taps[name] = x
             if extract_features:
                 feas.append(self._feature_head(G["layer%d" % (2 ** (j + 6))], x))
         # ToRGB (stylegan2_layers.py:477-495); fp32 from here on (3-channel IN is sensitive)
-        n, h, w, _ = x.shape
-        yrgb = ops.conv1x1_thin_out(x, G["rgb"].w32[0], G["rgb"].bias)
+        if yrgb is None:
+            yrgb = ops.conv1x1_thin_out(x, G["rgb"].w32[0], G["rgb"].bias)
+        n, h, w, _ = yrgb.shape
         a, b = self.coeffs(yrgb, style=st["rgb"])
-        rgb = self.apply(yrgb, a, b)
+        rgb = ops.nhwc_to_nchw(yrgb, a=a, b=b) if nchw_out else self.apply(yrgb, a, b)
         if not extract_features:
             return rgb
         # generator.py:272-280: concat pooled / bilinear-resampled heads, then layert / layert1

@@ -110,7 +110,7 @@ class SwapModel:
         goes through the guided-filter smoothing of photo_gif.GIFSmoothing(r=30, eps=(0.02*255)**2) -- on the device,
         without the reference's host round trip."""
         sp = self.engine.to_nhwc(spatial_code)
-        rgb = self._out(self.engine.generator(sp, global_code, noises=self._noises_for(sp.shape[0])))
+        rgb = self.engine.generator(sp, global_code, noises=self._noises_for(sp.shape[0]), nchw_out=True)
         if target is not None:
             rgb = ops.guided_smooth(rgb, self._in(target))
         return rgb
@@ -118,8 +118,8 @@ class SwapModel:
     def extract_feat(self, spatial_code, global_code):
         """ppst_model.py:308-309 -> (rgb, fea, fea1)."""
         sp = self.engine.to_nhwc(spatial_code)
-        rgb, fea, fea1 = self.engine.generator(sp, global_code, extract_features=True, noises=self.noises)
-        return self._out(rgb), self._out(fea), self._out(fea1)
+        rgb, fea, fea1 = self.engine.generator(sp, global_code, extract_features=True, noises=self.noises, nchw_out=True)
+        return rgb, self._out(fea), self._out(fea1)
 
     def extract_feat_from_image(self, img):
         """ppst_model.py:311-315 -> (fea [B,256,64,64], fea1 [B,64,256,256])."""
@@ -187,8 +187,7 @@ class SwapModel:
         corr = e.corrm(fs, fc, split_out=e.use_tc)
         gl_w = e.encoder_col_warp([x[n:] for x in levels], corr)
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
-        rgb = e.generator(sp_c, codes, noises=self._noises_for(n))
-        return rgb if return_nhwc else self._out(rgb)
+        return e.generator(sp_c, codes, noises=self._noises_for(n), nchw_out=not return_nhwc)
 
     def plain_swap(self, content, style, return_nhwc=False):
         """G(E1(content), E2(style)) without the correlation branch: the only swap the reference can run away from
@@ -197,8 +196,7 @@ class SwapModel:
         e = self.engine
         sp = e.encoder_con(self._in(content))
         gl, _ = e.encoder_col(self._in(style))
-        rgb = e.generator(sp, gl, noises=self._noises_for(sp.shape[0]))
-        return rgb if return_nhwc else self._out(rgb)
+        return e.generator(sp, gl, noises=self._noises_for(sp.shape[0]), nchw_out=not return_nhwc)
 
     def swap_grid(self, contents, styles, cell_batch=8, smooth=False):
         """Every (content i, style j) cell of evaluation/content_style_grid_generation_evaluator.py:57-91 in one call:
@@ -228,7 +226,7 @@ class SwapModel:
             sj = torch.tensor([c[1] for c in chunk], device=self.device)
             corr = e.corrm(f2.index_select(0, sj + nc), f2.index_select(0, ci), split_out=e.use_tc)
             gl_w = e.encoder_col_warp([x.index_select(0, sj) for x in lv_s], corr)
-            rgb = self._out(e.generator(sp_c.index_select(0, ci), gl_w, noises=self._noises_for(len(chunk))))
+            rgb = e.generator(sp_c.index_select(0, ci), gl_w, noises=self._noises_for(len(chunk)), nchw_out=True)
             if smooth:
                 rgb = ops.guided_smooth(rgb, xc.index_select(0, ci))
             out.view(nc * ns, *out.shape[2:])[k0:k0 + len(chunk)] = rgb

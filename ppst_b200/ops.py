@@ -77,12 +77,16 @@ def nchw_to_nhwc(x, dtype=None, out=None, c_off=0):
     return out
 
 
-def nhwc_to_nchw(x, c=None, c_off=0, dtype=None):
-    require_cuda(x)
+def nhwc_to_nchw(x, c=None, c_off=0, dtype=None, a=None, b=None):
+    """NHWC [n,h,w,cs] channel slice -> NCHW [n,c,h,w]; optional per-(n, c) affine a, b (f32 [n, c]) on the way."""
+    require_cuda(x, a, b)
     n, h, w, cs = x.shape
     c = cs if c is None else c
     out = torch.empty((n, c, h, w), device=x.device, dtype=dtype or x.dtype)
-    check(_L().ppst_nhwc_to_nchw(ptr(out), ptr(x), n, c, h * w, cs, c_off, dt(x), dt(out), stream()))
+    if a is not None:
+        assert a.dtype == torch.float32 and a.is_contiguous() and a.shape == (n, c)
+        assert b is None or (b.dtype == torch.float32 and b.is_contiguous() and b.shape == (n, c))
+    check(_L().ppst_nhwc_to_nchw(ptr(out), ptr(x), n, c, h * w, cs, c_off, dt(x), dt(out), ptr(a), ptr(b), stream()))
     return out
 
 
@@ -265,6 +269,29 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
         check(_L().ppst_affine_apply(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d),
                                      stream()))
     return out
+
+
+def affine_apply_torgb(x, a, b, res, rgb_w, rgb_bias, post_gain=1.0, write_out=True):
+    """The last UpsamplingResBlock tail + ToRGB's 1x1 conv in one pass (ppst_affine_apply_torgb).
+    x bf16 NHWC [n,h,w,128], res bf16 [n,h/2,w/2,128] -> (out bf16 [n,h,w,128] or None, rgb f32 [n,h,w,3])."""
+    require_cuda(x, a, b, res, rgb_w, rgb_bias)
+    n, h, w, c = x.shape
+    assert x.is_contiguous() and res.is_contiguous() and rgb_w.is_contiguous() and rgb_w.shape == (3, c)
+    out = torch.empty_like(x) if write_out else None
+    rgb = torch.empty((n, h, w, 3), device=x.device, dtype=torch.float32)
+    d = ApplyDesc()
+    d.n, d.h, d.w, d.c, d.up = n, h, w, c, 1
+    d.pad_t = d.pad_b = d.pad_l = d.pad_r = 0
+    d.pad_mode = 0
+    d.pre_slope, d.pre_gain, d.post_slope, d.post_gain = 1.0, 1.0, 1.0, post_gain
+    d.res_mode = 2
+    d.x_dtype = d.out_dtype = d.res_dtype = dt(x)
+    d.out_c_stride, d.out_c_off = c, 0
+    nbytes = x.numel() * 2 + res.numel() * 2 + (x.numel() * 2 if write_out else 0) + rgb.numel() * 4
+    with _Prof("affine_apply", nbytes, "n%d %dx%d c%d res2+torgb out%d" % (n, h, w, c, int(write_out))):
+        check(_L().ppst_affine_apply_torgb(ptr(out), ptr(rgb), ptr(x), ptr(a), ptr(b), ptr(res), ptr(rgb_w),
+                                           ptr(rgb_bias), ctypes.byref(d), stream()))
+    return out, rgb
 
 
 def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0, a=None, b=None, slope=1.0):

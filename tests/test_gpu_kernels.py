@@ -243,6 +243,37 @@ def test_upsample_reduce_matches_interpolate_then_pool():
     assert torch.equal(a["sum"][1:2], b["sum"]) and torch.equal(a["max"][1:2], b["max"])
 
 
+def test_affine_apply_torgb_and_affine_layout_conversion():
+    """UpsamplingResBlock64 tail + ToRGB conv in one pass (generator.py:63-77, stylegan2_layers.py:477-495), and the
+    ToRGB IN + StyleMod affine folded into the NHWC -> NCHW conversion."""
+    from ppst_b200 import ops
+    g = gen(77)
+    n, h, w, c = 2, 8, 128, 128
+    y = torch.randn(n, c, h, w, generator=g).bfloat16()
+    lo = torch.randn(n, c, h // 2, w // 2, generator=g).bfloat16()
+    a, b = torch.rand(n, c, generator=g) + 0.5, torch.randn(n, c, generator=g)
+    wr, br = torch.randn(3, c, generator=g) / math.sqrt(c), torch.randn(3, generator=g)
+    want_x = ((y.float() * a[:, :, None, None] + b[:, :, None, None] +
+               F.interpolate(lo.float(), scale_factor=2, mode="bilinear", align_corners=False)) / math.sqrt(2)).bfloat16()
+    want_rgb = F.conv2d(want_x.float(), wr.view(3, c, 1, 1), br)
+    yn, ln = ops.nchw_to_nhwc(y.to(DEV)), ops.nchw_to_nhwc(lo.to(DEV))
+    for write_out in (True, False):
+        x, rgb = ops.affine_apply_torgb(yn, a.to(DEV), b.to(DEV), ln, wr.to(DEV), br.to(DEV), post_gain=1 / math.sqrt(2),
+                                        write_out=write_out)
+        assert (x is None) == (not write_out)
+        if write_out:
+            # same values as the unfused kernel, bit for bit
+            ref = ops.affine_apply(yn, c, a.to(DEV), b.to(DEV), res=ln, res_mode=2, post_gain=1 / math.sqrt(2))
+            assert torch.equal(x, ref)
+            assert (x.float().permute(0, 3, 1, 2).cpu() - want_x.float()).abs().max() <= 4e-2
+            thin = ops.conv1x1_thin_out(ref, wr.to(DEV), br.to(DEV))
+            assert (rgb - thin).abs().max() <= 1e-4
+        assert (rgb.permute(0, 3, 1, 2).cpu() - want_rgb).abs().max() <= 5e-2
+    ra, rb = torch.rand(n, 3, generator=g) + 0.5, torch.randn(n, 3, generator=g)
+    img = ops.nhwc_to_nchw(rgb, a=ra.to(DEV), b=rb.to(DEV)).cpu()
+    assert (img - (rgb.permute(0, 3, 1, 2).cpu() * ra[:, :, None, None] + rb[:, :, None, None])).abs().max() <= 1e-5
+
+
 def test_layout_roundtrip():
     from ppst_b200 import ops
     x = torch.randn(2, 19, 13, 21, generator=gen(31))
@@ -487,6 +518,17 @@ def test_in_coeffs_and_affine_apply():
     y = ops.affine_apply(xin, 16, a, b, res=ops.nchw_to_nhwc(lo.to(DEV)), res_mode=2, post_gain=1 / math.sqrt(2))
     w4 = (want + F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=False)) / math.sqrt(2)
     assert (y.permute(0, 3, 1, 2).cpu() - w4).abs().max() <= 2e-5
+    y = ops.affine_apply(xin, 16, a, b, res=ops.nchw_to_nhwc(lo.to(DEV)), ra=ra.to(DEV), rb=rb.to(DEV), res_mode=2)
+    w5 = want + F.interpolate(lo, scale_factor=2, mode="bilinear", align_corners=False) * ra[:, :, None, None] + rb[:, :, None, None]
+    assert (y.permute(0, 3, 1, 2).cpu() - w5).abs().max() <= 2e-5
+    xb = torch.randn(2, 128, 32, 64, generator=g).bfloat16()                     # an UpsamplingResBlock tail shape
+    lob = torch.randn(2, 128, 16, 32, generator=g).bfloat16()
+    ab, bb = torch.rand(2, 128, generator=g) + 0.5, torch.randn(2, 128, generator=g)
+    y = ops.affine_apply(ops.nchw_to_nhwc(xb.to(DEV)), 128, ab.to(DEV), bb.to(DEV), res=ops.nchw_to_nhwc(lob.to(DEV)),
+                         res_mode=2, post_gain=1 / math.sqrt(2), out_dtype=torch.float32)
+    w6 = (xb.float() * ab[:, :, None, None] + bb[:, :, None, None] +
+          F.interpolate(lob.float(), scale_factor=2, mode="bilinear", align_corners=False)) / math.sqrt(2)
+    assert (y.permute(0, 3, 1, 2).cpu() - w6).abs().max() <= 2e-5
     # bf16 storage, 3-channel scalar path, channel-slice destination
     x3 = torch.randn(1, 3, 6, 6, generator=g)
     y = ops.affine_apply(ops.nchw_to_nhwc(x3.to(DEV)), 3, None, None, post_gain=2.0)
