@@ -166,6 +166,11 @@ typedef struct {
                       channel dim (cin = 2 x segment; hi = bf16(x), lo = bf16(x - hi)); the kernel accumulates
                       hi*hi + hi*lo + lo*hi.  Requires kh = kw = 1. */
   int32_t w_img_rows, split_terms;
+  /* ppst_conv_tc only.  out_pad > 0: `out` is a [n, full_h + 2*out_pad, full_w + 2*out_pad, cout_stride] buffer and
+     the result is stored into its interior (the border belongs to the caller: see ppst_fill_border) -- the next
+     convolution then reads the padded buffer as is.  bias_img_stride > 0: image i adds bias[i*bias_img_stride + c]
+     (a per-sample bias, see ppst_modulate_weights). */
+  int32_t out_pad, bias_img_stride;
 } ppst_conv_desc;
 
 /* CUDA-core implicit GEMM (fp32 accumulate; any channel counts).  fp32 mode and the thin layers
@@ -199,6 +204,19 @@ PPST_API int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, co
  * that PRECEDES the first convolution of the generator's feature heads (generator.py:180-231) into that convolution. */
 PPST_API int ppst_scale_weights(void* out, const float* w, const float* a, int64_t n, int64_t rows, int taps, int cin,
                        void* stream);
+
+/* Lazy InstanceNorm + StyleMod in front of a zero-padded convolution (StyledConv conv1 -> conv2 inside the generator's
+ * residual blocks, stylegan2_layers.py:439-475, generator.py:47-77): with x = a*y + b per (sample, channel),
+ *     conv(zero_pad(x), W)[co] = conv(y', W*a)[co] + sum_{tap,c} W[co][tap][c] * b[c],   y' = y with border -b/a.
+ * ppst_modulate_weights: w f32 [rows, taps*cin] (packed), a, b f32 [n, cin], base_bias f32 [rows] or NULL
+ *     -> out_w bf16 [n, rows, taps*cin] = W*a,  out_bias f32 [n, rows] = base_bias + sum W*b
+ *     (feed to ppst_conv_tc with w_img_rows = rows, bias_img_stride = rows).
+ * ppst_fill_border: the `pad`-pixel border of the bf16 buffer [n, h+2*pad, w+2*pad, c] <- -b/a (|a| clamped to 1e-20).
+ * The producing convolution writes the interior (ppst_conv_desc.out_pad). */
+PPST_API int ppst_modulate_weights(void* out_w, float* out_bias, const float* w, const float* a, const float* b,
+                          const float* base_bias, int64_t n, int64_t rows, int taps, int cin, void* stream);
+PPST_API int ppst_fill_border(void* buf, const float* a, const float* b, int64_t n, int h, int w, int c, int pad, int dtype,
+                     void* stream);
 
 /* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
 PPST_API int ppst_conv_tc_available(void);

@@ -24,7 +24,8 @@ class ConvDesc(ctypes.Structure):
                [("slope", c_float), ("gain", c_float), ("noise_w", c_float),
                 ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
                 ("in_row_pitch", ctypes.c_int64), ("in_img_pitch", ctypes.c_int64),
-                ("w_img_rows", ctypes.c_int32), ("split_terms", ctypes.c_int32)]
+                ("w_img_rows", ctypes.c_int32), ("split_terms", ctypes.c_int32),
+                ("out_pad", ctypes.c_int32), ("bias_img_stride", ctypes.c_int32)]
 
 
 class ApplyDesc(ctypes.Structure):
@@ -58,6 +59,8 @@ _SIGS = {
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_available": (c_int, []),
     "ppst_scale_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
+    "ppst_modulate_weights": (c_int, [c_void_p] * 6 + [c_i64, c_i64, c_int, c_int, c_void_p]),
+    "ppst_fill_border": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_conv1x1_in_nchw": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_float, c_float,
                                                      c_int, c_void_p]),
     "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),

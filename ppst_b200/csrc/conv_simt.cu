@@ -153,6 +153,8 @@ extern "C" int ppst_conv_simt(void* out, const void* in, const float* weight, co
   const ppst_conv_desc d = *dp;
   int rc = validate_conv_desc(d, "conv_simt");
   if (rc) return rc;
+  PPST_REQUIRE(d.out_pad == 0 && d.bias_img_stride == 0, PPST_ERR_UNSUPPORTED,
+               "conv_simt: out_pad / per-sample bias are ppst_conv_tc features");
   const int64_t M = (int64_t)d.n * d.out_h * d.out_w;
   dim3 grid(ceil_div(M, CBM), ceil_div(d.cout, CBN), d.phases_y * d.phases_x);
   PPST_REQUIRE(grid.y <= 65535 && grid.z <= 65535, PPST_ERR_ARG, "conv_simt: grid too large");

@@ -32,7 +32,8 @@ namespace tc {
 
 constexpr int kThreads = 384;           // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kEpiWarp0 = 4;            // first epilogue warp
-constexpr int kBiasSmem = 1024;         // bias values staged in shared memory (larger cout: read from global)
+constexpr int kBiasSmem = 1024;         // bias values staged in shared memory (larger cout: read from global);
+                                        // one copy per epilogue group (a per-sample bias is reloaded per image)
 constexpr int BM = 128;
 
 struct Params {
@@ -50,6 +51,8 @@ struct Params {
   int stats_partials;                   // partial slots per image = tiles_y*tiles_x*phases
   int w_img_rows;                       // weight rows per image (0: one weight matrix for the whole batch)
   int split_seg_kb;                     // 3-term split GEMM: k-blocks per [hi]/[lo] segment (0: plain)
+  int out_pad;                          // border (pixels) of the output buffer: stores go to its interior
+  int bias_img_stride;                  // > 0: image i adds bias[i * bias_img_stride + c] (per-sample bias)
   int stages, kps;                      // pipeline depth; k-blocks per pipeline stage (one barrier round trip each)
   // halo kernel only
   int tiles_ys;                         // super-tile rows per image = ceil(tiles_y / MT)
@@ -268,6 +271,17 @@ __device__ __forceinline__ void epilogue_rows_bf16(uint32_t taddr, uint32_t bias
   }
 }
 
+// Per-sample bias (bias_img_stride > 0): the 128 threads of an epilogue group swap their bias copy when the image of
+// their tile changes (tiles are image-major, so once per image and CTA).  bar_id = 1 + group.
+__device__ __forceinline__ void reload_group_bias(float* s_bias_g, const float* __restrict__ bias, int img, int stride,
+                                                  int cout, int group, int tid_in_group) {
+  if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+  for (int i = tid_in_group; i < cout; i += 128) s_bias_g[i] = bias[(int64_t)img * stride + i];
+  if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
 constexpr int kMaxStages = 8;
 template <int BN, int BKC>
 struct Smem {
@@ -275,7 +289,7 @@ struct Smem {
   static constexpr int kBBytes = BN * BKC * 2;
   static constexpr int kKblockBytes = kABytes + kBBytes;     // one k-block: A tile then B tile (both 1024-aligned)
   static constexpr int kStatsBytes = 2 /*buf*/ * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
-  static constexpr int kBiasBytes = kBiasSmem * 4;
+  static constexpr int kBiasBytes = 2 * kBiasSmem * 4;
   static constexpr int kEpiBytes = 8 * kEpiStageBytes;        // per-warp staging of the bf16 epilogue
   static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*align slack*/;
   static constexpr int kMaxDynamic = 232448 - 1024 /*static*/;
@@ -295,7 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* s_bias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + S::kStatsBytes);
   const bool bias_in_smem = (p.cout <= kBiasSmem);        // always true for bf16 output (checked on the host)
   if (bias_in_smem)
-    for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias ? bias[i] : 0.0f;
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = s_bias[kBiasSmem + i] = bias ? bias[i] : 0.0f;
   uint8_t* s_epi = smem + STAGES * stage_bytes + S::kStatsBytes + S::kBiasBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_epi + S::kEpiBytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -421,11 +435,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int group = (warp - kEpiWarp0) >> 2;           // epilogue group == accumulator stage it serves
     const int row = q * 32 + lane;                       // row of the 128-pixel tile
     const int ety = row / p.tw, etx = row - ety * p.tw;
-    int it = 0;
+    float* s_bias_g = s_bias + group * kBiasSmem;
+    const int fh_pad = p.full_h + 2 * p.out_pad, fw_pad = p.full_w + 2 * p.out_pad;
+    int it = 0, cur_img = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != group) continue;
       int nt, ph, tx, ty, img;
       decode(tile, nt, ph, tx, ty, img);
+      if (p.bias_img_stride > 0 && img != cur_img) {
+        reload_group_bias(s_bias_g, bias, img, p.bias_img_stride, p.cout, group, (threadIdx.x - kEpiWarp0 * 32) & 127);
+        cur_img = img;
+      }
       const int py = ph / p.phases_x, px = ph % p.phases_x;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -433,7 +453,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool valid = (oy < p.out_h) && (ox < p.out_w);
       const int64_t pix = ((int64_t)img * p.full_h + (oy * p.phases_y + py)) * p.full_w + (ox * p.phases_x + px);
       const float nz = (noise != nullptr && valid) ? p.noise_w * noise[pix] : 0.0f;
-      const int64_t obase = pix * p.cout_stride + p.c_off + nt * BN;
+      const int64_t opix = ((int64_t)img * fh_pad + (oy * p.phases_y + py) + p.out_pad) * fw_pad + (ox * p.phases_x + px) + p.out_pad;
+      const int64_t obase = opix * p.cout_stride + p.c_off + nt * BN;
       float* st_sum = s_stats + (size_t)(as * 2 + 0) * 4 * BN + q * BN;
       float* st_sq = s_stats + (size_t)(as * 2 + 1) * 4 * BN + q * BN;
 
@@ -454,7 +475,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
                 const int c = nt * BN + c0 + 4 * j + h;
-                const float bj = bias ? (bias_in_smem ? s_bias[c] : __ldg(bias + c)) : 0.0f;
+                const float bj = bias ? (bias_in_smem ? s_bias_g[c] : __ldg(bias + c)) : 0.0f;
                 float a = __uint_as_float(r[4 * j + h]) + bj + nz;
                 if (p.has_act) a = (a > 0.0f) ? a : a * p.slope;
                 v[h] = a * p.gain;
@@ -473,10 +494,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int sy = srow / p.tw, sx = srow - sy * p.tw;
           const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
           if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
-          const int64_t spix = ((int64_t)img * p.full_h + (soy * p.phases_y + py)) * p.full_w + (sox * p.phases_x + px);
+          const int64_t spix = ((int64_t)img * fh_pad + (soy * p.phases_y + py) + p.out_pad) * fw_pad + (sox * p.phases_x + px) + p.out_pad;
           soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
         }
-        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
+        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias_g + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
                                stats_sum ? st_sum : nullptr, st_sq, reinterpret_cast<__nv_bfloat16*>(out_raw), soff,
                                svalid, nz, valid, p.gain, p.has_act ? p.slope : 1.0f, lane);
       }
@@ -531,7 +552,7 @@ constexpr int kMaxA = 4, kMaxB = 8;
 template <int BN, int MT>
 struct HaloSmem {
   static constexpr int kStatsBytes = 2 /*acc stage*/ * MT * 2 /*sum,sq*/ * 4 /*warps*/ * BN * 4;
-  static constexpr int kBiasBytes = kBiasSmem * 4;
+  static constexpr int kBiasBytes = 2 * kBiasSmem * 4;
   static constexpr int kBarBytes = (2 * kMaxA + 2 * kMaxB + 4) * 8 + 16;
   static constexpr int kEpiBytes = 8 * kEpiStageBytes;
   static constexpr int kFixedBytes = kStatsBytes + kBiasBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
@@ -566,7 +587,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = b_empty + kMaxB;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = bias ? bias[i] : 0.0f;   // cout <= kBiasSmem (host)
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = s_bias[kBiasSmem + i] = bias ? bias[i] : 0.0f;   // cout <= kBiasSmem (host)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -676,11 +697,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int group = (warp - kEpiWarp0) >> 2;
     const int row = q * 32 + lane;
     const int ety = row / p.tw, etx = row - ety * p.tw;
-    int it = 0;
+    float* s_bias_g = s_bias + group * kBiasSmem;
+    const int fh_pad = p.full_h + 2 * p.out_pad, fw_pad = p.full_w + 2 * p.out_pad;
+    int it = 0, cur_img = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != group) continue;
       int nt, ph, tx, tys, img;
       decode(tile, nt, ph, tx, tys, img);
+      if (p.bias_img_stride > 0 && img != cur_img) {
+        reload_group_bias(s_bias_g, bias, img, p.bias_img_stride, p.cout, group, (threadIdx.x - kEpiWarp0 * 32) & 127);
+        cur_img = img;
+      }
       const int py = ph / p.phases_x, px = ph % p.phases_x;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -704,10 +731,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int sy = srow / p.tw, sx = srow - sy * p.tw;
           const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
           if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
-          const int64_t spix = ((int64_t)img * p.full_h + (soy * p.phases_y + py)) * p.full_w + (sox * p.phases_x + px);
+          const int64_t spix = ((int64_t)img * fh_pad + (soy * p.phases_y + py) + p.out_pad) * fw_pad + (sox * p.phases_x + px) + p.out_pad;
           soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
         }
-        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
+        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias_g + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
                                stats_sum ? b_sum + q * BN : nullptr, b_sq + q * BN, out, soff, svalid, nz, valid, p.gain,
                                p.has_act ? p.slope : 1.0f, lane);
         if (m == MT - 1) {
@@ -862,6 +889,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   }
   const int smem_total = p.stages * p.kps * S::kKblockBytes + S::kFixedBytes;
   p.w_img_rows = d.w_img_rows;
+  p.out_pad = d.out_pad; p.bias_img_stride = d.bias_img_stride;
   p.split_seg_kb = d.split_terms == 3 ? (d.cin / 2) / BKC : 0;
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
   p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
@@ -959,6 +987,7 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
     if (rc) return rc;
   }
   p.w_img_rows = d.w_img_rows;
+  p.out_pad = d.out_pad; p.bias_img_stride = d.bias_img_stride;
   auto kern = conv_tc_halo_kernel<BN, BKC, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1022,6 +1051,9 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
   PPST_REQUIRE(d.w_img_rows == 0 || (d.phases_y * d.phases_x == 1 && d.w_img_rows >= d.cout), PPST_ERR_ARG,
                "conv_tc: per-image weights need a single phase and w_img_rows >= cout");
   PPST_REQUIRE(d.out_dtype == PPST_BF16 || stats == nullptr, PPST_ERR_UNSUPPORTED, "conv_tc: statistics need bf16 output");
+  PPST_REQUIRE(d.out_pad >= 0 && d.out_pad <= 8, PPST_ERR_ARG, "conv_tc: out_pad %d", d.out_pad);
+  PPST_REQUIRE(d.bias_img_stride == 0 || (bias != nullptr && d.bias_img_stride >= d.cout && d.cout <= tc::kBiasSmem),
+               PPST_ERR_ARG, "conv_tc: per-sample bias needs bias_img_stride >= cout and cout <= %d", tc::kBiasSmem);
   PPST_REQUIRE(d.cin % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cin=%d must be a multiple of 32", d.cin);
   PPST_REQUIRE(d.cout % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cout=%d must be a multiple of 32", d.cout);
   PPST_REQUIRE(d.out_dtype == PPST_F32 || d.cout <= tc::kBiasSmem, PPST_ERR_UNSUPPORTED,

@@ -118,3 +118,108 @@ extern "C" int ppst_scale_weights(void* out, const float* w, const float* a, int
   PPST_LAUNCH_CHECK("scale_weights_kernel");
   return 0;
 }
+
+// Lazy InstanceNorm + StyleMod in FRONT of a zero-padded convolution (StyledConv conv1 -> conv2 of the generator's
+// residual blocks, stylegan2_layers.py:439-475).  With x = a*y + b per (sample, channel) and zero padding of x,
+//     conv(x, W)[co] = conv(y', W * a)[co] + sum_{t,c} W[co][t][c] * b[c]
+// where y' is y with its padding border set to -b/a (so that a*y' + b = 0 there: ppst_fill_border).  This kernel
+// writes the per-sample bf16 weights W*a and the per-sample bias  base_bias[co] + sum W*b  -- the normalised
+// activation is never materialised.  One block per (sample, output row of W).
+namespace ppst {
+__global__ void __launch_bounds__(256) modulate_weights_kernel(__nv_bfloat16* __restrict__ out, float* __restrict__ out_bias,
+                                                               const float* __restrict__ w, const float* __restrict__ a,
+                                                               const float* __restrict__ b,
+                                                               const float* __restrict__ base_bias, int64_t rows, int taps,
+                                                               int cin) {
+  __shared__ float red[8];
+  const int64_t r = blockIdx.x, ni = blockIdx.y;
+  const int K = taps * cin;
+  const float* wr = w + r * K;
+  __nv_bfloat16* o = out + (ni * rows + r) * K;
+  const float* av = a + ni * cin;
+  const float* bv = b + ni * cin;
+  float acc = 0.f;
+  for (int i = threadIdx.x * 4; i < K; i += 256 * 4) {
+    const int c = i % cin;                               // cin % 4 == 0: the 4 elements share a tap
+    const float4 wv = *reinterpret_cast<const float4*>(wr + i);
+    const float4 a4 = *reinterpret_cast<const float4*>(av + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(bv + c);
+    union { uint2 u; __nv_bfloat16 h[4]; } pk;
+    pk.h[0] = __float2bfloat16_rn(wv.x * a4.x); pk.h[1] = __float2bfloat16_rn(wv.y * a4.y);
+    pk.h[2] = __float2bfloat16_rn(wv.z * a4.z); pk.h[3] = __float2bfloat16_rn(wv.w * a4.w);
+    *reinterpret_cast<uint2*>(o + i) = pk.u;
+    acc = fmaf(wv.x, b4.x, acc); acc = fmaf(wv.y, b4.y, acc);
+    acc = fmaf(wv.z, b4.z, acc); acc = fmaf(wv.w, b4.w, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out_bias[ni * rows + r] = t + (base_bias ? base_bias[r] : 0.f);
+  }
+}
+
+// Border of a padded NHWC bf16 buffer [n, h + 2p, w + 2p, c] <- -b/a per (sample, channel): the value the lazy affine
+// a*y + b maps to zero, i.e. the zero padding of the normalised tensor.  |a| is clamped away from 0.
+__global__ void __launch_bounds__(256) fill_border_kernel(__nv_bfloat16* __restrict__ buf, const float* __restrict__ a,
+                                                          const float* __restrict__ b, int h, int w, int c, int pad) {
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  const int border = hp * wp - h * w;                    // border pixels per image
+  const int cv = c / 8;
+  const int64_t ni = blockIdx.y;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < (int64_t)border * cv;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cv);
+    int k = (int)(t / cv);                               // border pixel index: top rows, bottom rows, then side columns
+    int y, x;
+    if (k < pad * wp) { y = k / wp; x = k - y * wp; }
+    else if (k < 2 * pad * wp) { k -= pad * wp; y = h + pad + k / wp; x = k % wp; }
+    else {
+      k -= 2 * pad * wp;
+      y = pad + k / (2 * pad);
+      const int s = k % (2 * pad);
+      x = s < pad ? s : w + s;
+    }
+    union { uint4 u; __nv_bfloat16 v[8]; } pk;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float av = a[ni * c + cg * 8 + e];
+      const float bv = b[ni * c + cg * 8 + e];
+      if (fabsf(av) < 1e-20f) av = av < 0.f ? -1e-20f : 1e-20f;
+      pk.v[e] = __float2bfloat16_rn(-bv / av);
+    }
+    *reinterpret_cast<uint4*>(buf + ((ni * hp + y) * wp + x) * (int64_t)c + cg * 8) = pk.u;
+  }
+}
+}  // namespace ppst
+
+extern "C" int ppst_modulate_weights(void* out_w, float* out_bias, const float* w, const float* a, const float* b,
+                                     const float* base_bias, int64_t n, int64_t rows, int taps, int cin, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out_w && out_bias && w && a && b && n > 0 && n <= 65535 && rows > 0 && taps > 0 && cin > 0 && cin % 4 == 0,
+               PPST_ERR_ARG, "modulate_weights: bad args (cin must be a multiple of 4)");
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(out_w) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(a) |
+                 reinterpret_cast<uintptr_t>(b)) & 15) == 0, PPST_ERR_ARG, "modulate_weights: buffers must be 16-byte aligned");
+  modulate_weights_kernel<<<dim3((unsigned)rows, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)out_w, out_bias, w, a, b, base_bias, rows, taps, cin);
+  PPST_LAUNCH_CHECK("modulate_weights_kernel");
+  return 0;
+}
+
+extern "C" int ppst_fill_border(void* buf, const float* a, const float* b, int64_t n, int h, int w, int c, int pad,
+                                int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(buf && a && b && n > 0 && n <= 65535 && h > 0 && w > 0 && c > 0 && pad >= 1 && pad <= 8, PPST_ERR_ARG,
+               "fill_border: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 && c % 8 == 0 && (reinterpret_cast<uintptr_t>(buf) & 15) == 0, PPST_ERR_UNSUPPORTED,
+               "fill_border: bf16 buffers with c a multiple of 8");
+  const int64_t border = (int64_t)(h + 2 * pad) * (w + 2 * pad) - (int64_t)h * w;
+  const int64_t blocks = (border * (c / 8) + 255) / 256;
+  fill_border_kernel<<<dim3((unsigned)(blocks < 1024 ? blocks : 1024), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)buf, a, b, h, w, c, pad);
+  PPST_LAUNCH_CHECK("fill_border_kernel");
+  return 0;
+}

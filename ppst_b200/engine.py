@@ -152,31 +152,44 @@ class Engine:
         return G
 
     # ------------------------------------------------------------------------------------------ primitives
-    def conv(self, x, spec, noise=None, out=None, c_off=0, out_dtype=None, want_stats=False, w_per_image=None):
+    def conv(self, x, spec, noise=None, out=None, c_off=0, out_dtype=None, want_stats=False, w_per_image=None,
+             bias_per_image=None, out_pad=0, valid=False):
         """x: dense NHWC.  Returns (y, stats) with stats = None | dict(partials...) for in_coeffs.
-        w_per_image: bf16 [n, cout, K] per-sample weights (ops.scale_weights) instead of spec.w16 (tensor-core path)."""
+        w_per_image: bf16 [n, cout, K] per-sample weights (ops.scale_weights / modulate_weights) instead of spec.w16,
+        bias_per_image: f32 [n, cout] instead of spec.bias (tensor-core path only).
+        out_pad: the result goes into the interior of a new [n, fh+2p, fw+2p, cout] buffer (border left to the caller).
+        valid: x is already padded -- tap (0,0) of output (0,0) reads x[0,0] and the output shrinks by k-1."""
         n, h, w, cin = x.shape
         assert cin == spec.cin, (cin, spec.cin)
-        oh, ow = spec.out_hw(h, w)
+        off = spec.off
+        if valid:
+            assert spec.stride == 1 and spec.phases == (1, 1)
+            off = (0, 0)
+            oh, ow = h - spec.kh + 1, w - spec.kw + 1
+        else:
+            oh, ow = spec.out_hw(h, w)
         fh, fw = oh * spec.phases[0], ow * spec.phases[1]
         odt = out_dtype or self.adt
         if out is None:
-            out = torch.empty((n, fh, fw, spec.cout), device=x.device, dtype=odt)
+            out = torch.empty((n, fh + 2 * out_pad, fw + 2 * out_pad, spec.cout), device=x.device, dtype=odt)
         tc = self.use_tc and spec.w16 is not None and x.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
         code_in = BF16 if x.dtype == torch.bfloat16 else F32
         code_out = BF16 if out.dtype == torch.bfloat16 else F32
-        d = ops.conv_desc((n, h, w, cin), spec.cout, spec.kh, spec.kw, stride=spec.stride, off=spec.off,
+        d = ops.conv_desc((n, h, w, cin), spec.cout, spec.kh, spec.kw, stride=spec.stride, off=off,
                           out_hw=(oh, ow), phases=spec.phases, phase_off=spec.phase_off, full_hw=(fh, fw),
                           cout_stride=out.shape[3], c_off=c_off, act=spec.act, slope=0.2,
                           gain=SQRT2 if spec.act else 1.0, noise_w=spec.noise_w if noise is not None else 0.0,
-                          in_dtype=code_in, out_dtype=code_out, w_img_rows=spec.cout if w_per_image is not None else 0)
+                          in_dtype=code_in, out_dtype=code_out, w_img_rows=spec.cout if w_per_image is not None else 0,
+                          out_pad=out_pad, bias_img_stride=spec.cout if bias_per_image is not None else 0)
         stats = None
-        assert w_per_image is None or tc, "per-sample weights need the tensor-core path"
+        assert (w_per_image is None and bias_per_image is None and out_pad == 0) or tc, \
+            "per-sample weights / bias and padded outputs need the tensor-core path"
         if tc:
             sbuf = None
             if want_stats:
                 sbuf = torch.empty(ops.conv_tc_stats_elems(d), device=x.device, dtype=torch.float32)
-            ops.conv_tc(out, x, spec.w16 if w_per_image is None else w_per_image, spec.bias, noise, sbuf, d)
+            ops.conv_tc(out, x, spec.w16 if w_per_image is None else w_per_image,
+                        spec.bias if bias_per_image is None else bias_per_image, noise, sbuf, d)
             if want_stats:
                 half = sbuf.numel() // 2
                 stats = {"sum": sbuf[:half], "sumsq": sbuf[half:], "n_partials": half // (n * spec.cout),
@@ -369,16 +382,26 @@ class Engine:
                 out[key] = y[:, o:o + size]
         return out
 
-    def _styled(self, P, x, s, noise, upsample=False):
+    def _styled(self, P, x, s, noise, upsample=False, out_pad=0, lazy=None):
         """StyledConv.forward up to (and excluding) the application of IN+StyleMod: returns (y, a, b).
-        s: the layer's style vector [n, 2c] (a row-strided view into the batched linear's output)."""
-        if upsample and min(x.shape[1:3]) * 2 >= 128:
-            y, st = self.conv(x, P["fused_up"], noise=noise, want_stats=True)
+        s: the layer's style vector [n, 2c] (a row-strided view into the batched linear's output).
+        out_pad: y is the interior of a buffer with a 1-pixel border, for a following _styled(..., lazy=(a, b)).
+        lazy = (a_in, b_in): x is such a padded, NOT yet normalised buffer: its IN + StyleMod is folded into per-sample
+        weights and a per-sample bias, its border set to -b/a (= zero padding of the normalised tensor)."""
+        if lazy is not None:
+            a_in, b_in = lazy
+            spec = P["plain"]
+            ops.fill_border(x, a_in, b_in, 1)
+            wn, bn = ops.modulate_weights(spec.w32, a_in, b_in, spec.kh * spec.kw, spec.cin, base_bias=spec.bias)
+            y, st = self.conv(x, spec, noise=noise, want_stats=True, w_per_image=wn, bias_per_image=bn, valid=True,
+                              out_pad=out_pad)
+        elif upsample and min(x.shape[1:3]) * 2 >= 128:
+            y, st = self.conv(x, P["fused_up"], noise=noise, want_stats=True, out_pad=out_pad)
         else:
             if upsample:
                 x = self.apply(x, up=2)                              # Upscale2d nearest (stylegan2_layers.py:88-105)
-            y, st = self.conv(x, P["plain"], noise=noise, want_stats=True)
-        a, b = self.coeffs(y, st, style=s)
+            y, st = self.conv(x, P["plain"], noise=noise, want_stats=True, out_pad=out_pad)
+        a, b = self.coeffs(y, st, style=s, c=y.shape[3])
         return y, a, b
 
     def _feature_head(self, P, x):
@@ -442,9 +465,15 @@ class Engine:
             B = G["up%d" % res]
             name = "UpsamplingResBlock%d" % res
             skip = self.conv(x, B["skip"])[0] if "skip" in B else x
-            y, a, b = self._styled(B["conv1"], x, st["up%d.conv1" % res], noises.get(name + ".conv1"), upsample=True)
-            h = self.apply(y, a, b)
-            y, a, b = self._styled(B["conv2"], h, st["up%d.conv2" % res], noises.get(name + ".conv2"))
+            if self.use_tc and taps is None and x.dtype == torch.bfloat16 and min(x.shape[1:3]) * 2 >= 128:
+                # conv1's normalisation + style is never applied to the activation: it rides in conv2's weights
+                y, a, b = self._styled(B["conv1"], x, st["up%d.conv1" % res], noises.get(name + ".conv1"), upsample=True,
+                                       out_pad=1)
+                y, a, b = self._styled(B["conv2"], y, st["up%d.conv2" % res], noises.get(name + ".conv2"), lazy=(a, b))
+            else:
+                y, a, b = self._styled(B["conv1"], x, st["up%d.conv1" % res], noises.get(name + ".conv1"), upsample=True)
+                h = self.apply(y, a, b)
+                y, a, b = self._styled(B["conv2"], h, st["up%d.conv2" % res], noises.get(name + ".conv2"))
             yrgb = None
             last = j == len(UP_CH) - 1
             if (last and self.use_tc and taps is None and y.dtype == torch.bfloat16 and y.shape[3] == 128

@@ -159,7 +159,8 @@ def labels_pool_or(labels, factor, in_mode):
 # ----------------------------------------------------------------------------------------------- convolution
 def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(1, 1), phase_off=(0, 0),
               full_hw=None, cout_stride=None, c_off=0, act=False, slope=0.2, gain=1.0, noise_w=0.0,
-              in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0, w_img_rows=0, split_terms=0):
+              in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0, w_img_rows=0, split_terms=0, out_pad=0,
+              bias_img_stride=0):
     n, in_h, in_w, cin = x_shape
     d = ConvDesc()
     d.n, d.in_h, d.in_w, d.cin = n, in_h, in_w, cin
@@ -177,6 +178,7 @@ def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(
     d.in_dtype, d.out_dtype = in_dtype, out_dtype
     d.in_row_pitch, d.in_img_pitch = in_row_pitch, in_img_pitch
     d.w_img_rows, d.split_terms = w_img_rows, split_terms
+    d.out_pad, d.bias_img_stride = out_pad, bias_img_stride
     return d
 
 
@@ -423,6 +425,29 @@ def scale_weights(w32, a, taps, cin):
     out = torch.empty((a.shape[0], rows, taps * cin), device=w32.device, dtype=torch.bfloat16)
     check(_L().ppst_scale_weights(ptr(out), ptr(w32), ptr(a), a.shape[0], rows, int(taps), int(cin), stream()))
     return out
+
+
+def modulate_weights(w32, a, b, taps, cin, base_bias=None):
+    """Lazy affine in front of a zero-padded conv: (bf16 [n, rows, taps*cin] = W*a, f32 [n, rows] = base_bias + sum W*b)."""
+    require_cuda(w32, a, b, base_bias)
+    assert w32.dtype == torch.float32 and w32.is_contiguous() and a.dtype == torch.float32 and b.dtype == torch.float32
+    a, b = a.contiguous(), b.contiguous()
+    rows = w32.numel() // (taps * cin)
+    n = a.shape[0]
+    out_w = torch.empty((n, rows, taps * cin), device=w32.device, dtype=torch.bfloat16)
+    out_b = torch.empty((n, rows), device=w32.device, dtype=torch.float32)
+    check(_L().ppst_modulate_weights(ptr(out_w), ptr(out_b), ptr(w32), ptr(a), ptr(b), ptr(base_bias), n, rows, int(taps),
+                                     int(cin), stream()))
+    return out_w, out_b
+
+
+def fill_border(buf, a, b, pad=1):
+    """Border of the padded NHWC bf16 buffer [n, h+2p, w+2p, c] <- -b/a per (sample, channel)."""
+    require_cuda(buf, a, b)
+    n, hp, wp, c = buf.shape
+    assert buf.is_contiguous() and a.is_contiguous() and b.is_contiguous()
+    check(_L().ppst_fill_border(ptr(buf), ptr(a), ptr(b), n, hp - 2 * pad, wp - 2 * pad, c, pad, dt(buf), stream()))
+    return buf
 
 
 def guided_smooth(out_img, target, radius=30, eps=(0.02 * 255) ** 2):

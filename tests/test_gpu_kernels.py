@@ -463,6 +463,59 @@ def test_conv_tc_per_sample_scaled_weights():
             assert err <= 2e-2 * max(1.0, float(ref.abs().max())), (ci, co, k, i, float(err))
 
 
+def test_conv_tc_lazy_affine_input_padded_output():
+    """StyledConv conv1 -> [IN + StyleMod never materialised] -> conv2 (stylegan2_layers.py:439-475):
+    conv1 stores into the interior of a padded buffer (out_pad), ppst_fill_border sets the border to -b/a,
+    ppst_modulate_weights folds the affine into per-sample weights and a per-sample bias, conv2 reads the padded
+    buffer as a valid convolution.  Must equal conv2(zero_pad(a*y + b))."""
+    from ppst_b200 import ops
+    from ppst_b200._lib import BF16
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    for ci, cm, co, h, w, n in ((64, 128, 128, 40, 48, 3), (128, 256, 256, 24, 32, 2), (32, 64, 32, 200, 190, 2)):
+        g = gen(ci + co + h)
+        x = torch.randn(n, ci, h, w, generator=g)
+        w1 = torch.randn(cm, ci, 3, 3, generator=g) / math.sqrt(ci * 9)
+        b1 = torch.randn(cm, generator=g) * 0.3
+        w2 = torch.randn(co, cm, 3, 3, generator=g) / math.sqrt(cm * 9)
+        b2 = torch.randn(co, generator=g)
+        a = (torch.rand(n, cm, generator=g) + 0.5) * torch.where(torch.rand(n, cm, generator=g) < 0.3, -1.0, 1.0)
+        b = torch.randn(n, cm, generator=g)
+        xin = ops.nchw_to_nhwc(x.to(DEV), dtype=torch.bfloat16)
+        # conv1 -> interior of a padded buffer, with statistics of the stored interior
+        d1 = ops.conv_desc((n, h, w, ci), cm, 3, 3, off=(-1, -1), out_hw=(h, w), in_dtype=BF16, out_dtype=BF16, out_pad=1)
+        ypad = torch.full((n, h + 2, w + 2, cm), float("nan"), device=DEV, dtype=torch.bfloat16)
+        st = torch.empty(ops.conv_tc_stats_elems(d1), device=DEV)
+        ops.conv_tc(ypad, xin, pack_w(w1).to(DEV).bfloat16().contiguous(), b1.to(DEV), None, st, d1)
+        d0 = ops.conv_desc((n, h, w, ci), cm, 3, 3, off=(-1, -1), out_hw=(h, w), in_dtype=BF16, out_dtype=BF16)
+        y = torch.empty((n, h, w, cm), device=DEV, dtype=torch.bfloat16)
+        st0 = torch.empty(ops.conv_tc_stats_elems(d0), device=DEV)
+        ops.conv_tc(y, xin, pack_w(w1).to(DEV).bfloat16().contiguous(), b1.to(DEV), None, st0, d0)
+        assert torch.equal(ypad[:, 1:-1, 1:-1, :], y) and torch.equal(st, st0)
+        assert bool(torch.isnan(ypad[:, 0].float()).all()) and bool(torch.isnan(ypad[:, :, -1].float()).all())
+        ops.fill_border(ypad, a.to(DEV), b.to(DEV), 1)
+        want_border = (-b / a).bfloat16().float()
+        for sl in (ypad[:, 0], ypad[:, -1], ypad[:, :, 0], ypad[:, :, -1]):
+            assert (sl.float().cpu() - want_border[:, None, :]).abs().max() == 0.0
+        assert torch.equal(ypad[:, 1:-1, 1:-1, :], y)
+        wn, bn = ops.modulate_weights(pack_w(w2).to(DEV).contiguous(), a.to(DEV), b.to(DEV), 9, cm, base_bias=b2.to(DEV))
+        want_bias = b2[None] + torch.einsum("ockl,nc->no", w2, b)
+        assert (bn.cpu() - want_bias).abs().max() <= 1e-4 * max(1.0, float(want_bias.abs().max()))
+        d2 = ops.conv_desc((n, h + 2, w + 2, cm), co, 3, 3, off=(0, 0), out_hw=(h, w), in_dtype=BF16, out_dtype=BF16,
+                           w_img_rows=co, bias_img_stride=co, act=True, gain=math.sqrt(2))
+        out = torch.empty((n, h, w, co), device=DEV, dtype=torch.bfloat16)
+        ops.conv_tc(out, ypad, wn, bn, None, None, d2)
+        yf = y.float().permute(0, 3, 1, 2).cpu()
+        xn = yf * a[:, :, None, None] + b[:, :, None, None]
+        ref = F.leaky_relu(F.conv2d(xn, w2, b2, padding=1), 0.2) * math.sqrt(2)
+        err = (out.float().permute(0, 3, 1, 2).cpu() - ref).abs()
+        scale = max(1.0, float(ref.abs().max()))
+        assert err.max() <= 4e-2 * scale and err.mean() <= 4e-3 * scale, ((ci, cm, co), float(err.max()), float(err.mean()))
+        # the border rows / columns (where the padding matters) are as accurate as the interior
+        edge = torch.cat([err[:, :, 0].flatten(), err[:, :, -1].flatten(), err[:, :, :, 0].flatten(), err[:, :, :, -1].flatten()])
+        assert edge.max() <= 4e-2 * scale and edge.mean() <= 5e-3 * scale
+
+
 def test_conv_reads_interior_of_padded_buffer():
     from ppst_b200 import ops
     from ppst_b200._lib import F32
