@@ -95,6 +95,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def load_traffic():
+    """DRAM bytes per conv_tc launch from the committed `ncu --set full` capture of one step (tools/ncu_traffic.py)."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_tc_traffic.json")), reverse=True):
+        try:
+            with open(f) as fh:
+                j = json.load(fh)
+            return j["traffic_bytes_per_launch"], os.path.basename(f)
+        except Exception:
+            continue
+    return None, None
+
+
 def make_inputs(pairs, rank):
     from oracle import ppst_oracle as O     # seeded synthetic portraits only (input generation, not compute)
     c = O.make_portraits(pairs, SIZE, SIZE, seed=1234 + rank)
@@ -111,11 +124,14 @@ def cpu_baseline_sample(threads):
     c = O.make_portraits(1, SIZE, SIZE, seed=1234)
     s = O.make_portraits(1, SIZE, SIZE, seed=4321, smooth=True)
     noises = O.make_noises(1, SIZE, SIZE)
+    reps = 3
     with torch.no_grad():
+        O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)          # warm-up (allocator, oneDNN primitive caches)
         t0 = time.perf_counter()
-        O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
-        dt = time.perf_counter() - t0
-    return 1.0 / dt, dt
+        for _ in range(reps):
+            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
+        dt = (time.perf_counter() - t0) / reps
+    return 1.0 / dt, dt * (reps + 1)
 
 
 def run_reference(args):
@@ -156,7 +172,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="(content, style) pairs per GPU per step")
@@ -235,16 +251,23 @@ def main():
     ops.PROFILE = None
 
     peaks = load_peaks()
+    traffic, traffic_src = load_traffic()
     total_pairs = pairs * world
     value = total_pairs * args.steps / (ms * 1e-3)
     e2e = total_pairs * args.steps / (ms_e2e * 1e-3)
-    tc = prof.get("conv_tc", {"work": 0.0, "ms": 1.0, "launches": 0})
+    # every ppst_conv_tc launch of a step: the convolutions and the two split GEMMs (corrm logits, corr @ features)
+    tc = {"work": 0.0, "ms": 0.0, "launches": 0, "aux": 0.0}
+    for key in ("conv_tc", "gemm_split_tc"):
+        for f in tc:
+            tc[f] += prof.get(key, {}).get(f, 0)
+    if tc["ms"] <= 0:
+        tc["ms"] = 1.0
     achieved_tf = tc["work"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
     step_ms_prof = sum(v["ms"] for v in prof.values()) / max(prof_steps, 1)
     kernels = {k: {"launches_per_step": v["launches"] // max(prof_steps, 1), "ms_per_step": v["ms"] / max(prof_steps, 1),
                    "share": (v["ms"] / max(prof_steps, 1)) / step_ms_prof if step_ms_prof else None,
-                   ("tflops" if k in ("conv_tc", "conv_simt", "gemm_f32") else "gbs"):
-                       v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("conv_tc", "conv_simt", "gemm_f32") else 1e9)
+                   ("tflops" if k in ("conv_tc", "conv_simt", "gemm_f32", "gemm_split_tc") else "gbs"):
+                       v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("conv_tc", "conv_simt", "gemm_f32", "gemm_split_tc") else 1e9)
                        if v["ms"] > 0 else None}
                for k, v in prof.items()}
 
@@ -266,19 +289,25 @@ def main():
         "gpu_launches": int(launches),
         "launch_mode": "CUDA graph replay of %d kernels per step (captured from the eager path)" % launches_per_step,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv, all shapes of one step)",
+        "roofline": {"bound": "tensor", "kernel": "ppst_conv_tc (tcgen05 implicit-GEMM convolutions + the two split GEMMs: every "
+                                                 "launch of one step)",
                      "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": None,
+                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                     "traffic_source": traffic_src,
+                     "algorithmic_flop_per_launch": tc["work"] / max(tc["launches"], 1),
+                     "algorithmic_bytes_per_launch": tc.get("aux", 0.0) / max(tc["launches"], 1),
                      "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches_per_step": tc["launches"] // max(prof_steps, 1),
-                     "share_of_step": kernels.get("conv_tc", {}).get("share")},
+                     "share_of_step": (kernels.get("conv_tc", {}).get("share") or 0.0) +
+                                      (kernels.get("gemm_split_tc", {}).get("share") or 0.0)},
         "kernels": kernels,
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, secs = cpu_baseline_sample(threads)
         line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": "1 pair @512^2 (2.143 TFLOP), one run of %.1f s after no warm-up" % secs}
+                                "sample": "1 pair @512^2 (2.143 TFLOP) per run; 1 warm-up + 3 timed runs, %.1f s of CPU "
+                                          "work in total" % secs}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)

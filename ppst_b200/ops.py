@@ -27,9 +27,10 @@ PROFILE_DETAIL = False        # file launches under "name|tag" (tag = shape stri
 
 
 class _Prof:
-    def __init__(self, name, work, tag=None):
+    def __init__(self, name, work, tag=None, aux=0.0):
         self.name = name if not (PROFILE_DETAIL and tag) else "%s|%s" % (name, tag)
         self.work = work
+        self.aux = aux              # secondary work figure (conv_tc: algorithmic bytes next to the FLOPs)
 
     def __enter__(self):
         global _prof_count
@@ -47,7 +48,7 @@ class _Prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.setdefault(self.name, []).append((self.work, self.e0, self.e1))
+            PROFILE.setdefault(self.name, []).append((self.work, self.e0, self.e1, self.aux))
         return False
 
 
@@ -55,8 +56,9 @@ def profile_summary():
     """name -> dict(launches, work, ms) after a torch.cuda.synchronize()."""
     out = {}
     for name, recs in (PROFILE or {}).items():
-        ms = sum(e0.elapsed_time(e1) for _, e0, e1 in recs)
-        out[name] = {"launches": len(recs), "work": float(sum(w for w, _, _ in recs)), "ms": ms}
+        ms = sum(r[1].elapsed_time(r[2]) for r in recs)
+        out[name] = {"launches": len(recs), "work": float(sum(r[0] for r in recs)), "ms": ms,
+                     "aux": float(sum(r[3] for r in recs))}
     return out
 
 
@@ -195,7 +197,9 @@ def conv_tc_stats_elems(d):
 
 def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
     require_cuda(out, x, weight_bf16, bias, noise, stats)
-    with _Prof("conv_tc", _conv_flops(d), "n%d %dx%d ci%d co%d k%dx%d s%d ph%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride, d.phases_y * d.phases_x)):
+    nbytes = (d.n * d.in_h * d.in_w * d.cin * 2 + d.n * d.full_h * d.full_w * d.cout * (2 if d.out_dtype == BF16 else 4)
+              + weight_bf16.numel() * 2)
+    with _Prof("conv_tc", _conv_flops(d), "n%d %dx%d ci%d co%d k%dx%d s%d ph%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride, d.phases_y * d.phases_x), aux=nbytes):
         check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
                                 stream()))
     return out
