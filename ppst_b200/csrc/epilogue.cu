@@ -59,10 +59,22 @@ __global__ void __launch_bounds__(1024) in_coeffs_partials_kernel(
   if (ch < c) {
     const float* ps = sum + ni * n_partials * c + ch;
     const float* pq = sumsq + ni * n_partials * c + ch;
-    for (int64_t p = threadIdx.y; p < n_partials; p += 32) {
+    // 4 independent accumulator pairs (loads of 4 partials in flight instead of a dependent chain), combined in a
+    // fixed order: still deterministic, and independent of the batch
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    int64_t p = threadIdx.y;
+    for (; p + 96 < n_partials; p += 128) {
+      const float a0 = ps[p * c], a1 = ps[(p + 32) * c], a2 = ps[(p + 64) * c], a3 = ps[(p + 96) * c];
+      const float b0 = pq[p * c], b1 = pq[(p + 32) * c], b2 = pq[(p + 64) * c], b3 = pq[(p + 96) * c];
+      s += (double)a0; s1 += (double)a1; s2 += (double)a2; s3 += (double)a3;
+      q += (double)b0; q1 += (double)b1; q2 += (double)b2; q3 += (double)b3;
+    }
+    for (; p < n_partials; p += 32) {
       s += (double)ps[p * c];
       q += (double)pq[p * c];
     }
+    s = (s + s1) + (s2 + s3);
+    q = (q + q1) + (q2 + q3);
   }
   ss[threadIdx.y][threadIdx.x] = s;
   sq[threadIdx.y][threadIdx.x] = q;

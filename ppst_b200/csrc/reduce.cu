@@ -199,10 +199,17 @@ __global__ void plane_reduce_nhwc_final(float* __restrict__ sum, float* __restri
   const int r = (int)((t / c) % R);
   const int64_t nidx = t / (c * R);
   float a = 0.f, b = 0.f, mm = -FLT_MAX;
-  for (int k = 0; k < chunks; ++k) {
-    const float* o = scratch + ((((int64_t)nidx * chunks + k) * R + r) * c + ch) * 3;
-    a += o[0]; b += o[1]; mm = fmaxf(mm, o[2]);
+  const int64_t kstride = (int64_t)R * c * 3;
+  const float* o = scratch + ((((int64_t)nidx * chunks) * R + r) * c + ch) * 3;
+  int k = 0;
+  for (; k + 4 <= chunks; k += 4) {                     // 12 independent loads in flight; same left-to-right sum order
+    float v[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { v[u][0] = o[(k + u) * kstride]; v[u][1] = o[(k + u) * kstride + 1]; v[u][2] = o[(k + u) * kstride + 2]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a += v[u][0]; b += v[u][1]; mm = fmaxf(mm, v[u][2]); }
   }
+  for (; k < chunks; ++k) { a += o[k * kstride]; b += o[k * kstride + 1]; mm = fmaxf(mm, o[k * kstride + 2]); }
   if (sum) sum[t] = a;
   if (sumsq) sumsq[t] = b;
   if (vmax) vmax[t] = mm;
