@@ -338,6 +338,26 @@ PPST_API int64_t ppst_guided_smooth_workspace_bytes(int64_t n, int h, int w);
 PPST_API int ppst_guided_smooth(float* out, const float* src, const float* guide, int64_t n, int h, int w, int radius,
                        float eps, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * image pre- / post-processing around the path, integer / byte work: bit-exact
+ * ------------------------------------------------------------------------------------------- */
+/* One pass of Pillow's 8-bit resampler (Image.resize(..., Image.BICUBIC) in data/base_dataset.py:150-172; Pillow
+ * src/libImaging/Resample.c ImagingResampleHorizontal_8bpc / Vertical_8bpc):
+ *   out = clip8((2^21 + sum_k in[first + k] * kk[o][k]) >> 22)
+ * in: uint8 [n, in_h, in_w, c]; axis 0 resamples x (out [n, in_h, out_len, c]), axis 1 resamples y (out [n, out_len,
+ * in_w, c]).  bounds int32 [out_len][2] = (first input index, tap count), kk int32 [out_len][ksize] fixed-point
+ * (22 fractional bits) coefficients, both as Pillow's precompute_coeffs + normalize_coeffs_8bpc produce them (built on
+ * the host: ppst_b200/imageio.py). */
+PPST_API int ppst_resample_u8(uint8_t* out, const uint8_t* in, const int* bounds, const int* kk, int64_t n, int in_h, int in_w,
+                     int out_len, int c, int ksize, int axis, void* stream);
+/* transforms.ToTensor() + Normalize(mean, std) (data/base_dataset.py:143-148): uint8 [n, hw, c] -> f32 [n, c, hw],
+ * (x / 255 - mean) / std with every step rounded to fp32. */
+PPST_API int ppst_u8_to_nchw_norm(float* out, const uint8_t* in, int64_t n, int64_t hw, int c, float mean, float stdv,
+                         void* stream);
+/* util.tensor2im (util/util.py:98-131): f32 [n, c, hw] -> uint8 [n, hw, c];
+ * normalize != 0: trunc(clip((x + 1) / 2 * 255, 0, 255)), else trunc(clip(x * 255, 0, 255)), in fp32. */
+PPST_API int ppst_tensor2im(uint8_t* out, const float* in, int64_t n, int64_t hw, int c, int normalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,9 @@ _SIGS = {
     "ppst_softmax_rows_split": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p]),
     "ppst_gemm_f32": (c_int, [c_void_p] * 3 + [c_i64] * 10 + [c_int, c_float, c_void_p]),
     "ppst_softmax_rows": (c_int, [c_void_p, c_i64, c_i64, c_float, c_void_p]),
+    "ppst_resample_u8": (c_int, [c_void_p] * 4 + [c_i64] + [c_int] * 6 + [c_void_p]),
+    "ppst_u8_to_nchw_norm": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_float, c_float, c_void_p]),
+    "ppst_tensor2im": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_guided_smooth_workspace_bytes": (c_i64, [c_i64, c_int, c_int]),
     "ppst_guided_smooth": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_float, c_void_p, c_i64,
                                    c_void_p]),
