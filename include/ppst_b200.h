@@ -199,6 +199,14 @@ PPST_API int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, con
 PPST_API int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, const float* bias, int64_t pixels, int cin,
                           int cout, int in_dtype, void* stream);
 
+/* Weight gradient of the thin input convolution above (training; torch.autograd's share of
+ * ConvLayer(3, C, 1) in the encoders and the discriminator, stylegan2_layers.py:582-649):
+ *   dw f32 [cout][cin] = sum_{n,pix} g[n,pix,co] * x[n,ci,pix],  g NHWC (bf16 / f32) [n, hw, cout], x NCHW f32 [n, cin<=4, hw].
+ * scratch: f32 workspace of ppst_conv1x1_thin_wgrad_scratch_elems(n, hw, cout) elements.  Deterministic. */
+PPST_API int64_t ppst_conv1x1_thin_wgrad_scratch_elems(int64_t n, int64_t hw, int cout);
+PPST_API int ppst_conv1x1_thin_wgrad(float* dw, const void* g, const float* x, int64_t n, int cin, int64_t hw, int cout,
+                            int g_dtype, float* scratch, void* stream);
+
 /* Per-sample input-channel scaling of packed weights (StyleGAN2-style weight modulation) for ppst_conv_tc with
  * w_img_rows = rows:  out bf16 [n][rows][taps*cin] = w f32 [rows][taps*cin] * a f32 [n][cin].  Folds the InstanceNorm
  * that PRECEDES the first convolution of the generator's feature heads (generator.py:180-231) into that convolution. */
@@ -217,6 +225,26 @@ PPST_API int ppst_modulate_weights(void* out_w, float* out_bias, const float* w,
                           const float* base_bias, int64_t n, int64_t rows, int taps, int cin, void* stream);
 PPST_API int ppst_fill_border(void* buf, const float* a, const float* b, int64_t n, int h, int w, int c, int pad, int dtype,
                      void* stream);
+
+/* Weight gradient of a convolution on the tcgen05 path -- the training step's share of the convolution work
+ * (SURVEY.md 8(f)4).  Replaces what torch.autograd / cuDNN compute for the `weight` of F.conv2d in EqualConv2d
+ * (stylegan2_layers.py:188), EqualizedConv2d (:320,331,339-341) and nn.Conv2d (generator.py:14-19); with x and dy
+ * exchanged it is also the weight gradient of F.conv_transpose2d (:320).
+ *   dw[co][ty][tx][ci] = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n, oy*stride + ty + off_y, ox*stride + tx + off_x, ci]
+ * (x = 0 outside the image: off < 0 is zero padding).  x: bf16 NHWC [n,in_h,in_w,cin]; dy: bf16 NHWC [n,out_h,out_w,cout];
+ * dw: f32 [cout][kh*kw*cin], the packing ppst_conv_tc consumes.  fp32 accumulation in tensor memory, deterministic
+ * (fixed-order reduction over samples and pixel chunks).  The input gradient needs no entry point of its own: it is
+ * ppst_conv_tc over dy with the flipped / transposed weights (stride 2: four sub-pixel phases).
+ * workspace: device scratch of ppst_conv_wgrad_workspace_bytes(d) bytes, owned by the caller. */
+typedef struct {
+  int32_t n, in_h, in_w, cin;
+  int32_t out_h, out_w, cout;
+  int32_t kh, kw, stride;         /* stride 1 or 2 */
+  int32_t off_y, off_x;           /* input row / col of tap (0,0) for output (0,0), as in ppst_conv_desc */
+} ppst_wgrad_desc;
+PPST_API int64_t ppst_conv_wgrad_workspace_bytes(const ppst_wgrad_desc* d);
+PPST_API int ppst_conv_wgrad(float* dw, const void* x, const void* dy, const ppst_wgrad_desc* d, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 
 /* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
 PPST_API int ppst_conv_tc_available(void);

@@ -332,10 +332,57 @@ def gen_function_py():
     print("function_py.npz")
 
 
+def gen_discriminator():
+    """The reference Discriminator (stylegan2_layers.py:582-649) at 256x256 (the stage-1 training size, first layer 3 -> 128)
+    with oracle.make_discriminator weights: output,
+    the stage-1 discriminator losses (ppst_model.py:68-92) and the R1 penalty (:139-156) with their parameter gradients
+    -- first and second order through the reference's own (fallback) ops and torch.autograd."""
+    RH.install()
+    from models.networks import stylegan2_layers as L
+    from models.networks import loss as RL
+    size = 256
+    sd = O.make_discriminator(size, seed=0, prefix="")
+    D = L.Discriminator(size, 2.0, blur_kernel=[1, 3, 3, 1])
+    missing = D.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(99)
+    real = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+    fake = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+    store = {"real": real.numpy(), "fake": fake.numpy()}
+    store["pred_real"] = D(real).detach().numpy()
+    keys = ["convs.0.Conv.weight", "convs.0.Act.bias", "convs.1.conv1.Conv.weight", "convs.1.conv2.Conv.weight",
+            "convs.1.conv2.Act.bias", "convs.1.skip.Conv.weight", "convs.3.conv1.Conv.weight", "convs.6.conv2.Conv.weight",
+            "final_conv.Conv.weight",
+            "final_linear.0.weight", "final_linear.0.bias", "final_linear.1.weight"]
+    params = dict(D.named_parameters())
+    # D step
+    D.zero_grad()
+    l_real = RL.gan_loss(D(real), True)
+    l_rec = RL.gan_loss(D(fake), False) * 0.5
+    (l_real + l_rec).backward()
+    store["D_real"], store["D_rec"] = np.float64(l_real.item()), np.float64(l_rec.item())
+    for k in keys:
+        summarize(store, "dstep_grad/" + k, params[k].grad)
+    # R1 step (ppst_model.py:139-156, lambda_R1 = 10)
+    D.zero_grad()
+    r = real.clone().requires_grad_(True)
+    pred = D(r).sum()
+    grad_real, = torch.autograd.grad(outputs=pred, inputs=[r], create_graph=True, retain_graph=True)
+    pen = grad_real.pow(2).sum(dim=(1, 2, 3)) * 5.0
+    summarize(store, "r1/grad_real", grad_real)
+    store["r1/penalty"] = pen.detach().numpy().astype(np.float64)
+    pen.mean().backward()
+    for k in keys:
+        summarize(store, "r1_grad/" + k, params[k].grad)
+    np.savez_compressed(os.path.join(OUT, "discriminator.npz"), **store)
+    print("discriminator.npz", store["D_real"], store["D_rec"], store["r1/penalty"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "layers", "function", "nets"]
+    which = sys.argv[1:] or ["ops", "layers", "function", "nets", "discriminator"]
+    if "discriminator" in which:
+        gen_discriminator()
     if "ops" in which:
         gen_ops()
     if "layers" in which:

@@ -5,7 +5,7 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 legs may import it, and there only as the checker / the reported CPU baseline.
 
 This is a *functional restatement* (plain fp32 PyTorch-on-CPU tensor arithmetic, no
-nn.Module, no autograd) of what the reference computes on the path that
+nn.Module; autograd only as the differentiator of the restated discriminator, section D) of what the reference computes on the path that
 BASELINE.json:north_star names.  Every function cites the reference lines it follows
 (paths relative to /root/reference).  The dense arithmetic the reference delegates to
 third-party code (ATen conv2d / linear / interpolate, torch 2.x) is delegated to the same
@@ -512,6 +512,142 @@ def masked_gap_gmp(x, label, n_labels=3):
         xm = x * m
         outs.append((xm.mean(dim=(2, 3)), xm.amax(dim=(2, 3))))
     return outs
+
+
+# --------------------------------------------------------------------------------------
+# D -- discriminator and its training losses (models/networks/stylegan2_layers.py:582-649,
+# models/networks/discriminator.py:5-32, models/ppst_model.py:68-92,139-156, models/networks/loss.py:11-18).
+# These functions are differentiable torch expressions: gradients for the parity tests come from
+# torch.autograd through them, exactly as the reference obtains its own (fallback-op) gradients.
+# --------------------------------------------------------------------------------------
+D_CHANNELS = {4: 512, 8: 512, 16: 512, 32: 512, 64: 512, 128: 256, 256: 128, 512: 64, 1024: 32}   # channel_multiplier 2
+
+
+def d_block_names(size):
+    """stylegan2_layers.py:603-611: one ResBlock per octave from `size` down to 4x4."""
+    log_size = int(math.log(2 ** int(round(math.log(size, 2))), 2))
+    out = []
+    for i in range(log_size, 2, -1):
+        out.append(("convs." + (str(9 - i) if i <= 8 else "%dx%d" % (2 ** i, 2 ** i)), D_CHANNELS[2 ** i], D_CHANNELS[2 ** (i - 1)]))
+    return out
+
+
+def res_block_d(sd, p, x):
+    """ResBlock as the discriminator builds it (stylegan2_layers.py:559-579, :609): zero padding, blur [1,3,3,1]."""
+    out = conv_layer(sd, p + "conv1.", x, 3)
+    out = conv_layer(sd, p + "conv2.", out, 3, downsample=True)
+    skip = conv_layer(sd, p + "skip.", x, 1, downsample=True, activate=False)
+    return (out + skip) / SQRT2
+
+
+def discriminator(sd, x, prefix="stylegan2_D."):
+    """Discriminator.forward, stylegan2_layers.py:627-645 (minibatch-stddev is commented out upstream)."""
+    size = x.shape[-1]
+    out = conv_layer(sd, prefix + "convs.0.", x, 1)
+    for name, _, _ in d_block_names(size):
+        out = res_block_d(sd, prefix + name + ".", out)
+    out = conv_layer(sd, prefix + "final_conv.", out, 3)
+    out = out.reshape(out.shape[0], -1)
+    w0, b0 = sd[prefix + "final_linear.0.weight"], sd[prefix + "final_linear.0.bias"]
+    out = fused_leaky_relu(F.linear(out, w0 * (1.0 / math.sqrt(w0.shape[1]))), b0)       # EqualLinear(activation), :231-238
+    w1, b1 = sd[prefix + "final_linear.1.weight"], sd[prefix + "final_linear.1.bias"]
+    return F.linear(out, w1 * (1.0 / math.sqrt(w1.shape[1])), b1)
+
+
+def gan_loss(pred, real):
+    """loss.py:11-18 (the least-squares form that is live upstream)."""
+    return torch.mean((pred - 1) ** 2) if real else torch.mean(pred ** 2)
+
+
+def d_losses(sd, real, fake, lambda_gan=1.0):
+    """compute_image_discriminator_losses, training stage 1 (ppst_model.py:68-92)."""
+    return {"D_real": gan_loss(discriminator(sd, real), True) * lambda_gan,
+            "D_rec": gan_loss(discriminator(sd, fake), False) * (0.5 * lambda_gan)}
+
+
+def r1_loss(sd, real, lambda_r1=10.0):
+    """compute_R1_loss, ppst_model.py:139-156."""
+    real = real.detach().requires_grad_(True)
+    pred = discriminator(sd, real).sum()
+    grad_real, = torch.autograd.grad(outputs=pred, inputs=[real], create_graph=True, retain_graph=True)
+    return grad_real.pow(2).sum(dim=(1, 2, 3)) * (lambda_r1 * 0.5)
+
+
+def _q(t):
+    """Round to bfloat16 and back.  Under autograd the gradient is rounded at the same point on its way back."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def fold_fir(w, k):
+    """Stencil product of a conv weight [co,ci,kh,kw] and a FIR kernel: conv(w) o blur(k) == conv(fold_fir(w, k))."""
+    co, ci, kh, kw = w.shape
+    kf = torch.flip(k.to(w.dtype), [0, 1]).view(1, 1, *k.shape)
+    out = F.conv_transpose2d(w.reshape(co * ci, 1, kh, kw), kf)
+    return out.view(co, ci, kh + k.shape[0] - 1, kw + k.shape[1] - 1)
+
+
+def discriminator_bf16_emulation(sd, x, prefix="stylegan2_D."):
+    """NOT a restatement of the reference: the discriminator with the PRODUCT's bf16 rounding points (weights of the
+    tensor-core convolutions, every stored activation, every stored activation gradient) and its blur-folded stride-2
+    convolutions, in torch fp32 arithmetic.  Second checker for the training tests: against the fp32 reference a bf16
+    network differs mostly by leaky-ReLU branch flips of near-zero activations (several % in rel-L2 after 16 layers);
+    against this emulation the flips coincide and what is left is accumulation order."""
+    size = x.shape[-1]
+    blur = make_kernel([1, 3, 3, 1])
+    w = sd[prefix + "convs.0.Conv.weight"]
+    out = _q(fused_leaky_relu(F.conv2d(x, w * (1.0 / math.sqrt(3.0))), sd[prefix + "convs.0.Act.bias"]))
+    for name, c, co in d_block_names(size):
+        p = prefix + name + "."
+        s3 = 1.0 / math.sqrt(c * 9)
+        y = _q(fused_leaky_relu(F.conv2d(out, _q(sd[p + "conv1.Conv.weight"] * s3), padding=1), sd[p + "conv1.Act.bias"]))
+        y = _q(fused_leaky_relu(F.conv2d(y, _q(fold_fir(sd[p + "conv2.Conv.weight"] * s3, blur)), stride=2, padding=2),
+                                sd[p + "conv2.Act.bias"]))
+        sk = _q(F.conv2d(out, _q(fold_fir(sd[p + "skip.Conv.weight"] * (1.0 / math.sqrt(c)), blur)), stride=2, padding=1))
+        out = _q((y + sk) / SQRT2)
+    c = out.shape[1]
+    out = _q(fused_leaky_relu(F.conv2d(out, _q(sd[prefix + "final_conv.Conv.weight"] * (1.0 / math.sqrt(c * 9))), padding=1),
+                              sd[prefix + "final_conv.Act.bias"]))
+    out = out.reshape(out.shape[0], -1)
+    w0, b0 = sd[prefix + "final_linear.0.weight"], sd[prefix + "final_linear.0.bias"]
+    out = fused_leaky_relu(F.linear(out, w0 * (1.0 / math.sqrt(w0.shape[1]))), b0)
+    w1, b1 = sd[prefix + "final_linear.1.weight"], sd[prefix + "final_linear.1.bias"]
+    return F.linear(out, w1 * (1.0 / math.sqrt(w1.shape[1])), b1)
+
+
+def shapes_D(size):
+    sh = {}
+    c0 = D_CHANNELS[2 ** int(round(math.log(size, 2)))]
+    sh["convs.0.Conv.weight"] = (c0, 3, 1, 1)
+    sh["convs.0.Act.bias"] = (c0,)
+    c = c0
+    for name, ci, co in d_block_names(size):
+        sh[name + ".conv1.Conv.weight"] = (ci, ci, 3, 3)
+        sh[name + ".conv1.Act.bias"] = (ci,)
+        sh[name + ".conv2.Conv.weight"] = (co, ci, 3, 3)
+        sh[name + ".conv2.Act.bias"] = (co,)
+        sh[name + ".skip.Conv.weight"] = (co, ci, 1, 1)
+        c = co
+    sh["final_conv.Conv.weight"] = (512, c, 3, 3)
+    sh["final_conv.Act.bias"] = (512,)
+    sh["final_linear.0.weight"] = (512, 512 * 16)
+    sh["final_linear.0.bias"] = (512,)
+    sh["final_linear.1.weight"] = (1, 512)
+    sh["final_linear.1.bias"] = (1,)
+    return sh
+
+
+def make_discriminator(size, seed=0, prefix="stylegan2_D."):
+    """Seeded synthetic discriminator weights under the reference's state_dict keys (N(0,1) weights with the runtime
+    equalised-lr scaling, small non-zero biases)."""
+    g = torch.Generator().manual_seed(seed * 3 + 14)
+    sd = {}
+    shapes = shapes_D(size)
+    for k in sorted(shapes):
+        sd[prefix + k] = (0.1 * torch.randn(shapes[k], generator=g)) if k.endswith("bias") else torch.randn(shapes[k], generator=g)
+    for name, _, _ in d_block_names(size):
+        for l in ("conv2", "skip"):
+            sd[prefix + name + "." + l + ".Blur.kernel"] = make_kernel([1, 3, 3, 1])
+    return sd
 
 
 # --------------------------------------------------------------------------------------

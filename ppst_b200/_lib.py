@@ -28,6 +28,11 @@ class ConvDesc(ctypes.Structure):
                 ("out_pad", ctypes.c_int32), ("bias_img_stride", ctypes.c_int32)]
 
 
+class WgradDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("n", "in_h", "in_w", "cin", "out_h", "out_w", "cout", "kh", "kw", "stride", "off_y", "off_x")]
+
+
 class ApplyDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("n", "h", "w", "c", "up", "pad_t", "pad_b", "pad_l", "pad_r", "pad_mode")] + \
@@ -58,11 +63,15 @@ _SIGS = {
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_available": (c_int, []),
+    "ppst_conv_wgrad_workspace_bytes": (c_i64, [ctypes.POINTER(WgradDesc)]),
+    "ppst_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(WgradDesc), c_void_p, c_i64, c_void_p]),
     "ppst_scale_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_modulate_weights": (c_int, [c_void_p] * 6 + [c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_fill_border": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_conv1x1_in_nchw": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_float, c_float,
                                                      c_int, c_void_p]),
+    "ppst_conv1x1_thin_wgrad_scratch_elems": (c_i64, [c_i64, c_i64, c_int]),
+    "ppst_conv1x1_thin_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),
     "ppst_in_coeffs": (c_int, [c_void_p] * 6 + [c_i64, c_void_p, c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),

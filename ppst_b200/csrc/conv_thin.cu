@@ -141,27 +141,116 @@ __global__ void __launch_bounds__(256) conv1x1_thin_out_kernel(float* __restrict
   }
 }
 
+// Weight gradient of the thin input convolution (training): dw[co][ci] = sum_{n,pix} g[n,pix,co] * x[n,ci,pix]
+// with g NHWC (bf16 / f32) and x the NCHW f32 image.  Stage 1: one block per (sample, chunk of kWgChunk pixels); thread =
+// (group of 8 output channels, pixel lane); block partials are combined through shared memory in a fixed order.
+constexpr int kWgChunk = 2048;
+template <typename TG>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(float* __restrict__ partials, const TG* __restrict__ g,
+                                                         const float* __restrict__ x, int cin, int64_t hw, int cout) {
+  __shared__ float s[8192];                          // [pixel lane][cout][4]
+  const int V = cout / 8, PL = 256 / V;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V;
+  const int64_t chunks = (hw + kWgChunk - 1) / kWgChunk;
+  const int64_t ni = blockIdx.x / chunks, p0 = (blockIdx.x - ni * chunks) * kWgChunk;
+  const int np = (int)((hw - p0) < kWgChunk ? (hw - p0) : kWgChunk);
+  float acc[8][4];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) acc[e][ci] = 0.0f;
+  const TG* gp = g + (ni * hw + p0) * cout + v * 8;
+  const float* xp = x + ni * cin * hw + p0;
+  for (int pix = pl; pix < np; pix += PL) {
+    float gv[8];
+    if (sizeof(TG) == 2) {
+      const Vec16<TG> r = ld_vec16_stream(gp + (int64_t)pix * cout);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = Cvt<TG>::to_f(r.v[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gv[e] = Cvt<TG>::to_f(gp[(int64_t)pix * cout + e]);
+    }
+    float xv[4];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) xv[ci] = ci < cin ? xp[ci * hw + pix] : 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) acc[e][ci] = fmaf(gv[e], xv[ci], acc[e][ci]);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    *reinterpret_cast<float4*>(&s[((pl * cout) + v * 8 + e) * 4]) = make_float4(acc[e][0], acc[e][1], acc[e][2], acc[e][3]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout * 4; i += 256) {
+    float t = 0.0f;
+    for (int l = 0; l < PL; ++l) t += s[l * cout * 4 + i];
+    partials[(int64_t)blockIdx.x * cout * 4 + i] = t;
+  }
+}
+
+__global__ void thin_wgrad_final(float* __restrict__ dw, const float* __restrict__ partials, int64_t J, int cout, int cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin) return;
+  const int co = i / cin, ci = i - co * cin;
+  float t = 0.0f;
+  for (int64_t j = 0; j < J; ++j) t += partials[(j * cout + co) * 4 + ci];
+  dw[i] = t;
+}
+
 }  // namespace ppst
+
+extern "C" int64_t ppst_conv1x1_thin_wgrad_scratch_elems(int64_t n, int64_t hw, int cout) {
+  return n * ((hw + ppst::kWgChunk - 1) / ppst::kWgChunk) * cout * 4;
+}
+
+extern "C" int ppst_conv1x1_thin_wgrad(float* dw, const void* g, const float* x, int64_t n, int cin, int64_t hw, int cout,
+                                       int g_dtype, float* scratch, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(dw && g && x && scratch && n > 0 && hw > 0 && cin >= 1 && cin <= 4, PPST_ERR_ARG, "conv1x1_thin_wgrad: bad args");
+  PPST_REQUIRE(cout % 8 == 0 && cout >= 8 && cout <= 256 && 256 % (cout / 8) == 0, PPST_ERR_UNSUPPORTED,
+               "conv1x1_thin_wgrad: cout=%d (8, 16, 32, 64, 128 or 256)", cout);
+  const int64_t J = n * ((hw + kWgChunk - 1) / kWgChunk);
+  PPST_REQUIRE(J < (1LL << 31), PPST_ERR_ARG, "conv1x1_thin_wgrad: too many blocks");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_dtype == PPST_BF16)
+    thin_wgrad_kernel<__nv_bfloat16><<<(unsigned)J, 256, 0, st>>>(scratch, (const __nv_bfloat16*)g, x, cin, hw, cout);
+  else if (g_dtype == PPST_F32)
+    thin_wgrad_kernel<float><<<(unsigned)J, 256, 0, st>>>(scratch, (const float*)g, x, cin, hw, cout);
+  else
+    PPST_REQUIRE(false, PPST_ERR_DTYPE, "conv1x1_thin_wgrad: g dtype %d", g_dtype);
+  PPST_LAUNCH_CHECK("thin_wgrad_kernel");
+  thin_wgrad_final<<<(cout * cin + 127) / 128, 128, 0, st>>>(dw, scratch, J, cout, cin);
+  PPST_LAUNCH_CHECK("thin_wgrad_final");
+  return 0;
+}
 
 extern "C" int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, const float* bias, int64_t n, int cin,
                                     int64_t hw, int cout, int cout_stride, int c_off, int has_act, float slope,
                                     float gain, int out_dtype, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(out && x && w && n > 0 && hw > 0 && cin >= 1 && cin <= 4, PPST_ERR_ARG, "conv1x1_in_nchw: bad args");
-  PPST_REQUIRE(cout == 32, PPST_ERR_UNSUPPORTED, "conv1x1_in_nchw: cout=%d (32 supported: FromRGB)", cout);
+  PPST_REQUIRE(cout == 32 || cout == 64 || cout == 128, PPST_ERR_UNSUPPORTED,
+               "conv1x1_in_nchw: cout=%d (32: FromRGB of the encoders; 64 / 128: the discriminator's first layer)", cout);
   PPST_REQUIRE(c_off % 8 == 0 && cout_stride % 8 == 0 && c_off + cout <= cout_stride, PPST_ERR_ARG,
                "conv1x1_in_nchw: channel slice");
   const int64_t tiles = n * ((hw + kPixBlock - 1) / kPixBlock);
   const int blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == PPST_BF16)
-    conv1x1_in_nchw_kernel<__nv_bfloat16, 32><<<blocks, 256, 0, st>>>((__nv_bfloat16*)out, x, w, bias, n, cin, hw,
-                                                                      cout_stride, c_off, has_act, slope, gain);
-  else if (out_dtype == PPST_F32)
-    conv1x1_in_nchw_kernel<float, 32><<<blocks, 256, 0, st>>>((float*)out, x, w, bias, n, cin, hw, cout_stride, c_off,
-                                                              has_act, slope, gain);
-  else
-    PPST_REQUIRE(false, PPST_ERR_DTYPE, "conv1x1_in_nchw: out dtype %d", out_dtype);
+#define PPST_IN_NCHW(TO, CO) \
+  conv1x1_in_nchw_kernel<TO, CO><<<blocks, 256, 0, st>>>((TO*)out, x, w, bias, n, cin, hw, cout_stride, c_off, has_act, slope, gain)
+  PPST_REQUIRE(out_dtype == PPST_BF16 || out_dtype == PPST_F32, PPST_ERR_DTYPE, "conv1x1_in_nchw: out dtype %d", out_dtype);
+  if (out_dtype == PPST_BF16) {
+    if (cout == 32) PPST_IN_NCHW(__nv_bfloat16, 32);
+    else if (cout == 64) PPST_IN_NCHW(__nv_bfloat16, 64);
+    else PPST_IN_NCHW(__nv_bfloat16, 128);
+  } else {
+    if (cout == 32) PPST_IN_NCHW(float, 32);
+    else if (cout == 64) PPST_IN_NCHW(float, 64);
+    else PPST_IN_NCHW(float, 128);
+  }
+#undef PPST_IN_NCHW
   PPST_LAUNCH_CHECK("conv1x1_in_nchw_kernel");
   return 0;
 }

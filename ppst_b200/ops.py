@@ -324,7 +324,8 @@ def linear(x, w, b=None, w_scale=1.0, b_scale=1.0, relu_in=False):
     m, k = x.shape
     n = w.shape[0]
     y = torch.empty((m, n), device=x.device, dtype=torch.float32)
-    check(_L().ppst_linear(ptr(y), ptr(x), ptr(w), ptr(b), m, n, k, x.stride(0), float(w_scale), float(b_scale),
+    ldx = x.stride(0) if m > 1 else k               # the stride of a size-1 dimension is arbitrary
+    check(_L().ppst_linear(ptr(y), ptr(x), ptr(w), ptr(b), m, n, k, ldx, float(w_scale), float(b_scale),
                            1 if relu_in else 0, stream()))
     return y
 

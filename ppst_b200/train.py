@@ -1,0 +1,530 @@
+"""Training-side operators and the discriminator on the B200 kernels (BASELINE config 5).
+
+What the reference does with torch.autograd + cuDNN (F.conv2d / F.conv_transpose2d forward, dgrad, wgrad in fp32) runs
+here on the tcgen05 convolution kernel of the inference path:
+
+    forward   y  = conv(x, w)                     ppst_conv_tc                      (bf16 operands, fp32 accumulate)
+    dgrad     dx = conv(dy, flip(w)^T)            ppst_conv_tc again: stride 1 = one plain convolution with the rotated,
+                                                  transposed weights; stride 2 = four sub-pixel phases (no zero insertion)
+    wgrad     dw = sum_pixels dy (x) shift(x)     ppst_conv_wgrad (pixel-major operands, K-split tensor-core GEMM)
+
+The three maps are bilinear and closed under differentiation, so each is a torch.autograd.Function whose backward calls
+the other two: first AND second derivatives (the R1 penalty, models/ppst_model.py:139-156, differentiates the input
+gradient of D once more) run on the same kernels.  Activations are NHWC bf16 tensors [n, h, w, c]; parameters stay fp32
+in the reference's layout ([co, ci, kh, kw], state_dict keys unchanged) and are packed per call.
+
+torch supplies the tape (autograd), device memory and the optimiser; all activation-sized work is in libppst_b200.so.
+No CPU path: CPU tensors raise.
+"""
+import ctypes
+import math
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops, packing
+from ._lib import BF16, F32, WgradDesc, check, dt, ptr, require_cuda, stream
+
+SQRT2 = math.sqrt(2.0)
+
+
+# ------------------------------------------------------------------------------------------------ raw launches
+class Geom:
+    """A square-kernel convolution: kernel size k, stride (1 or 2), symmetric zero padding."""
+
+    __slots__ = ("k", "stride", "pad")
+
+    def __init__(self, k, stride=1, pad=0):
+        self.k, self.stride, self.pad = int(k), int(stride), int(pad)
+
+    def out_hw(self, h, w):
+        return (h + 2 * self.pad - self.k) // self.stride + 1, (w + 2 * self.pad - self.k) // self.stride + 1
+
+
+def _nhwc(t):
+    require_cuda(t)
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t.contiguous()
+
+
+def _conv_raw(x, w, g, bias=None, act=False):
+    """x NHWC bf16 [n,h,w,ci], w f32 [co,ci,k,k] -> NHWC bf16 [n,oh,ow,co]; optional fused bias + leaky-ReLU(0.2)*sqrt2."""
+    n, h, wd, ci = x.shape
+    co = w.shape[0]
+    assert w.shape[1] == ci and w.shape[2] == g.k and w.shape[3] == g.k, (tuple(w.shape), tuple(x.shape))
+    oh, ow = g.out_hw(h, wd)
+    wp = packing.pack_taps(w.detach().to(torch.float32)).to(torch.bfloat16).unsqueeze(0).contiguous()
+    out = torch.empty((n, oh, ow, co), device=x.device, dtype=torch.bfloat16)
+    d = ops.conv_desc(x.shape, co, g.k, g.k, stride=g.stride, off=(-g.pad, -g.pad), out_hw=(oh, ow), act=act,
+                      slope=0.2, gain=SQRT2 if act else 1.0, in_dtype=BF16, out_dtype=BF16)
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    ops.conv_tc(out, x, wp, b, None, None, d)
+    return out
+
+
+def _phase_taps(k, pad, r):
+    """Stride-2 input gradient, one axis: input index 2a + r receives dy[a - u] * w[2u + r + pad] for the u with a valid
+    tap.  Returns (u_hi, [tap index or -1 for j = 0.. : u = u_hi - j])."""
+    us = [u for u in range(-k, k + 1) if 0 <= 2 * u + r + pad < k]
+    return (max(us), min(us)) if us else (0, 1)
+
+
+def _dgrad_raw(gy, w, g, in_hw):
+    """dx NHWC bf16 [n, in_h, in_w, ci] of y = conv(x, w) given dy (NHWC bf16 [n,oh,ow,co])."""
+    n, oh, ow, co = gy.shape
+    ci, k = w.shape[1], g.k
+    assert w.shape[0] == co
+    w32 = w.detach().to(torch.float32)
+    out = torch.empty((n, in_hw[0], in_hw[1], ci), device=gy.device, dtype=torch.bfloat16)
+    if g.stride == 1:
+        wp = torch.flip(w32, [2, 3]).permute(1, 2, 3, 0).reshape(ci, k * k * co).to(torch.bfloat16).unsqueeze(0).contiguous()
+        off = -(k - 1) + g.pad
+        d = ops.conv_desc(gy.shape, ci, k, k, stride=1, off=(off, off), out_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
+        ops.conv_tc(out, gy, wp, None, None, None, d)
+        return out
+    assert g.stride == 2 and in_hw[0] % 2 == 0 and in_hw[1] % 2 == 0, "stride-2 input gradient needs even input sizes"
+    (hi0, lo0), (hi1, lo1) = _phase_taps(k, g.pad, 0), _phase_taps(k, g.pad, 1)
+    J = max(hi0 - lo0, hi1 - lo1) + 1
+    his = (hi0, hi1)
+    wph = w32.new_zeros(2, 2, ci, J, J, co)
+    for ry in range(2):
+        for rx in range(2):
+            for jy in range(J):
+                ty = 2 * (his[ry] - jy) + ry + g.pad
+                if not 0 <= ty < k:
+                    continue
+                for jx in range(J):
+                    tx = 2 * (his[rx] - jx) + rx + g.pad
+                    if 0 <= tx < k:
+                        wph[ry, rx, :, jy, jx, :] = w32[:, :, ty, tx].t()
+    wp = wph.reshape(4, ci, J * J * co).to(torch.bfloat16).contiguous()
+    d = ops.conv_desc(gy.shape, ci, J, J, stride=1, off=(-hi0, -hi0), out_hw=(in_hw[0] // 2, in_hw[1] // 2), phases=(2, 2),
+                      phase_off=(hi0 - hi1, hi0 - hi1), full_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
+    ops.conv_tc(out, gy, wp, None, None, None, d)
+    return out
+
+
+_ws = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), device=device, dtype=torch.uint8)
+        _ws[key] = buf
+    return buf
+
+
+def _wgrad_raw(x, gy, g, wshape):
+    """dw f32 [co,ci,k,k] of y = conv(x, w): x NHWC bf16 [n,h,w,ci], dy NHWC bf16 [n,oh,ow,co]."""
+    n, h, wd, ci = x.shape
+    _, oh, ow, co = gy.shape
+    assert tuple(wshape) == (co, ci, g.k, g.k), (tuple(wshape), co, ci, g.k)
+    d = WgradDesc(n, h, wd, ci, oh, ow, co, g.k, g.k, g.stride, -g.pad, -g.pad)
+    L = _lib.load()
+    nbytes = L.ppst_conv_wgrad_workspace_bytes(ctypes.byref(d))
+    if nbytes < 0:
+        check(-1)
+    ws = _workspace(x.device, nbytes)
+    dw = torch.empty((co, g.k * g.k * ci), device=x.device, dtype=torch.float32)
+    with ops._Prof("conv_wgrad", 2.0 * n * oh * ow * co * ci * g.k * g.k, "n%d %dx%d ci%d co%d k%d s%d" % (n, oh, ow, ci, co, g.k, g.stride)):
+        check(L.ppst_conv_wgrad(ptr(dw), ptr(x), ptr(gy), ctypes.byref(d), ptr(ws), ws.numel(), stream()))
+    return dw.view(co, g.k, g.k, ci).permute(0, 3, 1, 2).contiguous()
+
+
+def _act_grad_raw(gy, y):
+    """dy -> d(pre-activation) of y = lrelu(v, 0.2) * sqrt2, from the OUTPUT's sign (fused_act.py:27-35)."""
+    out = torch.empty_like(gy)
+    check(_lib.load().ppst_fused_bias_act(ptr(out), ptr(gy), None, ptr(y), gy.numel(), 1, 0, 3, 1, 0.2, SQRT2, dt(gy), stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ autograd closure
+class _Conv(Function):
+    @staticmethod
+    def forward(ctx, x, w, g):
+        x = _nhwc(x)
+        ctx.save_for_backward(x, w)
+        ctx.g = g
+        return _conv_raw(x, w, g)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _nhwc(gy)
+        dx = _ConvT.apply(gy, w, ctx.g, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
+        dw = _Wgrad.apply(x, gy, ctx.g, tuple(w.shape)) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+class _ConvT(Function):
+    """The input gradient of _Conv as a function of (dy, w)."""
+
+    @staticmethod
+    def forward(ctx, gy, w, g, in_hw):
+        gy = _nhwc(gy)
+        ctx.save_for_backward(gy, w)
+        ctx.g = g
+        return _dgrad_raw(gy, w, g, in_hw)
+
+    @staticmethod
+    def backward(ctx, gz):
+        gy, w = ctx.saved_tensors
+        gz = _nhwc(gz)
+        dgy = _Conv.apply(gz, w, ctx.g) if ctx.needs_input_grad[0] else None
+        dw = _Wgrad.apply(gz, gy, ctx.g, tuple(w.shape)) if ctx.needs_input_grad[1] else None
+        return dgy, dw, None, None
+
+
+class _Wgrad(Function):
+    """The weight gradient of _Conv as a function of (x, dy)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, g, wshape):
+        x, gy = _nhwc(x), _nhwc(gy)
+        ctx.save_for_backward(x, gy)
+        ctx.g = g
+        return _wgrad_raw(x, gy, g, wshape)
+
+    @staticmethod
+    def backward(ctx, gdw):
+        x, gy = ctx.saved_tensors
+        dx = _ConvT.apply(gy, gdw, ctx.g, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
+        dgy = _Conv.apply(x, gdw, ctx.g) if ctx.needs_input_grad[1] else None
+        return dx, dgy, None, None
+
+
+class _ActGrad(Function):
+    """g -> g * (y > 0 ? 1 : 0.2) * sqrt2; linear in g, y only selects the branch (FusedLeakyReLUFunctionBackward,
+    fused_act.py:23-52)."""
+
+    @staticmethod
+    def forward(ctx, gy, y):
+        ctx.save_for_backward(y)
+        return _act_grad_raw(gy.contiguous(), y)
+
+    @staticmethod
+    def backward(ctx, gg):
+        y, = ctx.saved_tensors
+        return _ActGrad.apply(gg.to(y.dtype), y), None
+
+
+class _ChannelSum(Function):
+    """NHWC [n,h,w,c] -> f32 [c]: the bias gradient (`grad_input.sum(dim)`, fused_act.py:37-42)."""
+
+    @staticmethod
+    def forward(ctx, g):
+        ctx.shape, ctx.dtype = g.shape, g.dtype
+        s = ops.plane_reduce(g.contiguous(), channels_last=True, want=("sum",))["sum"]      # [n, 1, c]
+        return s.sum(dim=(0, 1))
+
+    @staticmethod
+    def backward(ctx, gb):
+        return gb.to(ctx.dtype).view(1, 1, 1, -1).expand(ctx.shape)
+
+
+class _ConvBiasAct(Function):
+    """conv + bias (+ leaky-ReLU(0.2) * sqrt2) in ONE launch (EqualConv2d + FusedLeakyReLU, stylegan2_layers.py:497-555)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, g, act):
+        x = _nhwc(x)
+        y = _conv_raw(x, w, g, bias=b, act=act)
+        ctx.save_for_backward(x, w, y)
+        ctx.g, ctx.act = g, act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        gy = _nhwc(gy)
+        gp = _ActGrad.apply(gy, y) if ctx.act else gy
+        dx = _ConvT.apply(gp, w, ctx.g, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
+        dw = _Wgrad.apply(x, gp, ctx.g, tuple(w.shape)) if ctx.needs_input_grad[1] else None
+        db = _ChannelSum.apply(gp) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+def conv2d(x, w, stride=1, padding=0, bias=None, act=False):
+    """F.conv2d on NHWC bf16 activations (x [n,h,w,ci], w f32 [co,ci,k,k]) with the optional fused
+    FusedLeakyReLU epilogue; differentiable to second order."""
+    g = Geom(w.shape[2], stride, padding)
+    if bias is None and not act:
+        return _Conv.apply(x, w, g)
+    if bias is None:
+        bias = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
+    return _ConvBiasAct.apply(x, w, bias, g, act)
+
+
+# ------------------------------------------------------------------------------------------------ thin input layer
+def _thin_in_raw(img, w2, bias, act):
+    return ops.conv1x1_in_nchw(img.to(torch.float32), w2.detach().to(torch.float32).contiguous(),
+                               None if bias is None else bias.detach().to(torch.float32).contiguous(), act,
+                               torch.bfloat16)
+
+
+def _thin_out_raw(gp, w2):
+    """NHWC [n,h,w,co] x w2 [co, 3] -> d(image) NCHW f32 [n,3,h,w]."""
+    r = ops.conv1x1_thin_out(gp, w2.detach().to(torch.float32).t().contiguous(), None)     # [n,h,w,3] f32
+    return ops.nhwc_to_nchw(r)
+
+
+def _thin_wgrad_raw(gp, img):
+    n, h, wd, co = gp.shape
+    cin = img.shape[1]
+    L = _lib.load()
+    scratch = ops._get_scratch(gp.device, L.ppst_conv1x1_thin_wgrad_scratch_elems(n, h * wd, co))
+    dw = torch.empty((co, cin), device=gp.device, dtype=torch.float32)
+    check(L.ppst_conv1x1_thin_wgrad(ptr(dw), ptr(gp), ptr(img), n, cin, h * wd, co, dt(gp), ptr(scratch), stream()))
+    return dw
+
+
+class _ThinIn(Function):
+    """1x1 convolution of the NCHW f32 image (3 channels) into NHWC bf16 features, optional bias + FusedLeakyReLU
+    (ConvLayer(3, C, 1), stylegan2_layers.py:497-555)."""
+
+    @staticmethod
+    def forward(ctx, img, w2, b, act):
+        img = img.contiguous()
+        y = _thin_in_raw(img, w2, b, act)
+        ctx.save_for_backward(img, w2, y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        img, w2, y = ctx.saved_tensors
+        gy = _nhwc(gy)
+        gp = _ActGrad.apply(gy, y) if ctx.act else gy
+        dimg = _ThinOut.apply(gp, w2) if ctx.needs_input_grad[0] else None
+        dw = _ThinWgrad.apply(gp, img) if ctx.needs_input_grad[1] else None
+        db = _ChannelSum.apply(gp) if (ctx.needs_input_grad[2]) else None
+        return dimg, dw, db, None
+
+
+class _ThinOut(Function):
+    @staticmethod
+    def forward(ctx, gp, w2):
+        gp = _nhwc(gp)
+        ctx.save_for_backward(gp, w2)
+        return _thin_out_raw(gp, w2)
+
+    @staticmethod
+    def backward(ctx, gimg):
+        gp, w2 = ctx.saved_tensors
+        gimg = gimg.to(torch.float32).contiguous()
+        dgp = _ThinIn.apply(gimg, w2, None, False) if ctx.needs_input_grad[0] else None
+        dw = _ThinWgrad.apply(gp, gimg) if ctx.needs_input_grad[1] else None
+        return dgp, dw
+
+
+class _ThinWgrad(Function):
+    @staticmethod
+    def forward(ctx, gp, img):
+        gp, img = _nhwc(gp), img.to(torch.float32).contiguous()
+        ctx.save_for_backward(gp, img)
+        return _thin_wgrad_raw(gp, img)
+
+    @staticmethod
+    def backward(ctx, gdw):
+        gp, img = ctx.saved_tensors
+        dgp = _ThinIn.apply(img, gdw, None, False) if ctx.needs_input_grad[0] else None
+        dimg = _ThinOut.apply(gp, gdw) if ctx.needs_input_grad[1] else None
+        return dgp, dimg
+
+
+def conv1x1_from_image(img, w, bias=None, act=False):
+    """ConvLayer(3, C, 1): NCHW f32 image -> NHWC bf16 features.  w f32 [C, 3, 1, 1]."""
+    return _ThinIn.apply(img, w.reshape(w.shape[0], w.shape[1]), bias, act)
+
+
+# ------------------------------------------------------------------------------------------------ residual join, linear
+class _AddScale(Function):
+    """(a + b) * s on NHWC bf16 (ResBlock's `(out + skip) / sqrt(2)`, stylegan2_layers.py:571-579): one pass."""
+
+    @staticmethod
+    def forward(ctx, a, b, s):
+        ctx.s = s
+        a, b = _nhwc(a), _nhwc(b)
+        return ops.affine_apply(a, a.shape[3], res=b, res_mode=1, post_gain=s, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, g):
+        gs = _Scale.apply(g, ctx.s)
+        return gs, gs, None
+
+
+class _Scale(Function):
+    @staticmethod
+    def forward(ctx, g, s):
+        ctx.s = s
+        g = _nhwc(g)
+        return ops.affine_apply(g, g.shape[3], post_gain=s, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return _Scale.apply(gg, ctx.s), None
+
+
+def add_scale(a, b, s):
+    return _AddScale.apply(a, b, s)
+
+
+class _Linear(Function):
+    """y = x @ w^T on ppst_linear (f32; EqualLinear, stylegan2_layers.py:205-247).  x [m,k], w [n,k]."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.to(torch.float32).contiguous(), w.to(torch.float32).contiguous()
+        ctx.save_for_backward(x, w)
+        return ops.linear(x, w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        dx = _Linear.apply(gy, w.t()) if ctx.needs_input_grad[0] else None          # [m,n] @ [n,k]
+        dw = _Linear.apply(gy.t(), x.t()) if ctx.needs_input_grad[1] else None      # [n,m] @ [m,k]
+        return dx, dw
+
+
+def linear(x, w):
+    return _Linear.apply(x, w)
+
+
+# ------------------------------------------------------------------------------------------------ discriminator
+def _fold(w, blur_k):
+    """Blur (upfirdn2d, zero pad) followed by a stride-2 convolution == ONE stride-2 convolution with the stencil
+    product of the two kernels (packing.fold_fir, differentiable: F.conv_transpose2d on the small weight tensor)."""
+    return packing.fold_fir(w, blur_k)
+
+
+class Discriminator(torch.nn.Module):
+    """StyleGAN2 discriminator of the reference (stylegan2_layers.py:582-649, wrapped by models/networks/discriminator.py:
+    5-32) with the reference's parameter names and shapes: `load_state_dict` takes the reference's `stylegan2_D.*` keys
+    unchanged.  forward(x): NCHW f32 image [n,3,S,S] -> [n,1] f32.
+
+    Layer by layer: ConvLayer(3,C,1)+FusedLeakyReLU = one thin kernel; every ConvLayer = one tcgen05 convolution with the
+    bias + leaky-ReLU epilogue; Blur([1,3,3,1]) + stride-2 conv are folded into one 6x6 (main) / 4x4 (skip) stride-2
+    convolution whose zero padding is TMA out-of-bounds fill; the residual join is one pass; the two EqualLinear layers run
+    on ppst_linear."""
+
+    def __init__(self, size, channel_multiplier=2, blur_kernel=(1, 3, 3, 1)):
+        super().__init__()
+        nn = torch.nn
+        channels = {4: 512, 8: 512, 16: min(512, int(512 * channel_multiplier)), 32: min(512, int(512 * channel_multiplier)),
+                    64: int(256 * channel_multiplier), 128: int(128 * channel_multiplier), 256: int(64 * channel_multiplier),
+                    512: int(32 * channel_multiplier), 1024: int(16 * channel_multiplier)}
+        original_size = size
+        size = 2 ** int(round(math.log(size, 2)))
+        log_size = int(math.log(size, 2))
+        self.names = []
+        P = nn.ParameterDict()
+
+        def param(name, t):
+            P[name.replace(".", "/")] = nn.Parameter(t)
+
+        c = channels[size]
+        param("convs.0.Conv.weight", torch.randn(c, 3, 1, 1))
+        param("convs.0.Act.bias", torch.zeros(c))
+        self.blocks = []
+        for i in range(log_size, 2, -1):
+            co = channels[2 ** (i - 1)]
+            name = "convs." + (str(9 - i) if i <= 8 else "%dx%d" % (2 ** i, 2 ** i))
+            param(name + ".conv1.Conv.weight", torch.randn(c, c, 3, 3))
+            param(name + ".conv1.Act.bias", torch.zeros(c))
+            param(name + ".conv2.Conv.weight", torch.randn(co, c, 3, 3))
+            param(name + ".conv2.Act.bias", torch.zeros(co))
+            param(name + ".skip.Conv.weight", torch.randn(co, c, 1, 1))
+            self.blocks.append((name, c, co))
+            c = co
+        param("final_conv.Conv.weight", torch.randn(channels[4], c, 3, 3))
+        param("final_conv.Act.bias", torch.zeros(channels[4]))
+        self.side = int(4 * original_size / size)
+        param("final_linear.0.weight", torch.randn(channels[4], channels[4] * self.side ** 2))
+        param("final_linear.0.bias", torch.zeros(channels[4]))
+        param("final_linear.1.weight", torch.randn(1, channels[4]))
+        param("final_linear.1.bias", torch.zeros(1))
+        self.P = P
+        k = torch.tensor(list(blur_kernel), dtype=torch.float32)
+        k2 = k[None, :] * k[:, None]
+        self.register_buffer("blur", k2 / k2.sum(), persistent=False)
+        self.c_last = channels[4]
+
+    # reference state_dict layout <-> ParameterDict keys ('.' is not allowed in ParameterDict names)
+    def load_reference_state_dict(self, sd, prefix="stylegan2_D."):
+        own = {k.replace("/", "."): v for k, v in self.P.items()}
+        with torch.no_grad():
+            for k, v in own.items():
+                src = sd[prefix + k]
+                assert tuple(src.shape) == tuple(v.shape), (k, tuple(src.shape), tuple(v.shape))
+                v.copy_(src)
+        return self
+
+    def reference_state_dict(self, prefix="stylegan2_D."):
+        return {prefix + k.replace("/", "."): v.detach().clone() for k, v in self.P.items()}
+
+    def p(self, name):
+        return self.P[name.replace(".", "/")]
+
+    def forward(self, img):
+        p = self.p
+        w = p("convs.0.Conv.weight")
+        x = conv1x1_from_image(img, w * (1.0 / math.sqrt(3.0)), p("convs.0.Act.bias"), act=True)
+        for name, c, co in self.blocks:
+            s3 = 1.0 / math.sqrt(c * 9)
+            y = conv2d(x, p(name + ".conv1.Conv.weight") * s3, 1, 1, p(name + ".conv1.Act.bias"), act=True)
+            w6 = _fold(p(name + ".conv2.Conv.weight") * s3, self.blur)                       # [co, c, 6, 6]
+            y = conv2d(y, w6, 2, 2, p(name + ".conv2.Act.bias"), act=True)
+            w4 = _fold(p(name + ".skip.Conv.weight") * (1.0 / math.sqrt(c)), self.blur)     # [co, c, 4, 4]
+            sk = conv2d(x, w4, 2, 1)
+            x = add_scale(y, sk, 1.0 / SQRT2)
+        c = x.shape[3]
+        x = conv2d(x, p("final_conv.Conv.weight") * (1.0 / math.sqrt(c * 9)), 1, 1, p("final_conv.Act.bias"), act=True)
+        n, h, wd, c = x.shape
+        # the reference flattens NCHW (`out.view(batch, -1)`): permute the first linear's columns to NHWC order instead
+        w0 = p("final_linear.0.weight").view(-1, c, h, wd).permute(0, 2, 3, 1).reshape(-1, h * wd * c)
+        from .stylegan2_op import fused_leaky_relu
+        hdn = linear(x.reshape(n, -1), w0 * (1.0 / math.sqrt(w0.shape[1])))
+        hdn = fused_leaky_relu(hdn, p("final_linear.0.bias"))
+        w1 = p("final_linear.1.weight")
+        return linear(hdn, w1 * (1.0 / math.sqrt(w1.shape[1]))) + p("final_linear.1.bias")
+
+
+# ------------------------------------------------------------------------------------------------ losses / step
+def gan_loss(pred, real):
+    """models/networks/loss.py:11-18 (least squares)."""
+    return torch.mean((pred - 1) ** 2) if real else torch.mean(pred ** 2)
+
+
+def d_losses(D, real, fake, lambda_gan=1.0):
+    """compute_image_discriminator_losses, stage 1 (models/ppst_model.py:68-92): D_real + 0.5 * D_rec."""
+    return {"D_real": gan_loss(D(real), True) * lambda_gan, "D_rec": gan_loss(D(fake), False) * (0.5 * lambda_gan)}
+
+
+def r1_loss(D, real, lambda_r1=10.0):
+    """compute_R1_loss (models/ppst_model.py:139-156): 0.5 * lambda * |d D(real) / d real|^2 per sample."""
+    real = real.detach().requires_grad_(True)
+    pred = D(real).sum()
+    grad_real, = torch.autograd.grad(outputs=pred, inputs=[real], create_graph=True, retain_graph=True)
+    return grad_real.pow(2).sum(dim=(1, 2, 3)) * (lambda_r1 * 0.5)
+
+
+def allreduce_grads_(params, world):
+    """DDP's job for this step (models/__init__.py:88): ONE flat bucket, ONE NCCL all-reduce over NVLink,
+    averaged.  No-op for world == 1."""
+    import torch.distributed as dist
+    if world <= 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * 4

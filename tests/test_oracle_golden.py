@@ -230,3 +230,44 @@ def test_guided_oracle_properties():
     out = G.guided_filter_u8(guide, guide, 9, np.float32(1e-3))
     assert np.abs(out.astype(int) - guide.astype(int)).max() <= 1
     assert G.quantize_u8(np.array([-1.0, 0.0, 0.999, 1.0, 1.5])).tolist() == [0, 127, 254, 255, 255]
+
+
+# ---------------------------------------------------------------------------------------------- discriminator (8(f)4)
+D_KEYS = ["convs.0.Conv.weight", "convs.0.Act.bias", "convs.1.conv1.Conv.weight", "convs.1.conv2.Conv.weight",
+          "convs.1.conv2.Act.bias", "convs.1.skip.Conv.weight", "convs.3.conv1.Conv.weight", "convs.6.conv2.Conv.weight",
+          "final_conv.Conv.weight",
+          "final_linear.0.weight", "final_linear.0.bias", "final_linear.1.weight"]
+
+
+def _d_state(requires_grad=True):
+    sd = O.make_discriminator(256, seed=0)
+    return {k: (v.clone().requires_grad_(True) if (requires_grad and "Blur" not in k) else v) for k, v in sd.items()}
+
+
+def test_discriminator_forward_losses_and_gradients(golden):
+    """oracle.discriminator / d_losses / r1_loss against the reference Discriminator run by oracle/gen_golden.py:
+    output, both loss values, parameter gradients of the D step, and the double-backward gradients of the R1 penalty."""
+    g = golden("discriminator")
+    real, fake = T(g["real"]), T(g["fake"])
+    sd = _d_state()
+    pred = O.discriminator(sd, real)
+    assert np.abs(pred.detach().numpy() - g["pred_real"]).max() <= 1e-5
+    losses = O.d_losses(sd, real, fake)
+    assert abs(losses["D_real"].item() - float(g["D_real"])) <= 1e-5
+    assert abs(losses["D_rec"].item() - float(g["D_rec"])) <= 1e-6
+    (losses["D_real"] + losses["D_rec"]).backward()
+    for k in D_KEYS:
+        grad = sd["stylegan2_D." + k].grad
+        scale = float(g["dstep_grad/%s/stats" % k][2])
+        check_summary(g, "dstep_grad/" + k, grad, atol=2e-4 * scale + 1e-9)
+    sd = _d_state()
+    pen = O.r1_loss(sd, real)
+    assert np.abs(pen.detach().numpy() - g["r1/penalty"]).max() <= 1e-4 * np.abs(g["r1/penalty"]).max()
+    pen.mean().backward()
+    for k in D_KEYS:
+        grad = sd["stylegan2_D." + k].grad
+        if grad is None:                          # biases: the penalty does not depend on them (a.e.)
+            assert float(g["r1_grad/%s/stats" % k][2]) == 0.0, k
+            continue
+        scale = float(g["r1_grad/%s/stats" % k][2])
+        check_summary(g, "r1_grad/" + k, grad, atol=1e-3 * scale + 1e-12)
