@@ -246,6 +246,19 @@ PPST_API int64_t ppst_conv_wgrad_workspace_bytes(const ppst_wgrad_desc* d);
 PPST_API int ppst_conv_wgrad(float* dw, const void* x, const void* dy, const ppst_wgrad_desc* d, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* Per-step weight preparation of the training path (the parameters stay f32 [co, ci, kh, kw], the reference's
+ * state_dict layout).
+ * ppst_fold_fir: Blur + EqualConv2d of a downsampling ConvLayer (stylegan2_layers.py:142-164,497-555) as ONE
+ *   convolution: out [m][kh+fh-1][kw+fw-1] = stencil product of w [m][kh][kw] (m = co*ci) and the FIR kernel k [fh][fw]
+ *   (device memory); adjoint = 1: gradient of the folded weight (w, folded size) -> gradient of the original (out [m][kh][kw]).
+ * ppst_pack_conv_weights: out bf16 [groups][rows][slots*cols] = scale * w[..][tap slot_src[g*slots + s]] (-1: zero);
+ *   transpose = 0: rows = co, cols = ci (forward packing); 1: rows = ci, cols = co (input-gradient packings).
+ *   slot_src is HOST memory (at most 256 entries). */
+PPST_API int ppst_fold_fir(float* out, const float* w, const float* k, int64_t m, int kh, int kw, int fh, int fw, int adjoint,
+                  void* stream);
+PPST_API int ppst_pack_conv_weights(void* out, const float* w, int co, int ci, int kh, int kw, int groups, int slots,
+                           const int* slot_src, int transpose, float scale, void* stream);
+
 /* 1 if this build/device can run ppst_conv_tc (sm_100 family + driver entry point for tensor maps) */
 PPST_API int ppst_conv_tc_available(void);
 

@@ -63,6 +63,9 @@ _SIGS = {
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),
     "ppst_conv_tc": (c_int, [c_void_p] * 6 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_available": (c_int, []),
+    "ppst_fold_fir": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_pack_conv_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       ctypes.POINTER(ctypes.c_int), c_int, c_float, c_void_p]),
     "ppst_conv_wgrad_workspace_bytes": (c_i64, [ctypes.POINTER(WgradDesc)]),
     "ppst_conv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.POINTER(WgradDesc), c_void_p, c_i64, c_void_p]),
     "ppst_scale_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),

@@ -68,3 +68,27 @@ def swap_sharded(model, contents, styles, alpha=1.0):
         return lo, hi, None
     out = model.swap(contents[lo:hi], styles[lo:hi], alpha=alpha)
     return lo, hi, out
+
+
+def allreduce_grads_(params, world=None):
+    """The gradient exchange of the training-step config (the reference wraps the model in
+    torch.nn.parallel.DistributedDataParallel, models/__init__.py:88): every rank holds the gradients of its own batch
+    shard; ONE flat f32 bucket, ONE all-reduce (NCCL over NVLink on the GPU box, gloo in the CPU tests), divided by the
+    world size, scattered back into the .grad tensors in place.  Parameters without a gradient are skipped (the same
+    set on every rank, or the buckets would not line up).  Returns the bucket size in bytes (0 for a single process)."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    if world <= 1 or not dist.is_initialized():
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    dist.all_reduce(flat)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * 4

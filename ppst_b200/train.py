@@ -22,7 +22,7 @@ import math
 import torch
 from torch.autograd import Function
 
-from . import _lib, ops, packing
+from . import _lib, ops
 from ._lib import BF16, F32, WgradDesc, check, dt, ptr, require_cuda, stream
 
 SQRT2 = math.sqrt(2.0)
@@ -48,13 +48,33 @@ def _nhwc(t):
     return t.contiguous()
 
 
+_slot_cache = {}
+
+
+def _pack(w, slots_key, groups, slots, src, transpose):
+    """f32 [co,ci,k,k] -> bf16 [groups][rows][slots*cols] in one launch (ppst_pack_conv_weights)."""
+    co, ci, kh, kw = w.shape
+    tab = _slot_cache.get(slots_key)
+    if tab is None:
+        tab = (ctypes.c_int * len(src))(*src)
+        _slot_cache[slots_key] = tab
+    rows, cols = (ci, co) if transpose else (co, ci)
+    w32 = w.detach()
+    if w32.dtype != torch.float32 or not w32.is_contiguous():
+        w32 = w32.to(torch.float32).contiguous()
+    out = torch.empty((groups, rows, slots * cols), device=w.device, dtype=torch.bfloat16)
+    check(_lib.load().ppst_pack_conv_weights(ptr(out), ptr(w32), co, ci, kh, kw, groups, slots, tab, 1 if transpose else 0,
+                                             1.0, stream()))
+    return out
+
+
 def _conv_raw(x, w, g, bias=None, act=False):
     """x NHWC bf16 [n,h,w,ci], w f32 [co,ci,k,k] -> NHWC bf16 [n,oh,ow,co]; optional fused bias + leaky-ReLU(0.2)*sqrt2."""
     n, h, wd, ci = x.shape
     co = w.shape[0]
     assert w.shape[1] == ci and w.shape[2] == g.k and w.shape[3] == g.k, (tuple(w.shape), tuple(x.shape))
     oh, ow = g.out_hw(h, wd)
-    wp = packing.pack_taps(w.detach().to(torch.float32)).to(torch.bfloat16).unsqueeze(0).contiguous()
+    wp = _pack(w, ("fwd", g.k), 1, g.k * g.k, list(range(g.k * g.k)), False)
     out = torch.empty((n, oh, ow, co), device=x.device, dtype=torch.bfloat16)
     d = ops.conv_desc(x.shape, co, g.k, g.k, stride=g.stride, off=(-g.pad, -g.pad), out_hw=(oh, ow), act=act,
                       slope=0.2, gain=SQRT2 if act else 1.0, in_dtype=BF16, out_dtype=BF16)
@@ -65,7 +85,7 @@ def _conv_raw(x, w, g, bias=None, act=False):
 
 def _phase_taps(k, pad, r):
     """Stride-2 input gradient, one axis: input index 2a + r receives dy[a - u] * w[2u + r + pad] for the u with a valid
-    tap.  Returns (u_hi, [tap index or -1 for j = 0.. : u = u_hi - j])."""
+    tap.  Returns (u_hi, u_lo)."""
     us = [u for u in range(-k, k + 1) if 0 <= 2 * u + r + pad < k]
     return (max(us), min(us)) if us else (0, 1)
 
@@ -75,10 +95,11 @@ def _dgrad_raw(gy, w, g, in_hw):
     n, oh, ow, co = gy.shape
     ci, k = w.shape[1], g.k
     assert w.shape[0] == co
-    w32 = w.detach().to(torch.float32)
     out = torch.empty((n, in_hw[0], in_hw[1], ci), device=gy.device, dtype=torch.bfloat16)
     if g.stride == 1:
-        wp = torch.flip(w32, [2, 3]).permute(1, 2, 3, 0).reshape(ci, k * k * co).to(torch.bfloat16).unsqueeze(0).contiguous()
+        # rotated by 180 degrees and transposed: slot (ty', tx') reads tap (k-1-ty', k-1-tx'), rows = ci
+        src = [(k - 1 - ty) * k + (k - 1 - tx) for ty in range(k) for tx in range(k)]
+        wp = _pack(w, ("dgrad1", k), 1, k * k, src, True)
         off = -(k - 1) + g.pad
         d = ops.conv_desc(gy.shape, ci, k, k, stride=1, off=(off, off), out_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
         ops.conv_tc(out, gy, wp, None, None, None, d)
@@ -87,18 +108,15 @@ def _dgrad_raw(gy, w, g, in_hw):
     (hi0, lo0), (hi1, lo1) = _phase_taps(k, g.pad, 0), _phase_taps(k, g.pad, 1)
     J = max(hi0 - lo0, hi1 - lo1) + 1
     his = (hi0, hi1)
-    wph = w32.new_zeros(2, 2, ci, J, J, co)
+    src = []
     for ry in range(2):
         for rx in range(2):
             for jy in range(J):
                 ty = 2 * (his[ry] - jy) + ry + g.pad
-                if not 0 <= ty < k:
-                    continue
                 for jx in range(J):
                     tx = 2 * (his[rx] - jx) + rx + g.pad
-                    if 0 <= tx < k:
-                        wph[ry, rx, :, jy, jx, :] = w32[:, :, ty, tx].t()
-    wp = wph.reshape(4, ci, J * J * co).to(torch.bfloat16).contiguous()
+                    src.append(ty * k + tx if (0 <= ty < k and 0 <= tx < k) else -1)
+    wp = _pack(w, ("dgrad2", k, g.pad), 4, J * J, src, True)
     d = ops.conv_desc(gy.shape, ci, J, J, stride=1, off=(-hi0, -hi0), out_hw=(in_hw[0] // 2, in_hw[1] // 2), phases=(2, 2),
                       phase_off=(hi0 - hi1, hi0 - hi1), full_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
     ops.conv_tc(out, gy, wp, None, None, None, d)
@@ -395,10 +413,32 @@ def linear(x, w):
 
 
 # ------------------------------------------------------------------------------------------------ discriminator
+class _Fold(Function):
+    """Stencil product of a conv weight with the blur kernel (ppst_fold_fir) -- linear in w, so the backward is the
+    adjoint map and the backward of the adjoint is the map itself."""
+
+    @staticmethod
+    def forward(ctx, w, k, adjoint, kh, kw):
+        w = w.to(torch.float32).contiguous()
+        co, ci = w.shape[:2]
+        fh, fw = k.shape
+        ctx.save_for_backward(k)
+        ctx.adjoint, ctx.khw = adjoint, (kh, kw)
+        out = torch.empty((co, ci, kh, kw) if adjoint else (co, ci, kh + fh - 1, kw + fw - 1), device=w.device,
+                          dtype=torch.float32)
+        check(_lib.load().ppst_fold_fir(ptr(out), ptr(w), ptr(k), co * ci, kh, kw, fh, fw, 1 if adjoint else 0, stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k, = ctx.saved_tensors
+        return _Fold.apply(g, k, not ctx.adjoint, ctx.khw[0], ctx.khw[1]), None, None, None, None
+
+
 def _fold(w, blur_k):
     """Blur (upfirdn2d, zero pad) followed by a stride-2 convolution == ONE stride-2 convolution with the stencil
-    product of the two kernels (packing.fold_fir, differentiable: F.conv_transpose2d on the small weight tensor)."""
-    return packing.fold_fir(w, blur_k)
+    product of the two kernels; [co,ci,kh,kw] -> [co,ci,kh+fh-1,kw+fw-1]."""
+    return _Fold.apply(w, blur_k, False, w.shape[2], w.shape[3])
 
 
 class Discriminator(torch.nn.Module):
@@ -501,7 +541,12 @@ def gan_loss(pred, real):
 
 def d_losses(D, real, fake, lambda_gan=1.0):
     """compute_image_discriminator_losses, stage 1 (models/ppst_model.py:68-92): D_real + 0.5 * D_rec."""
-    return {"D_real": gan_loss(D(real), True) * lambda_gan, "D_rec": gan_loss(D(fake), False) * (0.5 * lambda_gan)}
+    # D has no cross-sample statistics (the minibatch-stddev layer is commented out upstream, stylegan2_layers.py:630-637):
+    # one pass over [real; fake] gives the same per-sample predictions as the reference's two passes and prepares the
+    # weights once
+    pred = D(torch.cat([real, fake], dim=0))
+    nr = real.shape[0]
+    return {"D_real": gan_loss(pred[:nr], True) * lambda_gan, "D_rec": gan_loss(pred[nr:], False) * (0.5 * lambda_gan)}
 
 
 def r1_loss(D, real, lambda_r1=10.0):
@@ -512,19 +557,7 @@ def r1_loss(D, real, lambda_r1=10.0):
     return grad_real.pow(2).sum(dim=(1, 2, 3)) * (lambda_r1 * 0.5)
 
 
-def allreduce_grads_(params, world):
-    """DDP's job for this step (models/__init__.py:88): ONE flat bucket, ONE NCCL all-reduce over NVLink,
-    averaged.  No-op for world == 1."""
-    import torch.distributed as dist
-    if world <= 1:
-        return 0
-    grads = [p.grad for p in params if p.grad is not None]
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
-    return flat.numel() * 4
+def allreduce_grads_(params, world=None):
+    """See sharding.allreduce_grads_ (one flat bucket, one all-reduce, averaged)."""
+    from .sharding import allreduce_grads_ as f
+    return f(params, world)

@@ -78,3 +78,38 @@ def test_two_rank_gloo_plumbing():
         assert [(lo, hi) for lo, hi, _ in rows] == [(0, 3), (3, 6)]
         merged = [v for _, _, vals in rows for v in vals]
         assert merged == [2 * i + 1 for i in range(6)]          # identical to the single-process result
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    sharding.init(backend="gloo")
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((5, 3), float(rank + 1))
+    params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+    # params[2] has no gradient on any rank: skipped
+    nbytes = sharding.allreduce_grads_(params)
+    dist.destroy_process_group()
+    q.put((rank, nbytes, params[0].grad.flatten().tolist(), params[1].grad.tolist(), params[2].grad))
+
+
+def test_two_rank_gradient_allreduce_is_one_averaged_flat_bucket():
+    """Training-step config: gradients averaged over ranks through one flat bucket."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, nbytes, g0, g1, g2 in results:
+        assert nbytes == (15 + 7) * 4
+        assert g0 == [1.5] * 15                                               # mean of 1 and 2
+        assert g1 == [1.5 * i for i in range(7)]
+        assert g2 is None
+    assert sharding.allreduce_grads_([torch.nn.Parameter(torch.zeros(1))]) == 0   # single process: no-op
