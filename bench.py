@@ -10,8 +10,9 @@ One step = one pass of the whole swap path over one batch of synthetic pairs:
   E1(c) E2(c) G.extract(c)  E1(s) E2(s) G.extract(s)  Rselfcorr x2  corrm  E2(s, corr)  G.decode   (2.143 TFLOP / image,
   SURVEY.md 8(d)).  No collective on the data path; torch.distributed is used for barriers and the max-over-ranks time.
 
-One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = through SwapModel.swap() with pinned HOST
-buffers, H2D of both image batches and D2H of the result inside the timed region.
+One JSON line on stdout (rank 0).  `value` = device-resident inputs; `e2e` = through SwapModel.swap_pipelined() with
+pinned HOST buffers, H2D of both image batches and D2H of the result of every step inside the timed region (the copies run
+on their own streams and overlap the neighbouring steps' kernels).
 """
 import argparse
 import json
@@ -207,19 +208,24 @@ def main():
     def step_eager():
         return model.swap(c_dev, s_dev)
 
+    last = [None]
+
     def step_e2e():
-        out = model.swap_graph(c_pin, s_pin)          # H2D of both batches into the graph's static inputs
-        out_pin.copy_(out, non_blocking=True)         # D2H of the step's result
-        return out
+        # H2D of both batches (copy stream, overlapping the previous step's kernels), graph replay, D2H of the result
+        # (third stream); every step moves its own 50 MB in and 25 MB out
+        last[0] = model.swap_pipelined(c_pin, s_pin, out_pin)
 
     def timed(fn, steps):
         sharding.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
+        last[0] = None
         e0.record()
         for _ in range(steps):
             fn()
+        if last[0] is not None:
+            torch.cuda.current_stream().wait_event(last[0])      # the last result has reached the host buffer
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()

@@ -29,6 +29,7 @@ class SwapModel:
         self.device = self.engine.device
         self._noises = None
         self._graphs = {}
+        self._pipes = {}
 
     @property
     def noises(self):
@@ -41,6 +42,7 @@ class SwapModel:
         self._noises = None if value is None else {
             k: v.to(self.device, torch.float32).contiguous() for k, v in value.items()}
         self._graphs.clear()
+        self._pipes.clear()
 
     def _noises_for(self, rows):
         """The noise dict for a pass over `rows` samples: the user's [B,...] maps repeated when the content and style
@@ -260,3 +262,50 @@ class SwapModel:
         s_static.copy_(style, non_blocking=True)
         graph.replay()
         return out_static
+
+    def swap_pipelined(self, content, style, out, alpha=1.0):
+        """Streaming form of swap_graph for HOST-resident batches (pinned `content`, `style`, `out`): the host-to-device
+        copy of this call's inputs runs on a copy stream into one of two staging buffers while the previous call's graph is
+        still executing, and the result leaves on a third stream, so PCIe time hides behind the step instead of adding to
+        it.  Every call still moves its own inputs and its own result.  Returns the CUDA event that marks `out` complete
+        (also make the launching stream wait for it before timing or reusing `out`)."""
+        dev = self.device
+        key = (tuple(content.shape), tuple(style.shape), float(alpha))
+        if key not in self._graphs:
+            self.swap_graph(content, style, alpha)                     # capture (and one un-pipelined step)
+        graph, c_static, s_static, out_static = self._graphs[key]
+        st = self._pipes
+        pp = st.get(key)
+        if pp is None:
+            pp = {"i": 0, "in": torch.cuda.Stream(device=dev), "out": torch.cuda.Stream(device=dev),
+                  "c": [torch.empty_like(c_static) for _ in range(2)], "s": [torch.empty_like(s_static) for _ in range(2)],
+                  "o": [torch.empty_like(out_static) for _ in range(2)],
+                  "h2d": [torch.cuda.Event() for _ in range(2)], "used": [torch.cuda.Event() for _ in range(2)],
+                  "ready": [torch.cuda.Event() for _ in range(2)], "d2h": [torch.cuda.Event() for _ in range(2)]}
+            st[key] = pp
+        i = pp["i"]
+        b = i & 1
+        pp["i"] = i + 1
+        main = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(pp["in"]):
+            if i >= 2:
+                pp["in"].wait_event(pp["used"][b])                     # staging buffer b was consumed by call i-2
+            else:
+                pp["in"].wait_stream(main)
+            pp["c"][b].copy_(content, non_blocking=True)
+            pp["s"][b].copy_(style, non_blocking=True)
+            pp["h2d"][b].record(pp["in"])
+        main.wait_event(pp["h2d"][b])
+        c_static.copy_(pp["c"][b], non_blocking=True)
+        s_static.copy_(pp["s"][b], non_blocking=True)
+        pp["used"][b].record(main)
+        graph.replay()
+        if i >= 2:
+            main.wait_event(pp["d2h"][b])                              # result buffer b has left for the host
+        pp["o"][b].copy_(out_static, non_blocking=True)
+        pp["ready"][b].record(main)
+        with torch.cuda.stream(pp["out"]):
+            pp["out"].wait_event(pp["ready"][b])
+            out.copy_(pp["o"][b], non_blocking=True)
+            pp["d2h"][b].record(pp["out"])
+        return pp["d2h"][b]

@@ -268,6 +268,16 @@ def test_bf16_end_to_end_swap(world, model_bf16):
     g1 = model_bf16.swap_graph(world["c"].pin_memory(), world["s"].pin_memory()).clone()
     g2 = model_bf16.swap_graph(world["c"].cuda(), world["s"].cuda()).clone()
     assert torch.equal(g1, out) and torch.equal(g2, out)
+    # the streaming form (host buffers in and out, copies on their own streams): alternate two different batches through
+    # the double-buffered pipeline; every result must be the bits of the plain swap of ITS inputs
+    ca, sa = world["c"].pin_memory(), world["s"].pin_memory()
+    cb, sb = world["s"].pin_memory(), world["c"].pin_memory()
+    ref_b = model_bf16.swap(world["s"], world["c"]).cpu()
+    outs = [torch.empty(out.shape, dtype=torch.float32).pin_memory() for _ in range(5)]
+    evs = [model_bf16.swap_pipelined(*((ca, sa) if i % 2 == 0 else (cb, sb)), outs[i]) for i in range(5)]
+    for i, ev in enumerate(evs):
+        ev.synchronize()
+        assert torch.equal(outs[i], out.cpu() if i % 2 == 0 else ref_b), i
 
 
 def test_batch_rows_are_independent(world, model_bf16):
