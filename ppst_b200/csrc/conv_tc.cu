@@ -784,6 +784,162 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+// =====================================================================================================================
+// Weight-gradient kernel with MN-major operands (wgrad.cu, path 2): dw[co][tap][ci] = sum_pixels dy[pix][co] * x[pix + tap][ci].
+// The contraction runs over pixels, and NHWC tensors are pixel-major with the channels contiguous -- exactly the
+// "MN-major" operand form of tcgen05.mma (instruction-descriptor bits 15 / 16): a TMA box {64 channels, 8 x 8 pixels} lands
+// in shared memory as 64 rows (K = pixels) of 128 bytes (64 channels of M or N) in the 128-byte swizzle, which is the
+// canonical MN-major SWIZZLE_128B layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) with SBO = 1024 bytes between 8-pixel groups
+// and LBO = one box (8192 bytes) between 64-channel blocks.  No transposition pass, no padded copies: a filter tap is a
+// coordinate offset of the x box (stride 2 = TMA element strides), zero padding is TMA out-of-bounds fill.
+// Work item = (tap, ci tile, co tile, sample, pixel chunk); taps fastest so the CTAs sharing a dy chunk run together.
+struct WgParams {
+  int n, out_h, out_w, cout, cin, kh, kw, stride, off_y, off_x;
+  int tiles_x, patches, chunk, k_split;      // 8x8 patches per row / per sample; patches per chunk; chunks per sample
+  int m_tiles, n_tiles, num_tiles, stages;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_mn_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                     float* __restrict__ partials, const WgParams p) {
+  constexpr int kBox = 64 * 64 * 2;                 // one {64 ch, 8, 8} box
+  constexpr int kABytes = 2 * kBox, kBBytes = (BN / 64) * kBox, kStage = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * kStage);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int taps = p.kh * p.kw;
+
+  auto decode = [&](int tile, int& tap, int& nt, int& mt, int& j) {
+    tap = tile % taps; tile /= taps;
+    nt = tile % p.n_tiles; tile /= p.n_tiles;
+    mt = tile % p.m_tiles; j = tile / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int tap, nt, mt, j;
+        decode(tile, tap, nt, mt, j);
+        const int img = j / p.k_split, ch = j - img * p.k_split;
+        const int ty_t = tap / p.kw, tx_t = tap - ty_t * p.kw;
+        const int p0 = ch * p.chunk, p1 = min(p0 + p.chunk, p.patches);
+        int py = p0 / p.tiles_x, px = p0 - py * p.tiles_x;
+        for (int pp = p0; pp < p1; ++pp) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStage;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)kStage);
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            tma_load_4d(sa + b * kBox, &map_dy, &full_bar[stage], mt * 128 + b * 64, px * 8, py * 8, img);
+          const int ix = px * 8 * p.stride + tx_t + p.off_x, iy = py * 8 * p.stride + ty_t + p.off_y;
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_4d(sa + kABytes + b * kBox, &map_x, &full_bar[stage], nt * BN + b * 64, ix, iy, img);
+          if (++px == p.tiles_x) { px = 0; ++py; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // kind::f16, D = f32, A = B = bf16, BOTH MN-major (bits 15, 16), N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      auto desc = [](uint32_t saddr) {
+        uint64_t d = 0;
+        d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+        d |= (uint64_t)(kBox >> 4) << 16;              // LBO: next 64-channel block
+        d |= (uint64_t)(1024 >> 4) << 32;              // SBO: next group of 8 pixels
+        d |= (uint64_t)1 << 46;
+        d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+        return d;
+      };
+      int stage = 0, it = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        int tap, nt, mt, j;
+        decode(tile, tap, nt, mt, j);
+        const int ch = j % p.k_split;
+        const int p0 = ch * p.chunk, p1 = min(p0 + p.chunk, p.patches);
+        const int as = it & 1;
+        mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int pp = p0; pp < p1; ++pp) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStage);
+          const uint64_t da = desc(sa), db = desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                 // 16 pixels = 2048 bytes per MMA
+            umma_bf16(tmem_d, da + (uint64_t)(k * (2048 >> 4)), db + (uint64_t)(k * (2048 >> 4)), idesc,
+                      (pp > p0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // epilogue: warps 2..5, TMEM lane quadrant = warp % 4; lane = output channel row of the 128-row tile
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      int tap, nt, mt, j;
+      decode(tile, tap, nt, mt, j);
+      const int as = it & 1;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      const int co = mt * 128 + q * 32 + lane;
+      float* dst = partials + (((int64_t)j * taps + tap) * p.cout + co) * p.cin + nt * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (co < p.cout) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            if (nt * BN + c0 + 4 * v < p.cin)
+              *reinterpret_cast<float4*>(dst + c0 + 4 * v) =
+                  make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                              __uint_as_float(r[4 * v + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1070,6 +1226,65 @@ int tc_wgrad_gemm(float* partials, const void* dyt, const void* xt, int samples,
   if (ci % 128 == 0) return tc::launch<128, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
   if (ci % 64 == 0) return tc::launch<64, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
   return tc::launch<32, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
+}
+
+// MN-major weight-gradient launch (wgrad.cu): partials f32 [n * k_split][taps][cout][cin].
+int tc_wgrad_mn(float* partials, const void* dy, const void* x, const ppst_wgrad_desc& d, int k_split, cudaStream_t st) {
+  tc::WgParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin; p.kh = d.kh; p.kw = d.kw;
+  p.stride = d.stride; p.off_y = d.off_y; p.off_x = d.off_x;
+  p.tiles_x = ceil_div(d.out_w, 8);
+  p.patches = p.tiles_x * ceil_div(d.out_h, 8);
+  p.chunk = ceil_div(p.patches, k_split);
+  PPST_REQUIRE(ceil_div(p.patches, p.chunk) == k_split, PPST_ERR_ARG, "conv_wgrad: a pixel chunk would be empty");
+  p.k_split = k_split;
+  p.m_tiles = ceil_div(d.cout, 128);
+  const int bn = d.cin > 128 ? 256 : d.cin > 64 ? 128 : 64;
+  p.n_tiles = ceil_div(d.cin, bn);
+  const int64_t tiles = (int64_t)d.n * k_split * p.m_tiles * p.n_tiles * d.kh * d.kw;
+  PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_wgrad: too many tiles");
+  p.num_tiles = (int)tiles;
+  const int stage_bytes = (2 + bn / 64) * 8192;
+  p.stages = (232448 - 1024 - 2048) / stage_bytes;
+  if (p.stages > tc::kMaxStages) p.stages = tc::kMaxStages;
+  const int smem_total = p.stages * stage_bytes + (2 * tc::kMaxStages + 4) * 8 + 16 + 1024;
+  CUtensorMap map_dy, map_x;
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cout, (uint64_t)d.out_w, (uint64_t)d.out_h, (uint64_t)d.n};
+    const uint64_t strides[3] = {(uint64_t)d.cout * 2, (uint64_t)d.out_w * d.cout * 2, (uint64_t)d.out_h * d.out_w * d.cout * 2};
+    const uint32_t box[4] = {64, 8, 8, 1};
+    const uint32_t est[4] = {1, 1, 1, 1};
+    int rc = tc::encode_map(&map_dy, dy, 4, dims, strides, box, est, 64);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)d.n};
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, (uint64_t)d.in_w * d.cin * 2, (uint64_t)d.in_h * d.in_w * d.cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)(8 * d.stride), (uint32_t)(8 * d.stride), 1};
+    const uint32_t est[4] = {1, (uint32_t)d.stride, (uint32_t)d.stride, 1};
+    int rc = tc::encode_map(&map_x, x, 4, dims, strides, box, est, 64);
+    if (rc) return rc;
+  }
+  const int grid = p.num_tiles < tc::num_sms() ? p.num_tiles : tc::num_sms();
+#define PPST_WG(BN_)                                                                                              \
+  do {                                                                                                            \
+    auto kern = tc::conv_wgrad_mn_kernel<BN_>;                                                                    \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024), \
+                          "cudaFuncSetAttribute(conv_wgrad_mn)");                                                 \
+      if (rc) return rc;                                                                                          \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    kern<<<grid, 192, smem_total, st>>>(map_dy, map_x, partials, p);                                              \
+  } while (0)
+  if (bn == 256) PPST_WG(256);
+  else if (bn == 128) PPST_WG(128);
+  else PPST_WG(64);
+#undef PPST_WG
+  PPST_LAUNCH_CHECK("conv_wgrad_mn_kernel");
+  return 0;
 }
 }  // namespace ppst
 

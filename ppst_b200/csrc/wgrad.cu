@@ -17,6 +17,7 @@
 //      CTAs that stream the same K range run side by side and share it through L2 (operands leave HBM once).
 //   3. reduce_kernel: fixed-order sum of the partials over (sample, chunk) into the packed weight layout [co][tap][ci].
 #include <cstring>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -24,6 +25,7 @@ namespace ppst {
 
 int tc_wgrad_gemm(float* partials, const void* dyt, const void* xt, int samples, int k_split, int kc, int m, int ci,
                   int xt_rows, int n_taps, const int* k_off, const int* row_off, cudaStream_t st);
+int tc_wgrad_mn(float* partials, const void* dy, const void* x, const ppst_wgrad_desc& d, int k_split, cudaStream_t st);
 
 namespace {
 
@@ -102,6 +104,43 @@ __global__ void __launch_bounds__(256) reduce_kernel(float* __restrict__ dw, con
   *reinterpret_cast<float4*>(dw + ((int64_t)(hi * 16 + lo) * taps_total + tap0 + t) * ci + c) = acc;
 }
 
+// path 2 (MN-major operands straight from NHWC): dw[co][tap][ci] = sum_j partials[j][tap][co][ci]
+__global__ void __launch_bounds__(256) reduce_mn_kernel(float* __restrict__ dw, const float* __restrict__ partials, int J,
+                                                        int co, int taps, int ci) {
+  const int64_t per_j = (int64_t)taps * co * ci;
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (e >= per_j) return;
+  const int c = (int)(e % ci);
+  int64_t r = e / ci;
+  const int o = (int)(r % co);
+  const int t = (int)(r / co);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < J; ++j) {
+    const float4 v = *reinterpret_cast<const float4*>(partials + (int64_t)j * per_j + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dw + ((int64_t)o * taps + t) * ci + c) = acc;
+}
+
+// pixel chunks per sample for path 2: about two waves of work items, at least 16 patches (1024 pixels) per chunk, no
+// empty chunk
+int mn_k_split(const ppst_wgrad_desc& d) {
+  const int patches = ceil_div(d.out_w, 8) * ceil_div(d.out_h, 8);
+  const int bn = d.cin > 128 ? 256 : d.cin > 64 ? 128 : 64;
+  const int64_t tiles = (int64_t)ceil_div(d.cout, 128) * ceil_div(d.cin, bn) * d.kh * d.kw;
+  int64_t ks = (2 * 148 + d.n * tiles - 1) / (d.n * tiles);
+  const int64_t ks_max = patches / 16 > 0 ? patches / 16 : 1;
+  if (ks > ks_max) ks = ks_max;
+  if (ks < 1) ks = 1;
+  const int chunk = ceil_div(patches, ks);
+  return ceil_div(patches, chunk);
+}
+
+bool use_mn_path() {
+  static const int v = [] { const char* e = getenv("PPST_WGRAD_PATH"); return (e && e[0] == 'p') ? 0 : 1; }();
+  return v != 0;
+}
+
 struct Plan {
   int s, planes, wp, k_split, kc, taps, groups, taps_per_group, ncopies, dx0;
   int64_t kpad, xt_elems, dyt_elems, partial_elems, bytes;
@@ -145,6 +184,7 @@ int make_plan(const ppst_wgrad_desc& d, Plan& pl) {
   pl.dyt_elems = (int64_t)d.n * d.cout * pl.kpad;
   pl.partial_elems = (int64_t)d.n * ks * d.cout * pl.taps_per_group * d.cin;
   pl.bytes = (pl.xt_elems + pl.dyt_elems) * 2 + pl.partial_elems * 4 + 512;
+  if (use_mn_path()) pl.bytes = (int64_t)d.n * mn_k_split(d) * pl.taps * d.cout * d.cin * 4 + 512;
   return 0;
 }
 
@@ -172,6 +212,16 @@ extern "C" int ppst_conv_wgrad(float* dw, const void* x, const void* dy, const p
                PPST_ERR_ARG, "conv_wgrad: buffers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   uintptr_t w0 = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  if (use_mn_path()) {
+    float* part = reinterpret_cast<float*>(w0);
+    const int ks = mn_k_split(d);
+    rc = tc_wgrad_mn(part, dy, x, d, ks, st);
+    if (rc) return rc;
+    const int64_t threads = (int64_t)pl.taps * d.cout * d.cin / 4;
+    reduce_mn_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(dw, part, d.n * ks, d.cout, pl.taps, d.cin);
+    PPST_LAUNCH_CHECK("conv_wgrad reduce_mn_kernel");
+    return 0;
+  }
   __nv_bfloat16* xt = reinterpret_cast<__nv_bfloat16*>(w0);
   __nv_bfloat16* dyt = xt + pl.xt_elems;
   float* partials = reinterpret_cast<float*>(dyt + pl.dyt_elems);
