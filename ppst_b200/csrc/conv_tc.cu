@@ -58,12 +58,6 @@ struct Params {
   int tiles_ys;                         // super-tile rows per image = ceil(tiles_y / MT)
   int a_rows, a_slot_bytes;             // rows of one A box (MT*th + kh - 1) and its 1024-aligned slot size
   int na, nb, bps;                      // A slots, B slots, taps per B slot (1 or kh)
-  // weight-gradient GEMM (plain kernel only, see wgrad.cu): "image" j = (sample j / k_split, K chunk j % k_split) of
-  // operands whose K extent is k_split * cin; phase ph = one filter tap, which reads the B operand k_off[ph] elements
-  // further along K and row_off[ph] rows further down (the parity plane of a strided convolution)
-  int k_split;                          // 0 / 1: off
-  int wg;                               // 1: per-phase B offsets below replace the per-phase weight rows
-  int ph_k_off[16], ph_row_off[16];
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -371,13 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int py = ph / p.phases_x, px = ph % p.phases_x;
         const int iy0 = ty * p.th * p.stride + p.off_y + py * p.phase_off_dy;
         const int ix0 = tx * p.tw * p.stride + p.off_x + px * p.phase_off_dx;
-        int a_img = img, k_base = 0;
-        if (p.k_split > 1) {
-          a_img = img / p.k_split;
-          k_base = (img - a_img * p.k_split) * p.cin;
-        }
-        const int brow = a_img * p.w_img_rows + (p.wg ? p.ph_row_off[ph] : ph * p.cout) + nt * BN;
-        const int b_k_off = p.wg ? p.ph_k_off[ph] : 0;
+        const int brow = img * p.w_img_rows + ph * p.cout + nt * BN;
         int tap = 0, cb = 0, ky = 0, kx = 0;                 // incremental (tap, channel block) decode: no div/mod
         for (int kb0 = 0; kb0 < kblocks; kb0 += p.kps) {
           const int nk = min(p.kps, kblocks - kb0);
@@ -392,11 +380,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               ca = ((seg == 2 ? p.split_seg_kb : 0) + r) * BKC;        // A: hi, hi, lo
               cbk = ((seg == 1 ? p.split_seg_kb : 0) + r) * BKC;       // B: hi, lo, hi
             } else {
-              ca = cb * BKC + k_base;
-              cbk = tap * p.cin + ca + b_k_off;
+              ca = cb * BKC;
+              cbk = tap * p.cin + ca;
             }
             uint8_t* sa = sbase + j * S::kKblockBytes;
-            tma_load_4d(sa, &map_a, &full_bar[stage], ca, ix0 + kx, iy0 + ky, a_img);
+            tma_load_4d(sa, &map_a, &full_bar[stage], ca, ix0 + kx, iy0 + ky, img);
             tma_load_2d(sa + S::kABytes, &map_b, &full_bar[stage], cbk, brow);
             if (!p.split_seg_kb && ++cb == p.kblocks_per_tap) {
               cb = 0; ++tap;
@@ -785,7 +773,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 // =====================================================================================================================
-// Weight-gradient kernel with MN-major operands (wgrad.cu, path 2): dw[co][tap][ci] = sum_pixels dy[pix][co] * x[pix + tap][ci].
+// Weight-gradient kernel with MN-major operands (entry point in wgrad.cu): dw[co][tap][ci] = sum_pixels dy[pix][co] * x[pix + tap][ci].
 // The contraction runs over pixels, and NHWC tensors are pixel-major with the channels contiguous -- exactly the
 // "MN-major" operand form of tcgen05.mma (instruction-descriptor bits 15 / 16): a TMA box {64 channels, 8 x 8 pixels} lands
 // in shared memory as 64 rows (K = pixels) of 128 bytes (64 channels of M or N) in the 128-byte swizzle, which is the
@@ -1025,23 +1013,12 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// weight-gradient use of the plain kernel (wgrad.cu): d.n = samples * k_split "images", d.cin = one K chunk
-struct WgExtra {
-  int k_split, n_taps;
-  int k_off[16], row_off[16];
-};
-
 template <int BN, int BKC, bool OUT_F32>
 static int launch(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
-                  const float* noise, float* stats, cudaStream_t st, const WgExtra* wg = nullptr) {
+                  const float* noise, float* stats, cudaStream_t st) {
   using S = Smem<BN, BKC>;
   Params p;
   std::memset(&p, 0, sizeof(p));
-  const int ks = wg ? wg->k_split : 1;
-  if (wg) {
-    p.k_split = wg->k_split; p.wg = 1;
-    for (int i = 0; i < 16; ++i) { p.ph_k_off[i] = wg->k_off[i]; p.ph_row_off[i] = wg->row_off[i]; }
-  }
   p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
   p.kh = d.kh; p.kw = d.kw; p.stride = d.stride;
   p.off_y = d.off_y; p.off_x = d.off_x; p.phases_y = d.phases_y; p.phases_x = d.phases_x;
@@ -1076,19 +1053,18 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
 
   CUtensorMap map_a, map_b;
   {
-    const uint64_t kext = (uint64_t)d.cin * ks;              // wgrad: the chunks of one sample are contiguous along K
-    const uint64_t dims[4] = {kext, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)(d.n / ks)};
-    const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * kext;
-    const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * kext;
-    const uint64_t strides[3] = {kext * 2, rowp * 2, imgp * 2};
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)d.n};
+    const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
+    const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
     const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)(p.tw * d.stride), (uint32_t)(p.th * d.stride), 1};
     const uint32_t est[4] = {1, (uint32_t)d.stride, (uint32_t)d.stride, 1};
     int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
     if (rc) return rc;
   }
   {
-    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin * ks;
-    const uint64_t dims[2] = {K, d.w_img_rows ? (uint64_t)d.w_img_rows * (d.n / ks) : (uint64_t)d.cout * n_phases};
+    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
+    const uint64_t dims[2] = {K, d.w_img_rows ? (uint64_t)d.w_img_rows * d.n : (uint64_t)d.cout * n_phases};
     const uint64_t strides[1] = {K * 2};
     const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)BN};
     const uint32_t est[2] = {1, 1};
@@ -1201,32 +1177,6 @@ static int halo_mode(const ppst_conv_desc& d, int bn) {
 }
 
 }  // namespace tc
-
-// Weight-gradient GEMM on the plain kernel (called by ppst_conv_wgrad, wgrad.cu):
-//   partials[j][m / 16][tap][m % 16][ci] = sum_{k in chunk j % k_split} dyt[j / k_split][m][k] * xt[j / k_split][row_off[tap] + ci][k + k_off[tap]]
-// dyt: bf16 [samples][m][k_split * kc], xt: bf16 [samples][xt_rows][k_split * kc]; out-of-range k reads as 0 (TMA fill).
-int tc_wgrad_gemm(float* partials, const void* dyt, const void* xt, int samples, int k_split, int kc, int m, int ci,
-                  int xt_rows, int n_taps, const int* k_off, const int* row_off, cudaStream_t st) {
-  PPST_REQUIRE(m % 16 == 0 && ci % 32 == 0 && kc % 64 == 0 && n_taps >= 1 && n_taps <= 16 && k_split >= 1, PPST_ERR_ARG,
-               "conv_wgrad: gemm geometry (m=%d ci=%d kc=%d taps=%d)", m, ci, kc, n_taps);
-  ppst_conv_desc d;
-  std::memset(&d, 0, sizeof(d));
-  d.n = samples * k_split; d.in_h = m / 16; d.in_w = 16; d.cin = kc;
-  d.out_h = d.in_h; d.out_w = 16; d.cout = ci; d.kh = d.kw = 1; d.stride = 1;
-  d.phases_y = n_taps; d.phases_x = 1;
-  d.full_h = d.out_h * n_taps; d.full_w = 16; d.cout_stride = ci;
-  d.gain = 1.0f; d.slope = 1.0f;
-  d.in_dtype = PPST_BF16; d.out_dtype = PPST_F32;
-  d.w_img_rows = xt_rows;
-  tc::WgExtra wg;
-  std::memset(&wg, 0, sizeof(wg));
-  wg.k_split = k_split; wg.n_taps = n_taps;
-  for (int i = 0; i < n_taps; ++i) { wg.k_off[i] = k_off[i]; wg.row_off[i] = row_off[i]; }
-  if (ci % 256 == 0) return tc::launch<256, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
-  if (ci % 128 == 0) return tc::launch<128, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
-  if (ci % 64 == 0) return tc::launch<64, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
-  return tc::launch<32, 64, true>(d, partials, dyt, xt, nullptr, nullptr, nullptr, st, &wg);
-}
 
 // MN-major weight-gradient launch (wgrad.cu): partials f32 [n * k_split][taps][cout][cin].
 int tc_wgrad_mn(float* partials, const void* dy, const void* x, const ppst_wgrad_desc& d, int k_split, cudaStream_t st) {
