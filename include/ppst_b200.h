@@ -113,6 +113,16 @@ PPST_API int64_t ppst_upsample_reduce_scratch_elems(int64_t n, int lh, int c);
 PPST_API int ppst_upsample_reduce(float* sum, float* vmax, const float* x, int64_t n, int lh, int lw, int c_stride,
                          int c_off, int c, int scale, float* scratch, void* stream);
 
+/* Backward reductions of InstanceNorm (+ StyleMod) for the training path: per (sample, channel) sum_g = sum_p g and
+ * sum_gx = sum_p g*x over the h*w pixels of the NHWC tensors g (upstream gradient) and x (the layer input), f32 [n, c]
+ * each.  With the forward mean / rstd they give the whole gradient of y = (x - mean) * rstd * (1 + s) + b
+ * (nn.InstanceNorm2d + StyleMod, stylegan2_layers.py:361-374,414-437): dx = alpha*g + beta*x + gamma per (n, c) -- one
+ * ppst_affine_apply pass -- and the style gradients.  c: a multiple of 8 (bf16) / 4 (f32), at most 2048 / 1024.  Deterministic.
+ * scratch: f32 workspace of ppst_plane_dot_scratch_elems(n, c, hw) elements. */
+PPST_API int64_t ppst_plane_dot_scratch_elems(int64_t n, int64_t c, int64_t hw);
+PPST_API int ppst_plane_dot(float* sum_g, float* sum_gx, const void* g, const void* x, float* scratch, int64_t n, int64_t c,
+                   int64_t hw, int dtype, void* stream);
+
 /* uint8 label map [n, hw] -> one-hot f32 [n, n_labels, hw]  (CelebAMaskDataset._mask_labels,
  * data/CelebAMask_dataset.py:54-60; bit-exact membership test label == i). */
 PPST_API int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64_t n, int64_t hw, int n_labels, void* stream);

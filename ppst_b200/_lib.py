@@ -53,6 +53,8 @@ _SIGS = {
     "ppst_plane_reduce": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_upsample_reduce_scratch_elems": (c_i64, [c_i64, c_int, c_int]),
     "ppst_upsample_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 6 + [c_void_p, c_void_p]),
+    "ppst_plane_dot_scratch_elems": (c_i64, [c_i64, c_i64, c_i64]),
+    "ppst_plane_dot": (c_int, [c_void_p] * 5 + [c_i64, c_i64, c_i64, c_int, c_void_p]),
     "ppst_labels_pool_or": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_labels_to_onehot": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_void_p]),
     "ppst_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),

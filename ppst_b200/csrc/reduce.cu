@@ -450,3 +450,103 @@ extern "C" int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64
   PPST_LAUNCH_CHECK("labels_to_onehot_kernel");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Backward reductions of InstanceNorm (+ StyleMod) in the training path: per (sample, channel)
+//   sum_g = sum_p g[p],   sum_gx = sum_p g[p] * x[p]       over the h*w pixels of NHWC bf16 / f32 tensors g, x.
+// Everything the gradient of y = (x - mean) * rstd * (1 + s) + b needs (nn.InstanceNorm2d + StyleMod,
+// stylegan2_layers.py:361-374,414-437) follows from these two and the forward statistics.  Two stages, fixed order.
+namespace ppst {
+constexpr int kDotChunk = 4096;
+template <typename T>
+__global__ void __launch_bounds__(256) plane_dot_kernel(float* __restrict__ partials, const T* __restrict__ g,
+                                                        const T* __restrict__ x, int64_t c, int64_t hw, int chunks) {
+  extern __shared__ float red[];                         // [pixel lanes][c][2]
+  constexpr int VEC = Vec16<T>::N;
+  const int cols = (int)(c / VEC);                       // vector columns, <= 256
+  const int lanes = 256 / cols;
+  const int col = threadIdx.x % cols, lane = threadIdx.x / cols;
+  const int64_t ni = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * kDotChunk, end = min(beg + (int64_t)kDotChunk, hw);
+  float sg[VEC], sx[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { sg[e] = 0.f; sx[e] = 0.f; }
+  if (lane < lanes) {
+    const T* gb = g + ni * hw * c + (int64_t)col * VEC;
+    const T* xb = x + ni * hw * c + (int64_t)col * VEC;
+    for (int64_t p = beg + lane; p < end; p += lanes) {
+      const Vec16<T> gv = ld_vec16_stream(gb + p * c), xv = ld_vec16_stream(xb + p * c);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float gf = Cvt<T>::to_f(gv.v[e]);
+        sg[e] += gf;
+        sx[e] = fmaf(gf, Cvt<T>::to_f(xv.v[e]), sx[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      red[((int64_t)lane * c + col * VEC + e) * 2 + 0] = sg[e];
+      red[((int64_t)lane * c + col * VEC + e) * 2 + 1] = sx[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(int64_t)l * c * 2 + i];
+    partials[((ni * chunks + blockIdx.x) * c) * 2 + i] = t;
+  }
+}
+
+__global__ void plane_dot_final(float* __restrict__ sum_g, float* __restrict__ sum_gx, const float* __restrict__ partials,
+                                int64_t n, int64_t c, int chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  const int64_t ni = t / c, ch = t - ni * c;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    a += partials[((ni * chunks + k) * c + ch) * 2 + 0];
+    b += partials[((ni * chunks + k) * c + ch) * 2 + 1];
+  }
+  sum_g[t] = a;
+  sum_gx[t] = b;
+}
+}  // namespace ppst
+
+extern "C" int64_t ppst_plane_dot_scratch_elems(int64_t n, int64_t c, int64_t hw) {
+  return n * ((hw + ppst::kDotChunk - 1) / ppst::kDotChunk) * c * 2;
+}
+
+extern "C" int ppst_plane_dot(float* sum_g, float* sum_gx, const void* g, const void* x, float* scratch, int64_t n, int64_t c,
+                              int64_t hw, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(sum_g && sum_gx && g && x && scratch && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "plane_dot: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "plane_dot: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0 && c / vec <= 256, PPST_ERR_UNSUPPORTED,
+               "plane_dot: c=%lld (a multiple of %d, at most %d)", (long long)c, vec, 256 * vec);
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, PPST_ERR_ARG,
+               "plane_dot: buffers must be 16-byte aligned");
+  const int chunks = (int)((hw + kDotChunk - 1) / kDotChunk);
+  const size_t smem = sizeof(float) * (size_t)(256 / (c / vec)) * c * 2;
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16) {
+    auto kern = plane_dot_kernel<__nv_bfloat16>;
+    if (smem > 48 * 1024) {
+      int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "plane_dot attr");
+      if (rc) return rc;
+    }
+    kern<<<grid, 256, smem, st>>>(scratch, (const __nv_bfloat16*)g, (const __nv_bfloat16*)x, c, hw, chunks);
+  } else {
+    auto kern = plane_dot_kernel<float>;
+    if (smem > 48 * 1024) {
+      int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "plane_dot attr");
+      if (rc) return rc;
+    }
+    kern<<<grid, 256, smem, st>>>(scratch, (const float*)g, (const float*)x, c, hw, chunks);
+  }
+  PPST_LAUNCH_CHECK("plane_dot_kernel");
+  plane_dot_final<<<ceil_div(n * c, 256), 256, 0, st>>>(sum_g, sum_gx, scratch, n, c, chunks);
+  PPST_LAUNCH_CHECK("plane_dot_final");
+  return 0;
+}

@@ -68,8 +68,9 @@ def _pack(w, slots_key, groups, slots, src, transpose):
     return out
 
 
-def _conv_raw(x, w, g, bias=None, act=False):
-    """x NHWC bf16 [n,h,w,ci], w f32 [co,ci,k,k] -> NHWC bf16 [n,oh,ow,co]; optional fused bias + leaky-ReLU(0.2)*sqrt2."""
+def _conv_raw(x, w, g, bias=None, act=False, noise=None):
+    """x NHWC bf16 [n,h,w,ci], w f32 [co,ci,k,k] -> NHWC bf16 [n,oh,ow,co]; optional fused bias + per-pixel noise
+    (f32 [n,oh,ow], already scaled) + leaky-ReLU(0.2)*sqrt2."""
     n, h, wd, ci = x.shape
     co = w.shape[0]
     assert w.shape[1] == ci and w.shape[2] == g.k and w.shape[3] == g.k, (tuple(w.shape), tuple(x.shape))
@@ -77,9 +78,11 @@ def _conv_raw(x, w, g, bias=None, act=False):
     wp = _pack(w, ("fwd", g.k), 1, g.k * g.k, list(range(g.k * g.k)), False)
     out = torch.empty((n, oh, ow, co), device=x.device, dtype=torch.bfloat16)
     d = ops.conv_desc(x.shape, co, g.k, g.k, stride=g.stride, off=(-g.pad, -g.pad), out_hw=(oh, ow), act=act,
-                      slope=0.2, gain=SQRT2 if act else 1.0, in_dtype=BF16, out_dtype=BF16)
+                      slope=0.2, gain=SQRT2 if act else 1.0, noise_w=1.0 if noise is not None else 0.0, in_dtype=BF16,
+                      out_dtype=BF16)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-    ops.conv_tc(out, x, wp, b, None, None, d)
+    nz = None if noise is None else noise.detach().to(torch.float32).contiguous()
+    ops.conv_tc(out, x, wp, b, nz, None, d)
     return out
 
 
@@ -90,19 +93,25 @@ def _phase_taps(k, pad, r):
     return (max(us), min(us)) if us else (0, 1)
 
 
-def _dgrad_raw(gy, w, g, in_hw):
-    """dx NHWC bf16 [n, in_h, in_w, ci] of y = conv(x, w) given dy (NHWC bf16 [n,oh,ow,co])."""
+def _dgrad_raw(gy, w, g, in_hw, bias=None, act=False, noise=None):
+    """dx NHWC bf16 [n, in_h, in_w, ci] of y = conv(x, w) given dy (NHWC bf16 [n,oh,ow,co]) -- equally the FORWARD of
+    F.conv_transpose2d(dy, w, stride, padding) (EqualizedConv2d's fused upscale, stylegan2_layers.py:312-321), for which
+    the optional bias / noise / leaky-ReLU epilogue exists."""
     n, oh, ow, co = gy.shape
     ci, k = w.shape[1], g.k
     assert w.shape[0] == co
     out = torch.empty((n, in_hw[0], in_hw[1], ci), device=gy.device, dtype=torch.bfloat16)
+    epi = dict(act=act, slope=0.2, gain=SQRT2 if act else 1.0, noise_w=1.0 if noise is not None else 0.0)
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    nz = None if noise is None else noise.detach().to(torch.float32).contiguous()
     if g.stride == 1:
         # rotated by 180 degrees and transposed: slot (ty', tx') reads tap (k-1-ty', k-1-tx'), rows = ci
         src = [(k - 1 - ty) * k + (k - 1 - tx) for ty in range(k) for tx in range(k)]
         wp = _pack(w, ("dgrad1", k), 1, k * k, src, True)
         off = -(k - 1) + g.pad
-        d = ops.conv_desc(gy.shape, ci, k, k, stride=1, off=(off, off), out_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
-        ops.conv_tc(out, gy, wp, None, None, None, d)
+        d = ops.conv_desc(gy.shape, ci, k, k, stride=1, off=(off, off), out_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16,
+                          **epi)
+        ops.conv_tc(out, gy, wp, b, nz, None, d)
         return out
     assert g.stride == 2 and in_hw[0] % 2 == 0 and in_hw[1] % 2 == 0, "stride-2 input gradient needs even input sizes"
     (hi0, lo0), (hi1, lo1) = _phase_taps(k, g.pad, 0), _phase_taps(k, g.pad, 1)
@@ -118,8 +127,8 @@ def _dgrad_raw(gy, w, g, in_hw):
                     src.append(ty * k + tx if (0 <= ty < k and 0 <= tx < k) else -1)
     wp = _pack(w, ("dgrad2", k, g.pad), 4, J * J, src, True)
     d = ops.conv_desc(gy.shape, ci, J, J, stride=1, off=(-hi0, -hi0), out_hw=(in_hw[0] // 2, in_hw[1] // 2), phases=(2, 2),
-                      phase_off=(hi0 - hi1, hi0 - hi1), full_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16)
-    ops.conv_tc(out, gy, wp, None, None, None, d)
+                      phase_off=(hi0 - hi1, hi0 - hi1), full_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16, **epi)
+    ops.conv_tc(out, gy, wp, b, nz, None, d)
     return out
 
 
@@ -244,14 +253,20 @@ class _ChannelSum(Function):
 
 
 class _ConvBiasAct(Function):
-    """conv + bias (+ leaky-ReLU(0.2) * sqrt2) in ONE launch (EqualConv2d + FusedLeakyReLU, stylegan2_layers.py:497-555)."""
+    """conv (or transposed conv) + bias + optional per-pixel noise + optional leaky-ReLU(0.2) * sqrt2 in ONE launch
+    (EqualConv2d + FusedLeakyReLU, stylegan2_layers.py:497-555; StyledConv's conv + NoiseInjection + bias + activate,
+    :439-475).  transposed: x is what a strided convolution with weight w would PRODUCE ([n,oh,ow,co]) and the result is
+    at its input resolution `out_hw` -- F.conv_transpose2d(x, w, stride, padding)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, g, act):
+    def forward(ctx, x, w, b, noise, g, act, transposed, out_hw):
         x = _nhwc(x)
-        y = _conv_raw(x, w, g, bias=b, act=act)
+        if transposed:
+            y = _dgrad_raw(x, w, g, out_hw, bias=b, act=act, noise=noise)
+        else:
+            y = _conv_raw(x, w, g, bias=b, act=act, noise=noise)
         ctx.save_for_backward(x, w, y)
-        ctx.g, ctx.act = g, act
+        ctx.g, ctx.act, ctx.transposed = g, act, transposed
         return y
 
     @staticmethod
@@ -259,21 +274,43 @@ class _ConvBiasAct(Function):
         x, w, y = ctx.saved_tensors
         gy = _nhwc(gy)
         gp = _ActGrad.apply(gy, y) if ctx.act else gy
-        dx = _ConvT.apply(gp, w, ctx.g, (x.shape[1], x.shape[2])) if ctx.needs_input_grad[0] else None
-        dw = _Wgrad.apply(x, gp, ctx.g, tuple(w.shape)) if ctx.needs_input_grad[1] else None
-        db = _ChannelSum.apply(gp) if ctx.needs_input_grad[2] else None
-        return dx, dw, db, None, None
+        need = ctx.needs_input_grad
+        dx = dw = db = dn = None
+        if ctx.transposed:
+            if need[0]:
+                dx = _Conv.apply(gp, w, ctx.g)
+            if need[1]:
+                dw = _Wgrad.apply(gp, x, ctx.g, tuple(w.shape))
+        else:
+            if need[0]:
+                dx = _ConvT.apply(gp, w, ctx.g, (x.shape[1], x.shape[2]))
+            if need[1]:
+                dw = _Wgrad.apply(x, gp, ctx.g, tuple(w.shape))
+        if need[2]:
+            db = _ChannelSum.apply(gp)
+        if need[3]:
+            dn = gp.sum(dim=3, dtype=torch.float32)              # d(noise)[n,y,x] = sum over channels (one read of gp)
+        return dx, dw, db, dn, None, None, None, None
 
 
-def conv2d(x, w, stride=1, padding=0, bias=None, act=False):
-    """F.conv2d on NHWC bf16 activations (x [n,h,w,ci], w f32 [co,ci,k,k]) with the optional fused
-    FusedLeakyReLU epilogue; differentiable to second order."""
+def conv2d(x, w, stride=1, padding=0, bias=None, act=False, noise=None):
+    """F.conv2d on NHWC bf16 activations (x [n,h,w,ci], w f32 [co,ci,k,k]) with the optional fused epilogue
+    (+ bias[co], + noise[n,oh,ow], leaky-ReLU(0.2) * sqrt2); differentiable to second order."""
     g = Geom(w.shape[2], stride, padding)
-    if bias is None and not act:
+    if bias is None and not act and noise is None:
         return _Conv.apply(x, w, g)
     if bias is None:
         bias = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
-    return _ConvBiasAct.apply(x, w, bias, g, act)
+    return _ConvBiasAct.apply(x, w, bias, noise, g, act, False, None)
+
+
+def conv_transpose2d(x, w, stride, padding, out_hw, bias=None, act=False, noise=None):
+    """F.conv_transpose2d(x, w, stride=stride, padding=padding) on NHWC bf16: x [n,h,w,c_in], w f32 [c_in, c_out, k, k] (torch's
+    transposed-conv weight layout), result [n, out_hw, c_out]; same optional epilogue as conv2d."""
+    g = Geom(w.shape[2], stride, padding)
+    if bias is None:
+        bias = torch.zeros(w.shape[1], device=w.device, dtype=torch.float32)
+    return _ConvBiasAct.apply(x, w, bias, noise, g, act, True, tuple(out_hw))
 
 
 # ------------------------------------------------------------------------------------------------ thin input layer
@@ -410,6 +447,132 @@ class _Linear(Function):
 
 def linear(x, w):
     return _Linear.apply(x, w)
+
+
+# ------------------------------------------------------------------------------------------------ norm / modulation
+def _plane_dot(g, x):
+    """(sum_p g, sum_p g*x) per (sample, channel): f32 [n, c] each (ppst_plane_dot)."""
+    n, h, w, c = x.shape
+    L = _lib.load()
+    scratch = ops._get_scratch(x.device, L.ppst_plane_dot_scratch_elems(n, c, h * w))
+    sg = torch.empty((n, c), device=x.device, dtype=torch.float32)
+    sgx = torch.empty((n, c), device=x.device, dtype=torch.float32)
+    with ops._Prof("plane_dot", 2 * x.numel() * x.element_size()):
+        check(L.ppst_plane_dot(ptr(sg), ptr(sgx), ptr(g), ptr(x), ptr(scratch), n, c, h * w, dt(x), stream()))
+    return sg, sgx
+
+
+class _NormMod(Function):
+    """y = act( InstanceNorm(x) * (1 + scale) + shift ): nn.InstanceNorm2d (biased variance, eps 1e-5) followed by
+    StyleMod (stylegan2_layers.py:361-374,414-437: scale / shift f32 [n, c]) or by a per-channel bias and
+    FusedLeakyReLU (ConvLayer with norm='in', :527-531: shift = bias, act = True).  Forward: statistics, coefficients,
+    ONE apply pass.  Backward: two fused reductions (ppst_plane_dot) and ONE apply pass dx = alpha*g + beta*x + gamma."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, act):
+        x = _nhwc(x)
+        n, h, w, c = x.shape
+        N = float(h * w)
+        st = ops.plane_reduce(x, channels_last=True, want=("sum", "sumsq"))
+        mean = st["sum"].view(n, c) / N
+        var = (st["sumsq"].view(n, c) / N - mean * mean).clamp_min(0.0)
+        rstd = torch.rsqrt(var + 1e-5)
+        a = rstd if scale is None else rstd * (1.0 + scale.to(torch.float32))
+        b = -mean * a
+        if shift is not None:
+            b = b + shift.to(torch.float32)
+        y = ops.affine_apply(x, c, a=a.contiguous(), b=b.contiguous(), post_slope=0.2 if act else 1.0,
+                             post_gain=SQRT2 if act else 1.0, out_dtype=torch.bfloat16)
+        ctx.save_for_backward(x, y if act else None, mean, rstd, scale)
+        ctx.act, ctx.has_shift = act, shift is not None
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, y, mean, rstd, scale = ctx.saved_tensors
+        g = _nhwc(g)
+        if ctx.act:
+            g = _act_grad_raw(g, y)
+        n, h, w, c = x.shape
+        N = float(h * w)
+        sg, sgx = _plane_dot(g, x)
+        m1 = sg / N
+        gxh = rstd * (sgx - mean * sg)                     # sum_p g * xhat
+        m2 = gxh / N
+        alpha = rstd if scale is None else rstd * (1.0 + scale.to(torch.float32))
+        beta = -alpha * m2 * rstd
+        gamma = -alpha * m1 + alpha * mean * rstd * m2
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.affine_apply(g, c, a=alpha.contiguous(), b=gamma.contiguous(), res=x, ra=beta.contiguous(), res_mode=1,
+                                  out_dtype=torch.bfloat16)
+        dscale = gxh if (scale is not None and ctx.needs_input_grad[1]) else None
+        dshift = sg if (ctx.has_shift and ctx.needs_input_grad[2]) else None
+        return dx, dscale, dshift, None
+
+
+def instance_norm_mod(x, scale=None, shift=None, act=False):
+    return _NormMod.apply(x, scale, shift, act)
+
+
+class _Affine(Function):
+    """y = x * a + b per (sample, channel) (GeneratorModulation, generator.py:80-91): a, b f32 [n, c]."""
+
+    @staticmethod
+    def forward(ctx, x, a, b):
+        x = _nhwc(x)
+        ctx.save_for_backward(x, a)
+        return ops.affine_apply(x, x.shape[3], a=a.to(torch.float32).contiguous(), b=b.to(torch.float32).contiguous(),
+                                out_dtype=torch.bfloat16)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, a = ctx.saved_tensors
+        g = _nhwc(g)
+        sg, sgx = _plane_dot(g, x)
+        dx = ops.affine_apply(g, g.shape[3], a=a.to(torch.float32).contiguous(), out_dtype=torch.bfloat16) \
+            if ctx.needs_input_grad[0] else None
+        return dx, sgx, sg
+
+
+def channel_affine(x, a, b):
+    return _Affine.apply(x, a, b)
+
+
+class _ReflectPad(Function):
+    """nn.ReflectionPad2d on NHWC (the encoders' ConvLayer(reflection_pad=True), stylegan2_layers.py:142-164,525):
+    forward = one ppst_affine_apply pass with reflect addressing; backward folds the border gradients back."""
+
+    @staticmethod
+    def forward(ctx, x, pad):
+        x = _nhwc(x)
+        ctx.pad = pad
+        return ops.affine_apply(x, x.shape[3], pad=tuple(pad), pad_mode=1, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        t, b, l, r = ctx.pad
+        g = g.to(torch.float32)
+        H, W = g.shape[1] - t - b, g.shape[2] - l - r
+        rows = g[:, t:t + H].clone()
+        if t:
+            rows[:, 1:t + 1] += g[:, :t].flip(1)
+        if b:
+            rows[:, H - 1 - b:H - 1] += g[:, t + H:].flip(1)
+        out = rows[:, :, l:l + W].clone()
+        if l:
+            out[:, :, 1:l + 1] += rows[:, :, :l].flip(2)
+        if r:
+            out[:, :, W - 1 - r:W - 1] += rows[:, :, l + W:].flip(2)
+        return out.to(torch.bfloat16), None
+
+
+def reflect_pad(x, pad):
+    """pad = (top, bottom, left, right)."""
+    return _ReflectPad.apply(x, tuple(int(p) for p in pad))
 
 
 # ------------------------------------------------------------------------------------------------ discriminator

@@ -284,3 +284,115 @@ def test_discriminator_matches_bf16_emulation():
     errs = {k: rel_l2(D.p(k[len("stylegan2_D."):]).grad, e[k].grad) for k in keys if not k.endswith("bias")}
     print("R1 gradient rel-L2 vs the bf16 emulation:", {k[12:]: round(v, 4) for k, v in errs.items()})
     assert max(errs.values()) <= GRAD_TOL_DEEP, errs
+
+
+# ---------------------------------------------------------------------------------------------- generator side (stage 1)
+def test_norm_mod_affine_reflect_pad_gradients():
+    """InstanceNorm + StyleMod (+ leaky-ReLU), the per-(n,c) affine and the reflection pad against torch autograd."""
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(11)
+    n, h, w, c = 2, 24, 40, 64
+    x = _bf(torch.randn(n, h, w, c, generator=g) * 1.5 + 0.3).cuda()
+    sc, sh = (0.3 * torch.randn(n, c, generator=g)).cuda(), (0.3 * torch.randn(n, c, generator=g)).cuda()
+    gy = _bf(torch.randn(n, h, w, c, generator=g)).cuda()
+    for act in (False, True):
+        xr, scr, shr = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+        mu = xr.mean(dim=(1, 2), keepdim=True)
+        var = ((xr - mu) ** 2).mean(dim=(1, 2), keepdim=True)
+        yr = (xr - mu) * torch.rsqrt(var + 1e-5) * (1 + scr[:, None, None, :]) + shr[:, None, None, :]
+        if act:
+            yr = F.leaky_relu(yr, 0.2) * math.sqrt(2)
+        yr.backward(gy)
+        xb, scb, shb = x.to(torch.bfloat16).requires_grad_(True), sc.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+        y = train.instance_norm_mod(xb, scb, shb, act=act)
+        y.backward(gy.to(torch.bfloat16))
+        assert rel_l2(y, yr) <= 5e-3
+        assert rel_l2(xb.grad, xr.grad) <= 1e-2, (act, rel_l2(xb.grad, xr.grad))
+        assert rel_l2(scb.grad, scr.grad) <= 1e-2 and rel_l2(shb.grad, shr.grad) <= 1e-2
+    # affine
+    xr, ar, br = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+    (xr * ar[:, None, None, :] + br[:, None, None, :]).backward(gy)
+    xb, ab, bb = x.to(torch.bfloat16).requires_grad_(True), sc.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+    train.channel_affine(xb, ab, bb).backward(gy.to(torch.bfloat16))
+    assert rel_l2(xb.grad, xr.grad) <= 5e-3 and rel_l2(ab.grad, ar.grad) <= 5e-3 and rel_l2(bb.grad, br.grad) <= 5e-3
+    # reflection pad, asymmetric
+    pad = (2, 1, 2, 2)
+    xr = x.clone().requires_grad_(True)
+    yr = F.pad(xr.permute(0, 3, 1, 2), (pad[2], pad[3], pad[0], pad[1]), mode="reflect").permute(0, 2, 3, 1)
+    gp = _bf(torch.randn(yr.shape, generator=g)).cuda()
+    yr.backward(gp)
+    xb = x.to(torch.bfloat16).requires_grad_(True)
+    y = train.reflect_pad(xb, pad)
+    assert torch.equal(y.float(), yr.detach())
+    y.backward(gp.to(torch.bfloat16))
+    assert rel_l2(xb.grad, xr.grad) <= 5e-3
+
+
+def test_conv_transpose_fused_upscale_matches_torch():
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(12)
+    n, h, w, ci, co = 2, 64, 64, 64, 128
+    x = _bf(torch.randn(n, h, w, ci, generator=g)).cuda()
+    wt = _bf(torch.randn(ci, co, 4, 4, generator=g) / math.sqrt(ci * 4)).cuda()
+    b = (0.2 * torch.randn(co, generator=g)).cuda()
+    nz = (0.3 * torch.randn(n, 2 * h, 2 * w, generator=g)).cuda()
+    gy = _bf(torch.randn(n, 2 * h, 2 * w, co, generator=g)).cuda()
+    xr, wr, br, nr = _nchw(x).requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True), nz.clone().requires_grad_(True)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        yr = F.conv_transpose2d(xr, wr, stride=2, padding=1) + br.view(1, -1, 1, 1) + nr[:, None]
+        yr = F.leaky_relu(yr, 0.2) * math.sqrt(2)
+        yr.backward(_nchw(gy))
+    xb, wb, bb, nb = x.to(torch.bfloat16).requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True), nz.clone().requires_grad_(True)
+    y = train.conv_transpose2d(xb, wb, 2, 1, (2 * h, 2 * w), bias=bb, act=True, noise=nb)
+    y.backward(gy.to(torch.bfloat16))
+    assert rel_l2(_nchw(y), yr) <= 5e-3
+    assert rel_l2(_nchw(xb.grad), xr.grad) <= 1e-2
+    assert rel_l2(wb.grad, wr.grad) <= 1e-2 and rel_l2(bb.grad, br.grad) <= 1e-2 and rel_l2(nb.grad, nr.grad) <= 1e-2
+
+
+def test_stage1_networks_forward_and_l1_gradients_match_oracle():
+    """E1 / E2 / G of training stage 1 at 128x128 against the CPU oracle: forward (bf16 drift bounds of the inference
+    tests) and the gradients of the L1 reconstruction loss w.r.t. parameters of all three networks (torch.autograd through
+    the oracle's fp32 expression; whole-network bound: cosine >= 0.99, see GRAD_TOL_DEEP)."""
+    from oracle import ppst_oracle as O
+    from ppst_b200 import train_nets as TN
+    sdE1, sdE2, sdG = O.make_networks(0)
+    size, n = 128, 2
+    real = O.make_portraits(n, size, size, seed=21, smooth=True)
+    noises = O.make_noises(n, size, size, seed=5)
+    keys = {"E1": ["FromRGB.Conv.weight", "DownToSpatialCode.ResBlockDownBy2.conv2.Conv.weight", "ToSpatialCode.1.Conv.weight"],
+            "E2": ["DownToGlobalCode1.ResBlockDownBy1.conv1.Conv.weight", "projector1.3.weight", "conv1x1_2.weight"],
+            "G": ["HeadResnetBlock0.conv1.conv.weight", "HeadResnetBlock2.skip.Conv.weight",
+                  "UpsamplingResBlock32.conv1.conv.weight", "UpsamplingResBlock64.conv2.epi1.style_mod.lin.weight",
+                  "UpsamplingResBlock64.conv2.noise.weight", "ToRGB.conv.weight", "SpatialCodeModulation.scale.weight"]}
+    ref = {}
+    for name, sd in (("E1", sdE1), ("E2", sdE2), ("G", sdG)):
+        ref[name] = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and not k.endswith("kernel")) else v)
+                     for k, v in sd.items()}
+    sp_r = O.encoder_con(ref["E1"], real)
+    gl_r = O.encoder_col(ref["E2"], real)[0]
+    rec_r = O.generator(ref["G"], sp_r, gl_r, noises=noises)
+    (rec_r - real).abs().mean().backward()
+    E1, E2, G = TN.ParamSet(sdE1).cuda(), TN.ParamSet(sdE2).cuda(), TN.ParamSet(sdG).cuda()
+    rc = real.cuda()
+    sp = TN.encoder_con(E1, rc)
+    gl = TN.encoder_col(E2, rc)
+    rec = TN.generator(G, sp, gl, noises=noises)
+    assert rel_l2(sp.float().permute(0, 3, 1, 2), sp_r) <= 2e-2
+    for a, b in zip(gl, gl_r):
+        assert rel_l2(a, b) <= 2e-2
+    peak = float(rec_r.max() - rec_r.min())
+    psnr = 10 * math.log10(peak * peak / float(((rec.detach().cpu() - rec_r.detach()) ** 2).mean()))
+    assert psnr >= 40.0, psnr
+    (rec - rc).abs().mean().backward()
+    errs = {}
+    for name, P in (("E1", E1), ("E2", E2), ("G", G)):
+        for k in keys[name]:
+            errs[name + "." + k] = rel_l2(P[k].grad, ref[name][k].grad)
+    print("stage-1 L1-loss gradient rel-L2 vs the oracle:", {k: round(v, 4) for k, v in errs.items()}, "PSNR %.1f" % psnr)
+    # ~40 bf16 layers with leaky-ReLU between the loss and E1's first layer, 16x16 .. 128x128 maps, batch 2: a forward
+    # drift of 1 % flips ~0.8 % of the branches of a layer, i.e. ~0.1 of that layer's gradient in rel-L2 (tools/train_diag.py
+    # decomposes it per network: 0.05-0.11 for E1 / E2 alone, 0.02 -> 0.2 from ToRGB down to the spatial code for G alone).
+    # Bound: cosine >= 0.95 for every probed parameter, >= 0.99 next to the loss.
+    assert max(errs.values()) <= 0.30, errs
+    assert errs["G.ToRGB.conv.weight"] <= GRAD_TOL_DEEP and errs["G.UpsamplingResBlock64.conv2.epi1.style_mod.lin.weight"] <= GRAD_TOL_DEEP

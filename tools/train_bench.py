@@ -25,13 +25,110 @@ def timed(fn, steps, warm=2):
     return e0.elapsed_time(e1) / steps
 
 
+def stage1(args):
+    """Training stage 1 (ppst_model.py:113-137,139-156,158-236 with lambda_StyleCon = 0): generator step = E1, E2, G forward
+    + backward with the L1 and GAN losses (D forward + input gradient), discriminator step (reconstructions without
+    grad, D forward + backward), R1 step; Adam on both parameter sets; one flat gradient all-reduce per step."""
+    from oracle import ppst_oracle as O
+    from ppst_b200 import train, train_nets as TN, ops, _lib, sharding
+    world, rank, local_rank = sharding.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sdE1, sdE2, sdG = O.make_networks(0)
+    for k in sdG:
+        if k.endswith("noise.weight"):
+            sdG[k] = torch.zeros_like(sdG[k])                     # the reference's initial value
+    D = train.Discriminator(args.size, 2.0)
+    D.load_reference_state_dict(O.make_discriminator(args.size, seed=0))
+    m = TN.Stage1(sdE1, sdE2, sdG, D, noise_seed=1234 + rank).to(dev)
+    g_params, d_params = m.g_params(), list(D.parameters())
+    opt_g = torch.optim.Adam(g_params, lr=2e-3, betas=(0.0, 0.99), fused=True)
+    opt_d = torch.optim.Adam(d_params, lr=2e-3, betas=(0.0, 0.99), fused=True)
+    real = O.make_portraits(args.batch, args.size, args.size, seed=77 + rank, smooth=True).to(dev)
+    bucket = {}
+
+    def g_step():
+        opt_g.zero_grad(set_to_none=True)
+        for p in d_params:
+            p.requires_grad_(False)
+        losses, _ = m.generator_losses(real)
+        sum(losses.values()).backward()
+        for p in d_params:
+            p.requires_grad_(True)
+        bucket["g"] = sharding.allreduce_grads_(g_params, world)
+        opt_g.step()
+
+    def d_step():
+        opt_d.zero_grad(set_to_none=True)
+        sum(m.discriminator_losses(real).values()).backward()
+        bucket["d"] = sharding.allreduce_grads_(d_params, world)
+        opt_d.step()
+
+    def r1_step():
+        opt_d.zero_grad(set_to_none=True)
+        train.r1_loss(D, real).mean().backward()
+        sharding.allreduce_grads_(d_params, world)
+        opt_d.step()
+
+    l0 = _lib.launch_count()
+    g_step(); d_step(); r1_step()
+    launches = _lib.launch_count() - l0
+    sharding.barrier()
+    ms = {k: sharding.max_over_ranks(timed(f, args.steps), device=dev) for k, f in (("g_step", g_step), ("d_step", d_step), ("r1_step", r1_step))}
+    ops.PROFILE = {}
+    g_step(); d_step()
+    torch.cuda.synchronize()
+    prof = ops.profile_summary()
+    ops.PROFILE = None
+    kern = {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1) if k in ("conv_tc", "conv_wgrad") and v["ms"] > 0 else None}
+            for k, v in prof.items()}
+    # one iteration of the reference's loop = G step + D step, R1 every 16th iteration (R1_once_every, ppst_optimizer.py)
+    it_ms = ms["g_step"] + ms["d_step"] + ms["r1_step"] / 16.0
+    out = {"workload": "training stage 1 @%d^2, batch %d per GPU: G step (E1+E2+G+D), D step, R1 every 16th" % (args.size, args.batch),
+           "n_gpus": world, "scaling": "weak", "images_per_s": round(world * args.batch / (it_ms * 1e-3), 1),
+           "ms": {k: round(v, 2) for k, v in ms.items()}, "iteration_ms": round(it_ms, 2),
+           "grad_allreduce_bytes": bucket, "launches_g_d_r1": launches, "kernels_g_plus_d": kern}
+    if rank != 0:
+        return
+    if not args.no_torch and world == 1:
+        def leaf(sd):
+            return {k: (v.to(dev).requires_grad_(True) if (v.is_floating_point() and not k.endswith("kernel")) else v.to(dev)) for k, v in sd.items()}
+        rE1, rE2, rG, rD = leaf(sdE1), leaf(sdE2), leaf(sdG), leaf(O.make_discriminator(args.size, seed=0))
+        rp = [v for d in (rE1, rE2, rG) for v in d.values() if v.requires_grad]
+        topt = torch.optim.Adam(rp, lr=2e-3, betas=(0.0, 0.99), fused=True)
+        tdopt = torch.optim.Adam([v for v in rD.values() if v.requires_grad], lr=2e-3, betas=(0.0, 0.99), fused=True)
+
+        def t_rec(x):
+            return O.generator(rG, O.encoder_con(rE1, x), O.encoder_col(rE2, x)[0])
+
+        def t_g():
+            topt.zero_grad(set_to_none=True)
+            rec = t_rec(real)
+            ((rec - real).abs().mean() + 0.5 * O.gan_loss(O.discriminator(rD, rec), True)).backward()
+            topt.step()
+
+        def t_d():
+            tdopt.zero_grad(set_to_none=True)
+            with torch.no_grad():
+                rec = t_rec(real[: args.batch // 2])
+            sum(O.d_losses(rD, real, rec).values()).backward()
+            tdopt.step()
+        out["torch_cudnn_tf32_ms"] = {"g_step": round(timed(t_g, max(2, args.steps // 2), warm=1), 2),
+                                      "d_step": round(timed(t_d, max(2, args.steps // 2), warm=1), 2)}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-torch", action="store_true")
+    ap.add_argument("--stage1", action="store_true", help="whole stage-1 iteration: G step (E1, E2, G, D), D step, R1 step")
     args = ap.parse_args()
+    if args.stage1:
+        return stage1(args)
     from oracle import ppst_oracle as O
     from ppst_b200 import train, ops, _lib, sharding
     world, rank, local_rank = sharding.init()

@@ -1,4 +1,5 @@
-"""CUPTI kernel timeline of one discriminator D step + R1 step (which kernels the step's GPU time goes to)."""
+"""CUPTI kernel timeline of one discriminator D step + R1 step, or (third argument `stage1`) of the stage-1 generator
+step (which kernels the step's GPU time goes to)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,7 +23,25 @@ def step(r1):
     opt.step()
 
 
-for r1 in (False, True):
+if len(sys.argv) > 3 and sys.argv[3] == "stage1":
+    from ppst_b200 import train_nets as TN
+    sdE1, sdE2, sdG = O.make_networks(0)
+    for k in sdG:
+        if k.endswith("noise.weight"):
+            sdG[k] = torch.zeros_like(sdG[k])
+    m = TN.Stage1(sdE1, sdE2, sdG, D, noise_seed=1).to(dev)
+    gp = m.g_params()
+    gopt = torch.optim.Adam(gp, lr=2e-3, betas=(0.0, 0.99), fused=True)
+    for p in D.parameters():
+        p.requires_grad_(False)
+
+    def step(_):
+        gopt.zero_grad(set_to_none=True)
+        losses, _r = m.generator_losses(real)
+        sum(losses.values()).backward()
+        gopt.step()
+
+for r1 in ((False,) if len(sys.argv) > 3 else (False, True)):
     step(r1); step(r1)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
