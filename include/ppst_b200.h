@@ -336,6 +336,16 @@ PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in
 PPST_API int ppst_linear(float* y, const float* x, const float* w, const float* b, int64_t m, int64_t n, int64_t k,
                 int64_t ldx, float w_scale, float b_scale, int relu_in, void* stream);
 
+/* Backward of ppst_linear for the training path (EqualLinear / EqualizedLinear / the projector MLPs under torch.autograd in
+ * the reference): y[m, n] = x[m, k] . w[n, k]^T with a tiny batch m.
+ *   ppst_linear_dgrad: dx[m, k] = gy[m, n] . w[n, k]    (scratch: ppst_linear_dgrad_scratch_elems(m, n, k) floats)
+ *   ppst_linear_wgrad: dw[n, k] = gy[m, n]^T . x[m, k]
+ * All f32, contiguous, k a multiple of 4; fixed summation order. */
+PPST_API int64_t ppst_linear_dgrad_scratch_elems(int64_t m, int64_t n, int64_t k);
+PPST_API int ppst_linear_dgrad(float* dx, const float* gy, const float* w, float* scratch, int64_t m, int64_t n, int64_t k,
+                      void* stream);
+PPST_API int ppst_linear_wgrad(float* dw, const float* gy, const float* x, int64_t m, int64_t n, int64_t k, void* stream);
+
 /* mode 0: y = v * rsqrt(sum v^2 + eps)        (util.normalize, util/util.py:18-22, eps = 1e-8)
  * mode 1: y = v / max(||v||, eps)              (F.normalize, encoder_col.py:166, eps = 1e-12) */
 PPST_API int ppst_l2_normalize(float* y, const float* x, int64_t rows, int64_t cols, float eps, int mode, void* stream);

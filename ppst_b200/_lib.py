@@ -82,6 +82,9 @@ _SIGS = {
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),
     "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p, c_void_p, c_float, c_void_p]),
     "ppst_linear": (c_int, [c_void_p] * 4 + [c_i64] * 4 + [c_float, c_float, c_int, c_void_p]),
+    "ppst_linear_dgrad_scratch_elems": (c_i64, [c_i64, c_i64, c_i64]),
+    "ppst_linear_dgrad": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_i64, c_void_p]),
+    "ppst_linear_wgrad": (c_int, [c_void_p] * 3 + [c_i64, c_i64, c_i64, c_void_p]),
     "ppst_l2_normalize": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_float, c_int, c_void_p]),
     "ppst_lerp": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_i64, c_void_p]),
     "ppst_rselfcorr": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 7 + [c_void_p]),

@@ -236,7 +236,100 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x
   for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) xr[i] = xr[i] / tot;
 }
 
+// ---- backward of the skinny linear (training): the batch m is tiny, the weights are the traffic ------
+// dw[n][k] = sum_m gy[m][n] * x[m][k]: one thread per (n, 4 consecutive k); x (m x k) stays in L1 / L2.
+__global__ void __launch_bounds__(256) linear_wgrad_kernel(float* __restrict__ dw, const float* __restrict__ gy,
+                                                           const float* __restrict__ x, int m, int64_t n, int64_t k) {
+  const int64_t k4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t row = blockIdx.y;
+  if (k4 >= k) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < m; ++i) {
+    const float g = gy[(int64_t)i * n + row];
+    const float4 xv = *reinterpret_cast<const float4*>(x + (int64_t)i * k + k4);
+    acc.x = fmaf(g, xv.x, acc.x); acc.y = fmaf(g, xv.y, acc.y); acc.z = fmaf(g, xv.z, acc.z); acc.w = fmaf(g, xv.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(dw + row * k + k4) = acc;
+}
+
+// dx[m][k] = sum_n gy[m][n] * w[n][k]: a block owns 128 columns of k (32 lanes x float4), 8 batch rows and one slice of n;
+// its 8 warps interleave over the slice, every weight element is read once per 8 rows.  Partials [slice][m][k] are
+// summed in slice order by linear_dgrad_final.
+constexpr int kDgRows = 8;
+__global__ void __launch_bounds__(256) linear_dgrad_kernel(float* __restrict__ partial, const float* __restrict__ gy,
+                                                           const float* __restrict__ w, int m, int64_t n, int64_t k,
+                                                           int64_t n_per_slice) {
+  __shared__ float red[8][kDgRows][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t k4 = (int64_t)blockIdx.x * 128 + lane * 4;
+  const int64_t n0 = (int64_t)blockIdx.y * n_per_slice, n1 = min(n0 + n_per_slice, n);
+  const int m0 = blockIdx.z * kDgRows;
+  float acc[kDgRows][4];
+#pragma unroll
+  for (int r = 0; r < kDgRows; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+  if (k4 < k) {
+    for (int64_t j = n0 + warp; j < n1; j += 8) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + j * k + k4);
+#pragma unroll
+      for (int r = 0; r < kDgRows; ++r) {
+        const float g = (m0 + r < m) ? gy[(int64_t)(m0 + r) * n + j] : 0.f;
+        acc[r][0] = fmaf(g, wv.x, acc[r][0]); acc[r][1] = fmaf(g, wv.y, acc[r][1]);
+        acc[r][2] = fmaf(g, wv.z, acc[r][2]); acc[r][3] = fmaf(g, wv.w, acc[r][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kDgRows; ++r)
+    *reinterpret_cast<float4*>(&red[warp][r][lane * 4]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDgRows * 128; i += 256) {
+    const int r = i / 128, c = i - r * 128;
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][r][c];
+    const int64_t kk = (int64_t)blockIdx.x * 128 + c;
+    if (m0 + r < m && kk < k) partial[((int64_t)blockIdx.y * m + m0 + r) * k + kk] = t;
+  }
+}
+
+__global__ void linear_dgrad_final(float* __restrict__ dx, const float* __restrict__ partial, int64_t mk, int slices) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mk) return;
+  float t = 0.f;
+  for (int s = 0; s < slices; ++s) t += partial[(int64_t)s * mk + i];
+  dx[i] = t;
+}
+
 }  // namespace ppst
+
+static int linear_dgrad_slices(int64_t n) { return n >= 512 ? 8 : (n >= 64 ? 2 : 1); }
+
+extern "C" int64_t ppst_linear_dgrad_scratch_elems(int64_t m, int64_t n, int64_t k) { return linear_dgrad_slices(n) * m * k; }
+
+extern "C" int ppst_linear_dgrad(float* dx, const float* gy, const float* w, float* scratch, int64_t m, int64_t n, int64_t k,
+                                 void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(dx && gy && w && scratch && m > 0 && n > 0 && k > 0 && k % 4 == 0, PPST_ERR_ARG, "linear_dgrad: bad args (k %% 4)");
+  const int slices = linear_dgrad_slices(n);
+  const int64_t per = (n + slices - 1) / slices;
+  dim3 grid((unsigned)ceil_div(k, 128), (unsigned)slices, (unsigned)ceil_div(m, kDgRows));
+  cudaStream_t st = (cudaStream_t)stream;
+  linear_dgrad_kernel<<<grid, 256, 0, st>>>(scratch, gy, w, (int)m, n, k, per);
+  PPST_LAUNCH_CHECK("linear_dgrad_kernel");
+  linear_dgrad_final<<<ceil_div(m * k, 256), 256, 0, st>>>(dx, scratch, m * k, slices);
+  PPST_LAUNCH_CHECK("linear_dgrad_final");
+  return 0;
+}
+
+extern "C" int ppst_linear_wgrad(float* dw, const float* gy, const float* x, int64_t m, int64_t n, int64_t k, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(dw && gy && x && m > 0 && n > 0 && k > 0 && k % 4 == 0 && n <= 65535, PPST_ERR_ARG,
+               "linear_wgrad: bad args (k %% 4, n <= 65535)");
+  dim3 grid((unsigned)ceil_div(k / 4, 256), (unsigned)n);
+  linear_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dw, gy, x, (int)m, n, k);
+  PPST_LAUNCH_CHECK("linear_wgrad_kernel");
+  return 0;
+}
 
 extern "C" int ppst_linear(float* y, const float* x, const float* w, const float* b, int64_t m, int64_t n, int64_t k,
                            int64_t ldx, float w_scale, float b_scale, int relu_in, void* stream) {

@@ -427,8 +427,28 @@ def add_scale(a, b, s):
     return _AddScale.apply(a, b, s)
 
 
+def _lin_dgrad(gy, w):
+    m, n = gy.shape
+    k = w.shape[1]
+    L = _lib.load()
+    scratch = ops._get_scratch(gy.device, L.ppst_linear_dgrad_scratch_elems(m, n, k))
+    dx = torch.empty((m, k), device=gy.device, dtype=torch.float32)
+    check(L.ppst_linear_dgrad(ptr(dx), ptr(gy), ptr(w), ptr(scratch), m, n, k, stream()))
+    return dx
+
+
+def _lin_wgrad(gy, x):
+    m, n = gy.shape
+    k = x.shape[1]
+    dw = torch.empty((n, k), device=gy.device, dtype=torch.float32)
+    check(_lib.load().ppst_linear_wgrad(ptr(dw), ptr(gy), ptr(x), m, n, k, stream()))
+    return dw
+
+
 class _Linear(Function):
-    """y = x @ w^T on ppst_linear (f32; EqualLinear, stylegan2_layers.py:205-247).  x [m,k], w [n,k]."""
+    """y = x @ w^T (f32; EqualLinear, stylegan2_layers.py:205-247).  x [m,k], w [n,k]; the batch m is tiny, so forward,
+    input gradient and weight gradient are three weight-streaming kernels (ppst_linear / _dgrad / _wgrad).  The three maps
+    are bilinear and closed, so the backward is itself differentiable (R1 passes through D's head)."""
 
     @staticmethod
     def forward(ctx, x, w):
@@ -439,10 +459,48 @@ class _Linear(Function):
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        gy = gy.contiguous()
-        dx = _Linear.apply(gy, w.t()) if ctx.needs_input_grad[0] else None          # [m,n] @ [n,k]
-        dw = _Linear.apply(gy.t(), x.t()) if ctx.needs_input_grad[1] else None      # [n,m] @ [m,k]
+        gy = gy.to(torch.float32).contiguous()
+        dx = _LinearT.apply(gy, w) if ctx.needs_input_grad[0] else None
+        dw = _LinearW.apply(gy, x) if ctx.needs_input_grad[1] else None
         return dx, dw
+
+
+class _LinearT(Function):
+    """dx = gy @ w   (gy [m,n], w [n,k])."""
+
+    @staticmethod
+    def forward(ctx, gy, w):
+        gy, w = gy.to(torch.float32).contiguous(), w.to(torch.float32).contiguous()
+        ctx.save_for_backward(gy, w)
+        if w.shape[1] % 4:
+            return ops.linear(gy, w.t().contiguous())
+        return _lin_dgrad(gy, w)
+
+    @staticmethod
+    def backward(ctx, gz):
+        gy, w = ctx.saved_tensors
+        dgy = _Linear.apply(gz, w) if ctx.needs_input_grad[0] else None
+        dw = _LinearW.apply(gy, gz) if ctx.needs_input_grad[1] else None
+        return dgy, dw
+
+
+class _LinearW(Function):
+    """dw = gy^T @ x   (gy [m,n], x [m,k])."""
+
+    @staticmethod
+    def forward(ctx, gy, x):
+        gy, x = gy.to(torch.float32).contiguous(), x.to(torch.float32).contiguous()
+        ctx.save_for_backward(gy, x)
+        if x.shape[1] % 4 or gy.shape[1] > 65535:
+            return ops.linear(gy.t().contiguous(), x.t().contiguous())
+        return _lin_wgrad(gy, x)
+
+    @staticmethod
+    def backward(ctx, gdw):
+        gy, x = ctx.saved_tensors
+        dgy = _Linear.apply(x, gdw) if ctx.needs_input_grad[0] else None        # [m,k] @ [n,k]^T
+        dx = _LinearT.apply(gy, gdw) if ctx.needs_input_grad[1] else None       # [m,n] @ [n,k]
+        return dgy, dx
 
 
 def linear(x, w):

@@ -396,3 +396,30 @@ def test_stage1_networks_forward_and_l1_gradients_match_oracle():
     # Bound: cosine >= 0.95 for every probed parameter, >= 0.99 next to the loss.
     assert max(errs.values()) <= 0.30, errs
     assert errs["G.ToRGB.conv.weight"] <= GRAD_TOL_DEEP and errs["G.UpsamplingResBlock64.conv2.epi1.style_mod.lin.weight"] <= GRAD_TOL_DEEP
+
+
+def test_linear_forward_backward_and_second_order():
+    """ppst_linear / _dgrad / _wgrad closure against torch (f32): first derivatives and a gradient-penalty second derivative."""
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(13)
+    for (m, k, n) in [(8, 2048, 512), (3, 512, 1), (16, 260, 2048)]:
+        x = torch.randn(m, k, generator=g).cuda()
+        w = (torch.randn(n, k, generator=g) / math.sqrt(k)).cuda()
+        gy = torch.randn(m, n, generator=g).cuda()
+        xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        yr = xr @ wr.t()
+        yr.backward(gy)
+        xb, wb = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = train.linear(xb, wb)
+        y.backward(gy)
+        assert rel_l2(y, yr) <= 1e-5 and rel_l2(xb.grad, xr.grad) <= 1e-5 and rel_l2(wb.grad, wr.grad) <= 1e-5, (m, k, n)
+    m, k, n = 4, 64, 32
+    x = torch.randn(m, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).cuda()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    gx, = torch.autograd.grad((torch.tanh(xr @ wr.t())).sum(), [xr], create_graph=True)
+    gx.pow(2).sum().backward()
+    xb, wb = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    gxb, = torch.autograd.grad((torch.tanh(train.linear(xb, wb))).sum(), [xb], create_graph=True)
+    gxb.pow(2).sum().backward()
+    assert rel_l2(gxb, gx) <= 1e-5 and rel_l2(wb.grad, wr.grad) <= 1e-4 and rel_l2(xb.grad, xr.grad) <= 1e-4
