@@ -11,6 +11,8 @@ import argparse, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 
 def timed(fn, steps, warm=2):
     for _ in range(warm):
