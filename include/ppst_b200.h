@@ -327,6 +327,11 @@ PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in
                   int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
                   const float* b, float slope, void* stream);
 
+/* Adjoint of ppst_resample mode 0 at scale exactly 2 (the bilinear x2 skip of UpsamplingResnetBlock, generator.py:75) for
+ * the training path: g NHWC [n, 2h, 2w, c] -> gin NHWC [n, h, w, c], as a gather with a fixed summation order
+ * (deterministic; ATen's upsample_bilinear2d_backward scatters with atomics).  bf16 (c % 8 == 0) or f32 (c % 4 == 0). */
+PPST_API int ppst_bilinear2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * small dense layers and vector normalisation (f32)
  * ------------------------------------------------------------------------------------------- */

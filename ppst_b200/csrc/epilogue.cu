@@ -724,3 +724,82 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
   PPST_LAUNCH_CHECK("resample_kernel");
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Adjoint of the bilinear x2 upsampling (F.interpolate(scale_factor=2, mode="bilinear", align_corners=False),
+// generator.py:75) for the training path: gin[n, i, j, :] = sum over the <= 4 x 4 output pixels that read input (i, j),
+// as a GATHER (one thread per input pixel and 16-byte channel vector, fixed summation order) -- deterministic, unlike the
+// scatter-with-atomics form.  Per axis, output 2i reads inputs (i-1: 0.25, i: 0.75) and output 2i+1 reads (i: 0.75,
+// i+1: 0.25), with the source coordinate clamped at both ends, so input i collects
+//   0.25 * g[2i-1] + 0.75 * g[2i] + 0.75 * g[2i+1] + 0.25 * g[2i+2]      (+0.25 * g[0] at i = 0, +0.25 * g[2L-1] at i = L-1).
+namespace ppst {
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear2x_backward_kernel(T* __restrict__ gin, const T* __restrict__ g, int64_t n,
+                                                                  int h, int w, int c) {
+  constexpr int VEC = Vec16<T>::N;
+  const int cv = c / VEC;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n * h * w * cv;
+  if (idx >= total) return;
+  const int v = (int)(idx % cv);
+  int64_t r = idx / cv;
+  const int j = (int)(r % w); r /= w;
+  const int i = (int)(r % h);
+  const int64_t ni = r / h;
+  const int oh = 2 * h, ow = 2 * w;
+  // the (up to) four output rows / columns touching input i / j and their weights
+  int ys[4], xs[4];
+  float wy[4], wx[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int oy = 2 * i - 1 + t, ox = 2 * j - 1 + t;
+    const float base = (t == 0 || t == 3) ? 0.25f : 0.75f;
+    ys[t] = oy; xs[t] = ox;
+    wy[t] = (oy >= 0 && oy < oh) ? base : 0.0f;
+    wx[t] = (ox >= 0 && ox < ow) ? base : 0.0f;
+  }
+  // clamping: output 0 puts its whole weight on input 0, output 2L-1 on input L-1
+  if (i == 0) wy[1] = 1.0f;
+  if (i == h - 1) wy[2] = 1.0f;
+  if (j == 0) wx[1] = 1.0f;
+  if (j == w - 1) wx[2] = 1.0f;
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+  const T* gb = g + (ni * oh * ow) * (int64_t)c + (int64_t)v * VEC;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (wy[a] == 0.0f) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (wx[b] == 0.0f) continue;
+      const Vec16<T> gv = ld_vec16(gb + ((int64_t)ys[a] * ow + xs[b]) * c);
+      const float wgt = wy[a] * wx[b];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] = fmaf(wgt, Cvt<T>::to_f(gv.v[e]), acc[e]);
+    }
+  }
+  Vec16<T> o;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) o.v[e] = Cvt<T>::from_f(acc[e]);
+  st_vec16(gin + ((ni * h + i) * w + j) * (int64_t)c + (int64_t)v * VEC, o);
+}
+}  // namespace ppst
+
+extern "C" int ppst_bilinear2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(gin && g && n > 0 && h > 0 && w > 0 && c > 0, PPST_ERR_ARG, "bilinear2x_backward: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "bilinear2x_backward: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0, PPST_ERR_UNSUPPORTED, "bilinear2x_backward: c=%d must be a multiple of %d", c, vec);
+  const int64_t total = n * h * w * (c / vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16)
+    bilinear2x_backward_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (__nv_bfloat16*)gin, (const __nv_bfloat16*)g, n, h, w, c);
+  else
+    bilinear2x_backward_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((float*)gin, (const float*)g, n, h, w, c);
+  PPST_LAUNCH_CHECK("bilinear2x_backward_kernel");
+  return 0;
+}

@@ -633,6 +633,30 @@ def reflect_pad(x, pad):
     return _ReflectPad.apply(x, tuple(int(p) for p in pad))
 
 
+class _Bilinear2x(Function):
+    """F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) on NHWC bf16 (the skip of UpsamplingResnetBlock,
+    generator.py:63-77): forward ppst_resample, backward its adjoint as a deterministic gather (ppst_bilinear2x_backward)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _nhwc(x)
+        ctx.shape = x.shape
+        return ops.resample(x, (2 * x.shape[1], 2 * x.shape[2]), 0, out_dtype=torch.bfloat16)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = _nhwc(g)
+        n, h, w, c = ctx.shape
+        gin = torch.empty((n, h, w, c), device=g.device, dtype=torch.bfloat16)
+        check(_lib.load().ppst_bilinear2x_backward(ptr(gin), ptr(g), n, h, w, c, dt(g), stream()))
+        return gin
+
+
+def bilinear2x(x):
+    return _Bilinear2x.apply(x)
+
+
 # ------------------------------------------------------------------------------------------------ discriminator
 class _Fold(Function):
     """Stencil product of a conv weight with the blur kernel (ppst_fold_fir) -- linear in w, so the backward is the
@@ -782,3 +806,27 @@ def allreduce_grads_(params, world=None):
     """See sharding.allreduce_grads_ (one flat bucket, one all-reduce, averaged)."""
     from .sharding import allreduce_grads_ as f
     return f(params, world)
+
+
+def capture_step(body, zero_grad, generators=(), warmup=2):
+    """Capture one training step -- forward, autograd backward (its tape is replayed as recorded), weight preparation,
+    noise draws, gradient all-reduce, optimiser (must be `capturable=True`) -- into a CUDA graph and return it; replaying
+    costs one host call instead of the ~2500 launches of a generator step.  `body()` must read its batch from tensors that
+    stay alive (copy_ the next batch into them before graph.replay()); `zero_grad()` is called before every warm-up
+    iteration and before the capture (use set_to_none=True so the gradients are allocated inside the graph's pool);
+    `generators`: torch.Generator objects drawn from inside `body` (registered so every replay advances them)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            zero_grad()
+            body()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    for gen in generators:
+        if gen is not None:
+            graph.register_generator_state(gen)
+    zero_grad()
+    with torch.cuda.graph(graph):
+        body()
+    return graph

@@ -7,7 +7,7 @@ state_dict keys (E1.* / E2.* / G.*), activations are NHWC 
 is a differentiable wrapper around the C-ABI kernels (ppst_b200/train.py): tcgen05 convolution forward / input gradient /
 weight gradient (plain, strided with the blur folded in, transposed for the fused upscale), InstanceNorm + StyleMod as
 statistics + one apply pass each way, the thin RGB layers, the residual joins.  What still runs as ATen kernels on
-channels-last views: bilinear / nearest x2 resampling of the skip paths, the global average / max pooling of the colour
+channels-last views: the nearest x2 of the one block below the fused-upscale threshold, the global average / max pooling of the colour
 encoder's heads, and everything that is [n, c]-sized (style linears' bias adds, normalisations, losses).
 
 Covers what training stage 1 executes: E1, E2 without the correlation / mask branches, G without feature extraction.
@@ -54,10 +54,24 @@ class ParamSet(torch.nn.Module):
         return out
 
 
+_consts = {}
+
+
+def _const(name, device, make):
+    """Small constant tensors (FIR kernels), created once per device -- not inside a CUDA-graph capture."""
+    key = (name, str(device))
+    t = _consts.get(key)
+    if t is None:
+        t = _consts[key] = make().to(device).contiguous()
+    return t
+
+
 def _k121(device):
-    k = torch.tensor([1.0, 2.0, 1.0], device=device)
-    k = k[None, :] * k[:, None]
-    return (k / k.sum()).contiguous()
+    def make():
+        k = torch.tensor([1.0, 2.0, 1.0])
+        k = k[None, :] * k[:, None]
+        return k / k.sum()
+    return _const("k121", device, make)
 
 
 def _eq(w):
@@ -138,13 +152,10 @@ def encoder_col(P, img):
 
 # ------------------------------------------------------------------------------------------------ generator
 def _resize2(x, mode):
-    """x2 nearest / bilinear (align_corners=False) of an NHWC tensor through a channels-last view (ATen)."""
-    v = x.permute(0, 3, 1, 2)
-    if mode == "nearest":
-        v = F.interpolate(v, scale_factor=2, mode="nearest")
-    else:
-        v = F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=False)
-    return v.permute(0, 2, 3, 1)
+    """x2 nearest (Upscale2d, stylegan2_layers.py:88-105: the 32 -> 64 block below the fused-upscale threshold) of an NHWC
+    tensor through a channels-last view (ATen; forward and backward are gathers)."""
+    assert mode == "nearest"
+    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
 
 
 def _styled(P, p, x, code, upsample, noise_gen, noises=None):
@@ -162,7 +173,7 @@ def _styled(P, p, x, code, upsample, noise_gen, noises=None):
         noise = torch.randn((n, oh, ow), device=x.device, generator=noise_gen) * P[p + "noise.weight"].view(())
     if upsample and min(h, wd) * 2 >= 128:
         # W' = 2x2 box sum of the zero-padded transposed weight -> conv_transpose2d(stride 2, padding 1) (:312-321)
-        wt = train._fold(w.permute(1, 0, 2, 3), torch.ones(2, 2, device=w.device))      # [ci, co, 4, 4]
+        wt = train._fold(w.permute(1, 0, 2, 3), _const("box2", w.device, lambda: torch.ones(2, 2)))   # [ci, co, 4, 4]
         y = train.conv_transpose2d(x, wt, 2, 1, (oh, ow), bias=bias, act=True, noise=noise)
     else:
         if upsample:
@@ -195,7 +206,7 @@ def generator(P, sp, codes, noise_gen=None, noises=None):
         p = "UpsamplingResBlock%d." % res
         code = codes[-2 - j]
         skip = train.conv2d(x, _eq(P[p + "skip.Conv.weight"]), 1, 0, bias=P[p + "skip.Act.bias"], act=True) if cin != cout else x
-        skip = _resize2(skip, "bilinear")
+        skip = train.bilinear2x(skip)
         r = _styled(P, p + "conv1.", x, code, True, noise_gen, noises)
         r = _styled(P, p + "conv2.", r, code, False, noise_gen, noises)
         x = train.add_scale(skip, r, 1.0 / SQRT2)

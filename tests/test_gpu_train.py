@@ -423,3 +423,83 @@ def test_linear_forward_backward_and_second_order():
     gxb, = torch.autograd.grad((torch.tanh(train.linear(xb, wb))).sum(), [xb], create_graph=True)
     gxb.pow(2).sum().backward()
     assert rel_l2(gxb, gx) <= 1e-5 and rel_l2(wb.grad, wr.grad) <= 1e-4 and rel_l2(xb.grad, xr.grad) <= 1e-4
+
+
+def test_stage1_graph_replay_trains_like_eager_steps():
+    """train.capture_step: a generator step (E1, E2, G, D, L1 + GAN losses, Adam) replayed from a CUDA graph moves the
+    parameters like the same number of eager steps, and the loss goes down."""
+    from oracle import ppst_oracle as O
+    from ppst_b200 import train, train_nets as TN
+    sdE1, sdE2, sdG = O.make_networks(0)
+    size, n = 256, 2
+    real = O.make_portraits(n, size, size, seed=31, smooth=True).cuda()
+
+    def build():
+        D = train.Discriminator(size, 2.0)
+        D.load_reference_state_dict(O.make_discriminator(size, seed=0))
+        m = TN.Stage1(sdE1, sdE2, sdG, D, noise_seed=None).cuda()
+        for p in D.parameters():
+            p.requires_grad_(False)
+        opt = torch.optim.Adam(m.g_params(), lr=1e-3, betas=(0.0, 0.99), fused=True, capturable=True)
+        return m, opt
+
+    losses_seen = []
+
+    def make_body(m, opt, log=None):
+        def body():
+            losses, _ = m.generator_losses(real)
+            total = sum(losses.values())
+            total.backward()
+            opt.step()
+            if log is not None:
+                log.append(total.detach())
+        return body
+
+    ma, oa = build()
+    body_a = make_body(ma, oa, losses_seen)
+    for _ in range(5):
+        oa.zero_grad(set_to_none=True)
+        body_a()
+    vals = [float(v) for v in losses_seen]
+    assert vals[-1] < vals[0], vals
+    # 2 steps eagerly vs 1 warm-up step + 1 replay.  Not bit-comparable: the ATen pieces of the step (bilinear backward:
+    # atomics) make even two EAGER runs differ, and Adam's first steps are ~lr * sign(g), so near-zero gradients step either
+    # way (eager vs eager: displacement cosine 0.984 after 2 steps) -- compare displacements
+    ma, oa = build()
+    body_a = make_body(ma, oa)
+    for _ in range(2):
+        oa.zero_grad(set_to_none=True)
+        body_a()
+    mb, ob = build()
+    graph = train.capture_step(make_body(mb, ob), lambda: ob.zero_grad(set_to_none=True), warmup=1)
+    graph.replay()
+    torch.cuda.synchronize()
+
+    def cos(pa, pb, init):
+        da, db = (pa.detach().cpu() - init).flatten(), (pb.detach().cpu() - init).flatten()
+        return float((da * db).sum() / (da.norm() * db.norm()).clamp_min(1e-30))
+    for k in ("UpsamplingResBlock64.conv2.conv.weight", "HeadResnetBlock0.conv1.conv.weight", "ToRGB.conv.weight"):
+        c = cos(ma.G[k], mb.G[k], sdG[k])
+        assert c >= 0.95, (k, c)
+        assert float((mb.G[k].detach().cpu() - sdG[k]).abs().max()) > 0            # the replay did move the weights
+    assert cos(ma.E1["FromRGB.Conv.weight"], mb.E1["FromRGB.Conv.weight"], sdE1["FromRGB.Conv.weight"]) >= 0.95
+
+
+def test_bilinear2x_forward_and_deterministic_adjoint():
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(14)
+    for (n, h, w, c) in [(2, 16, 24, 64), (1, 1, 5, 8), (2, 7, 3, 32)]:
+        x = _bf(torch.randn(n, h, w, c, generator=g)).cuda()
+        gy = _bf(torch.randn(n, 2 * h, 2 * w, c, generator=g)).cuda()
+        xr = _nchw(x).requires_grad_(True)
+        yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+        yr.backward(_nchw(gy))
+        xb = x.to(torch.bfloat16).requires_grad_(True)
+        y = train.bilinear2x(xb)
+        y.backward(gy.to(torch.bfloat16))
+        assert rel_l2(_nchw(y), yr) <= 5e-3, (n, h, w, c)
+        assert rel_l2(_nchw(xb.grad), xr.grad) <= 5e-3, (n, h, w, c, rel_l2(_nchw(xb.grad), xr.grad))
+        g2 = xb.grad.clone()
+        xb.grad = None
+        train.bilinear2x(xb).backward(gy.to(torch.bfloat16))
+        assert torch.equal(g2, xb.grad)
