@@ -171,6 +171,33 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train(args):
+    """BASELINE configs[4] (training step, DDP with NCCL gradient all-reduce at 1/2/4/8 GPUs): training stage 1 at 256^2,
+    8 images per GPU (weak scaling) -- generator step (E1, E2, G forward + backward, D forward + input gradient), discriminator
+    step, R1 step on every 16th iteration, Adam, one flat NCCL all-reduce per step; CUDA-graph replay.  Measured by
+    tools/train_bench.py (same code, more detail); this wrapper prints the bench.py-shaped line."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("train_bench", os.path.join(ROOT, "tools", "train_bench.py"))
+    tb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tb)
+    a = types.SimpleNamespace(size=256, batch=8, steps=max(4, min(args.steps, 10)), no_torch=True, stage1=True, return_dict=True)
+    out = tb.stage1(a)
+    if out is None:
+        return
+    line = {"metric": "training images/s @256^2 (stage 1: G step + D step + R1/16)", "value": out["images_per_s"],
+            "unit": "images/s", "n_gpus": out["n_gpus"], "steps": a.steps, "warmup": 2, "ms_per_step": out["iteration_ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "C5 (BASELINE configs[4]): " + out["workload"], "batch_per_gpu": a.batch, "size": a.size,
+                       "parallelism": "data parallel, one flat NCCL gradient all-reduce per step",
+                       "grad_allreduce_bytes": out["grad_allreduce_bytes"]},
+            "e2e": {"value": out["e2e_images_per_s"], "unit": "images/s", "h2d_bytes_per_step": out["h2d_bytes_per_iteration"],
+                    "d2h_bytes_per_step": out["d2h_bytes_per_iteration"], "ms_per_step": out["iteration_e2e_ms"]},
+            "gpu_launches": out["launches_g_d_r1"] * a.steps, "step_ms": out["graph_ms"], "eager_step_ms": out["ms"],
+            "kernels": out["kernels_g_plus_d"]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,9 +206,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="(content, style) pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="swap", choices=["swap", "train"],
+                    help="swap: the headline metric (BASELINE configs[1]); train: configs[4], training stage 1 at 256^2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     from ppst_b200 import sharding
     world, rank, local_rank = sharding.init()

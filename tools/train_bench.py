@@ -92,9 +92,13 @@ def stage1(args):
         cg = torch.optim.Adam(g_params, lr=2e-3, betas=(0.0, 0.99), fused=True, capturable=True)
         cd = torch.optim.Adam(d_params, lr=2e-3, betas=(0.0, 0.99), fused=True, capturable=True)
 
+        loss_buf = torch.zeros(1, device=dev)
+
         def body_g():
             losses, _ = m.generator_losses(real)
-            sum(losses.values()).backward()
+            total = sum(losses.values())
+            total.backward()
+            loss_buf.copy_(total.detach().reshape(1))
             sharding.allreduce_grads_(g_params, world)
             cg.step()
 
@@ -121,6 +125,21 @@ def stage1(args):
             p.requires_grad_(True)
         sharding.barrier()
         ms_graph = {k: sharding.max_over_ranks(timed(g.replay, args.steps), device=dev) for k, g in graphs.items()}
+        # end to end: every iteration copies its batch from pinned host memory into the graphs' static input and reads the
+        # generator loss back (R1 on every 16th iteration, as the reference's optimiser schedules it)
+        real_pin = real.cpu().pin_memory()
+        loss_pin = torch.zeros(1).pin_memory()
+        it = [0]
+
+        def iteration():
+            real.copy_(real_pin, non_blocking=True)
+            graphs["g_step"].replay()
+            graphs["d_step"].replay()
+            if it[0] % 16 == 0:
+                graphs["r1_step"].replay()
+            it[0] += 1
+            loss_pin.copy_(loss_buf, non_blocking=True)
+        ms_graph["iteration_e2e"] = sharding.max_over_ranks(timed(iteration, 16, warm=1), device=dev)
     except Exception as e:                                       # report the eager numbers only
         ms_graph = {"error": str(e).split("\n")[0][:200]}
         for p in d_params:
@@ -128,14 +147,17 @@ def stage1(args):
     # one iteration of the reference's loop = G step + D step, R1 every 16th iteration (R1_once_every, ppst_optimizer.py)
     best = ms_graph if (ms_graph and "error" not in ms_graph) else ms
     it_ms = best["g_step"] + best["d_step"] + best["r1_step"] / 16.0
+    e2e_ms = ms_graph.get("iteration_e2e") if isinstance(ms_graph.get("iteration_e2e"), float) else None
     out = {"workload": "training stage 1 @%d^2, batch %d per GPU: G step (E1+E2+G+D), D step, R1 every 16th" % (args.size, args.batch),
            "n_gpus": world, "scaling": "weak", "images_per_s": round(world * args.batch / (it_ms * 1e-3), 1),
            "ms": {k: round(v, 2) for k, v in ms.items()},
            "graph_ms": {k: (round(v, 2) if isinstance(v, float) else v) for k, v in ms_graph.items()},
-           "iteration_ms": round(it_ms, 2),
+           "iteration_ms": round(it_ms, 2), "iteration_e2e_ms": round(e2e_ms, 2) if e2e_ms else None,
+           "e2e_images_per_s": round(world * args.batch / (e2e_ms * 1e-3), 1) if e2e_ms else None,
+           "h2d_bytes_per_iteration": int(real.numel() * 4), "d2h_bytes_per_iteration": 4,
            "grad_allreduce_bytes": bucket, "launches_g_d_r1": launches, "kernels_g_plus_d": kern}
     if rank != 0:
-        return
+        return None
     if not args.no_torch and world == 1:
         def leaf(sd):
             return {k: (v.to(dev).requires_grad_(True) if (v.is_floating_point() and not k.endswith("kernel")) else v.to(dev)) for k, v in sd.items()}
@@ -161,6 +183,8 @@ def stage1(args):
             tdopt.step()
         out["torch_cudnn_tf32_ms"] = {"g_step": round(timed(t_g, max(2, args.steps // 2), warm=1), 2),
                                       "d_step": round(timed(t_d, max(2, args.steps // 2), warm=1), 2)}
+    if getattr(args, "return_dict", False):
+        return out
     print(json.dumps(out), flush=True)
 
 
