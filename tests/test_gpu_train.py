@@ -503,3 +503,27 @@ def test_bilinear2x_forward_and_deterministic_adjoint():
         xb.grad = None
         train.bilinear2x(xb).backward(gy.to(torch.bfloat16))
         assert torch.equal(g2, xb.grad)
+
+
+def test_discriminator_512_and_stage1_256_forward_match_oracle():
+    """The sizes the reference trains at: D at crop 512 (first layer 3 -> 64) and the stage-1 reconstruction at 256^2."""
+    from oracle import ppst_oracle as O
+    from ppst_b200 import train, train_nets as TN
+    x = O.make_portraits(1, 512, 512, seed=41, smooth=True)
+    sdD = O.make_discriminator(512, seed=1)
+    D = train.Discriminator(512, 2.0).cuda()
+    D.load_reference_state_dict(sdD)
+    with torch.no_grad():
+        want = O.discriminator(sdD, x)
+        got = D(x.cuda()).cpu()
+    assert (got - want).abs().max() <= 2e-2 * max(1.0, float(want.abs().max())), (got, want)
+    sdE1, sdE2, sdG = O.make_networks(0)
+    real = O.make_portraits(1, 256, 256, seed=42, smooth=True)
+    noises = O.make_noises(1, 256, 256, seed=6)
+    with torch.no_grad():
+        rec_r = O.generator(sdG, O.encoder_con(sdE1, real), O.encoder_col(sdE2, real)[0], noises=noises)
+        E1, E2, G = TN.ParamSet(sdE1).cuda(), TN.ParamSet(sdE2).cuda(), TN.ParamSet(sdG).cuda()
+        rec = TN.generator(G, TN.encoder_con(E1, real.cuda()), TN.encoder_col(E2, real.cuda()), noises=noises).cpu()
+    peak = float(rec_r.max() - rec_r.min())
+    psnr = 10 * math.log10(peak * peak / float(((rec - rec_r) ** 2).mean()))
+    assert psnr >= 45.0, psnr                      # north_star's bf16 output bound
