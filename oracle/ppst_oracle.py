@@ -586,10 +586,10 @@ def fold_fir(w, k):
     return out.view(co, ci, kh + k.shape[0] - 1, kw + k.shape[1] - 1)
 
 
-def discriminator_bf16_emulation(sd, x, prefix="stylegan2_D."):
+def discriminator_bf16_emulation(sd, x, prefix="stylegan2_D.", fold_blur=False):
     """NOT a restatement of the reference: the discriminator with the PRODUCT's bf16 rounding points (weights of the
-    tensor-core convolutions, every stored activation, every stored activation gradient) and its blur-folded stride-2
-    convolutions, in torch fp32 arithmetic.  Second checker for the training tests: against the fp32 reference a bf16
+    tensor-core convolutions, every stored activation incl. the blurred maps, every stored activation gradient; fold_blur:
+    the product's alternative with the blur folded into 6x6 / 4x4 stride-2 convolutions), in torch fp32 arithmetic.  Second checker for the training tests: against the fp32 reference a bf16
     network differs mostly by leaky-ReLU branch flips of near-zero activations (several % in rel-L2 after 16 layers);
     against this emulation the flips coincide and what is left is accumulation order."""
     size = x.shape[-1]
@@ -600,9 +600,14 @@ def discriminator_bf16_emulation(sd, x, prefix="stylegan2_D."):
         p = prefix + name + "."
         s3 = 1.0 / math.sqrt(c * 9)
         y = _q(fused_leaky_relu(F.conv2d(out, _q(sd[p + "conv1.Conv.weight"] * s3), padding=1), sd[p + "conv1.Act.bias"]))
-        y = _q(fused_leaky_relu(F.conv2d(y, _q(fold_fir(sd[p + "conv2.Conv.weight"] * s3, blur)), stride=2, padding=2),
-                                sd[p + "conv2.Act.bias"]))
-        sk = _q(F.conv2d(out, _q(fold_fir(sd[p + "skip.Conv.weight"] * (1.0 / math.sqrt(c)), blur)), stride=2, padding=1))
+        if fold_blur:
+            y = _q(fused_leaky_relu(F.conv2d(y, _q(fold_fir(sd[p + "conv2.Conv.weight"] * s3, blur)), stride=2, padding=2),
+                                    sd[p + "conv2.Act.bias"]))
+            sk = _q(F.conv2d(out, _q(fold_fir(sd[p + "skip.Conv.weight"] * (1.0 / math.sqrt(c)), blur)), stride=2, padding=1))
+        else:
+            y = _q(fused_leaky_relu(F.conv2d(_q(upfirdn2d(y, blur, pad=(2, 2))), _q(sd[p + "conv2.Conv.weight"] * s3), stride=2),
+                                    sd[p + "conv2.Act.bias"]))
+            sk = _q(F.conv2d(_q(upfirdn2d(out, blur, pad=(1, 1))), _q(sd[p + "skip.Conv.weight"] * (1.0 / math.sqrt(c))), stride=2))
         out = _q((y + sk) / SQRT2)
     c = out.shape[1]
     out = _q(fused_leaky_relu(F.conv2d(out, _q(sd[prefix + "final_conv.Conv.weight"] * (1.0 / math.sqrt(c * 9))), padding=1),

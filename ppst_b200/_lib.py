@@ -49,6 +49,7 @@ _SIGS = {
                                     c_float, c_float, c_int, c_void_p]),
     "ppst_bias_grad_reduce": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),
     "ppst_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 14 + [c_void_p]),
+    "ppst_blur_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 11 + [c_void_p]),
     "ppst_plane_reduce_scratch_elems": (c_i64, [c_i64, c_i64, c_i64, c_int]),
     "ppst_plane_reduce": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_upsample_reduce_scratch_elems": (c_i64, [c_i64, c_int, c_int]),

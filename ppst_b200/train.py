@@ -633,6 +633,36 @@ def reflect_pad(x, pad):
     return _ReflectPad.apply(x, tuple(int(p) for p in pad))
 
 
+class _Blur(Function):
+    """Blur (upfirdn2d, up = down = 1) on NHWC bf16: pads (p0 before, p1 after) on both axes.  Linear, so the backward is the
+    adjoint blur (unflipped kernel, pads k-1-p) and the backward of that is the blur again (second order for R1)."""
+
+    @staticmethod
+    def forward(ctx, x, k, p0, p1, flip):
+        x = _nhwc(x)
+        n, h, w, c = x.shape
+        kh, kw = k.shape
+        ctx.save_for_backward(k)
+        ctx.cfg = (p0, p1, flip)
+        out = torch.empty((n, h + p0 + p1 - kh + 1, w + p0 + p1 - kw + 1, c), device=x.device, dtype=torch.bfloat16)
+        with ops._Prof("blur_nhwc", (x.numel() + out.numel()) * 2):
+            check(_lib.load().ppst_blur_nhwc(ptr(out), ptr(x), ptr(k), n, h, w, c, kh, kw, p0, p1, p0, p1, 1 if flip else 0,
+                                             dt(x), stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        k, = ctx.saved_tensors
+        p0, p1, flip = ctx.cfg
+        kh = k.shape[0]
+        return _Blur.apply(g, k, kh - 1 - p0, kh - 1 - p1, not flip), None, None, None, None
+
+
+def blur(x, k, pad):
+    """upfirdn2d(x, k, pad=(p0, p1)) for an NHWC bf16 tensor and a square FIR kernel k (f32 [kh, kh], device)."""
+    return _Blur.apply(x, k, int(pad[0]), int(pad[1]), True)
+
+
 class _Bilinear2x(Function):
     """F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) on NHWC bf16 (the skip of UpsamplingResnetBlock,
     generator.py:63-77): forward ppst_resample, backward its adjoint as a deterministic gather (ppst_bilinear2x_backward)."""
@@ -692,13 +722,15 @@ class Discriminator(torch.nn.Module):
     unchanged.  forward(x): NCHW f32 image [n,3,S,S] -> [n,1] f32.
 
     Layer by layer: ConvLayer(3,C,1)+FusedLeakyReLU = one thin kernel; every ConvLayer = one tcgen05 convolution with the
-    bias + leaky-ReLU epilogue; Blur([1,3,3,1]) + stride-2 conv are folded into one 6x6 (main) / 4x4 (skip) stride-2
-    convolution whose zero padding is TMA out-of-bounds fill; the residual join is one pass; the two EqualLinear layers run
-    on ppst_linear."""
+    bias + leaky-ReLU epilogue; Blur([1,3,3,1]) = ppst_blur_nhwc in front of the 3x3 / 1x1 stride-2 convolution
+    (fold_blur=True: folded into ONE 6x6 / 4x4 stride-2 convolution instead -- saves the blur's HBM passes but quadruples
+    those layers' tensor FLOPs, slower at these channel counts); the residual join is one pass; the two EqualLinear layers
+    run on ppst_linear."""
 
-    def __init__(self, size, channel_multiplier=2, blur_kernel=(1, 3, 3, 1)):
+    def __init__(self, size, channel_multiplier=2, blur_kernel=(1, 3, 3, 1), fold_blur=False):
         super().__init__()
         nn = torch.nn
+        self.fold_blur = fold_blur
         channels = {4: 512, 8: 512, 16: min(512, int(512 * channel_multiplier)), 32: min(512, int(512 * channel_multiplier)),
                     64: int(256 * channel_multiplier), 128: int(128 * channel_multiplier), 256: int(64 * channel_multiplier),
                     512: int(32 * channel_multiplier), 1024: int(16 * channel_multiplier)}
@@ -761,10 +793,18 @@ class Discriminator(torch.nn.Module):
         for name, c, co in self.blocks:
             s3 = 1.0 / math.sqrt(c * 9)
             y = conv2d(x, p(name + ".conv1.Conv.weight") * s3, 1, 1, p(name + ".conv1.Act.bias"), act=True)
-            w6 = _fold(p(name + ".conv2.Conv.weight") * s3, self.blur)                       # [co, c, 6, 6]
-            y = conv2d(y, w6, 2, 2, p(name + ".conv2.Act.bias"), act=True)
-            w4 = _fold(p(name + ".skip.Conv.weight") * (1.0 / math.sqrt(c)), self.blur)     # [co, c, 4, 4]
-            sk = conv2d(x, w4, 2, 1)
+            if self.fold_blur:
+                w6 = _fold(p(name + ".conv2.Conv.weight") * s3, self.blur)                       # [co, c, 6, 6]
+                y = conv2d(y, w6, 2, 2, p(name + ".conv2.Act.bias"), act=True)
+                w4 = _fold(p(name + ".skip.Conv.weight") * (1.0 / math.sqrt(c)), self.blur)     # [co, c, 4, 4]
+                sk = conv2d(x, w4, 2, 1)
+            else:
+                # Blur(pad (2,2)) -> 3x3 stride 2 and Blur(pad (1,1)) -> 1x1 stride 2, with ONE more zero row / column of
+                # padding after the image: no tap of the strided convolution reads the extra blurred row, and the even size
+                # lets the input gradient run as four sub-pixel phases
+                y = conv2d(blur(y, self.blur, (2, 3)), p(name + ".conv2.Conv.weight") * s3, 2, 0,
+                           p(name + ".conv2.Act.bias"), act=True)
+                sk = conv2d(blur(x, self.blur, (1, 2)), p(name + ".skip.Conv.weight") * (1.0 / math.sqrt(c)), 2, 0)
             x = add_scale(y, sk, 1.0 / SQRT2)
         c = x.shape[3]
         x = conv2d(x, p("final_conv.Conv.weight") * (1.0 / math.sqrt(c * 9)), 1, 1, p("final_conv.Act.bias"), act=True)

@@ -35,6 +35,8 @@ GEOMS = [  # (k, stride, pad, cin, cout, n, h, w)
     (3, 1, 0, 64, 64, 2, 18, 34),          # valid conv (the encoders' reflect-padded inputs)
     (6, 2, 2, 64, 128, 2, 32, 48),         # Blur[1,3,3,1] folded into conv2 of a discriminator ResBlock
     (4, 2, 1, 64, 256, 2, 16, 32),         # Blur folded into the 1x1 stride-2 skip
+    (3, 2, 0, 64, 128, 2, 34, 50),         # the unfolded stride-2 convolutions behind ppst_blur_nhwc
+    (1, 2, 0, 64, 128, 2, 32, 48),
     (3, 1, 1, 256, 256, 1, 64, 64),
     (3, 1, 1, 512, 512, 2, 8, 8),          # tiny maps (the 4x4 / 8x8 end of the discriminator)
     (3, 1, 1, 512, 512, 2, 4, 4),
@@ -253,8 +255,8 @@ def test_discriminator_matches_bf16_emulation():
     size = 256
     D, sd = _make_d(size)
     g = torch.Generator().manual_seed(123)
-    real = torch.rand(2, 3, size, size, generator=g) * 2 - 1
-    fake = torch.rand(2, 3, size, size, generator=g) * 2 - 1
+    real = torch.rand(4, 3, size, size, generator=g) * 2 - 1          # 4 + 4 samples: less head-flip noise than the fixture's 2 + 2
+    fake = torch.rand(4, 3, size, size, generator=g) * 2 - 1
     keys = ["stylegan2_D." + k for k in D_KEYS]
 
     def leaf_sd():
@@ -527,3 +529,27 @@ def test_discriminator_512_and_stage1_256_forward_match_oracle():
     peak = float(rec_r.max() - rec_r.min())
     psnr = 10 * math.log10(peak * peak / float(((rec - rec_r) ** 2).mean()))
     assert psnr >= 45.0, psnr                      # north_star's bf16 output bound
+
+
+def test_blur_nhwc_matches_upfirdn2d_and_is_self_adjoint_to_second_order():
+    from oracle import ppst_oracle as O
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(15)
+    for taps, pad in (([1, 3, 3, 1], (2, 3)), ([1, 3, 3, 1], (1, 2)), ([1, 2, 1], (0, 0)), ([1, 2, 1], (1, 1))):
+        k = O.make_kernel(taps)
+        x = _bf(torch.randn(2, 18, 26, 32, generator=g))
+        want = O.upfirdn2d(x.permute(0, 3, 1, 2), k, pad=pad)                  # NCHW oracle
+        xb = x.cuda().to(torch.bfloat16).requires_grad_(True)
+        y = train.blur(xb, k.cuda(), pad)
+        assert rel_l2(_nchw(y), want) <= 5e-3, (taps, pad)
+        gy = _bf(torch.randn(y.shape, generator=g)).cuda()
+        xr = x.clone().requires_grad_(True)
+        O.upfirdn2d(xr.permute(0, 3, 1, 2), k, pad=pad).backward(_nchw(gy).cpu())
+        gx, = torch.autograd.grad(y, [xb], gy.to(torch.bfloat16), create_graph=True)
+        assert rel_l2(gx, xr.grad) <= 5e-3, (taps, pad)
+        # second order: d/d(gy) of <gx, R> is the blur of R
+        R = _bf(torch.randn(x.shape, generator=g)).cuda()
+        gyb = gy.to(torch.bfloat16).requires_grad_(True)
+        gx2, = torch.autograd.grad(train.blur(xb, k.cuda(), pad), [xb], gyb, create_graph=True)
+        d, = torch.autograd.grad((gx2.float() * R).sum(), [gyb])
+        assert rel_l2(_nchw(d), O.upfirdn2d(R.cpu().permute(0, 3, 1, 2), k, pad=pad)) <= 5e-3
