@@ -81,7 +81,7 @@ PPST_API int ppst_upfirdn2d(void* y, const void* x, const float* kernel, int64_t
  *   out[n, oy, ox, :] = sum_{ky,kx} in[n, oy + ky - py0, ox + kx - px0, :] * f[ky][kx]   (zero outside),
  * out size = in + p0 + p1 - k + 1 per axis; flip = 1: f = the flipped kernel (what ppst_upfirdn2d computes); flip = 0: the
  * kernel as given -- with pads (k-1-p0, k-1-p1) that is the adjoint (UpFirDn2dBackward, upfirdn2d.py:24-90).
- * kernel: f32 [kh, kw] device memory, at most 16 taps; bf16 (c % 8 == 0) or f32 (c % 4 == 0). */
+ * kernel: f32 [kh, kw] device memory, square, 1..4 taps per axis; bf16 (c % 8 == 0) or f32 (c % 4 == 0). */
 PPST_API int ppst_blur_nhwc(void* out, const void* in, const float* kernel, int64_t n, int in_h, int in_w, int c, int kh, int kw,
                    int py0, int py1, int px0, int px1, int flip, int dtype, void* stream);
 

@@ -457,7 +457,7 @@ extern "C" int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64
 // Everything the gradient of y = (x - mean) * rstd * (1 + s) + b needs (nn.InstanceNorm2d + StyleMod,
 // stylegan2_layers.py:361-374,414-437) follows from these two and the forward statistics.  Two stages, fixed order.
 namespace ppst {
-constexpr int kDotChunk = 4096;
+constexpr int kDotChunk = 512;           // pixels per block: (hw / 512) x n blocks keep every SM busy at 64x64 and up
 template <typename T>
 __global__ void __launch_bounds__(256) plane_dot_kernel(float* __restrict__ partials, const T* __restrict__ g,
                                                         const T* __restrict__ x, int64_t c, int64_t hw, int chunks) {
@@ -474,7 +474,25 @@ __global__ void __launch_bounds__(256) plane_dot_kernel(float* __restrict__ part
   if (lane < lanes) {
     const T* gb = g + ni * hw * c + (int64_t)col * VEC;
     const T* xb = x + ni * hw * c + (int64_t)col * VEC;
-    for (int64_t p = beg + lane; p < end; p += lanes) {
+    // four pixels per iteration: all eight 16-byte loads are issued before the first use
+    int64_t p = beg + lane;
+    for (; p + 3 * (int64_t)lanes < end; p += 4 * (int64_t)lanes) {
+      Vec16<T> gv[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        gv[u] = ld_vec16_stream(gb + (p + u * (int64_t)lanes) * c);
+        xv[u] = ld_vec16_stream(xb + (p + u * (int64_t)lanes) * c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float gf = Cvt<T>::to_f(gv[u].v[e]);
+          sg[e] += gf;
+          sx[e] = fmaf(gf, Cvt<T>::to_f(xv[u].v[e]), sx[e]);
+        }
+    }
+    for (; p < end; p += lanes) {
       const Vec16<T> gv = ld_vec16_stream(gb + p * c), xv = ld_vec16_stream(xb + p * c);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
