@@ -25,7 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # NCCL prints its version banner to STDOUT at this level;
+    os.environ["NCCL_DEBUG"] = "WARN"                          # stdout must carry exactly one JSON line (warnings stay on)
 
 import torch  # noqa: E402
 
@@ -195,6 +196,22 @@ def run_train(args):
                     "d2h_bytes_per_step": out["d2h_bytes_per_iteration"], "ms_per_step": out["iteration_e2e_ms"]},
             "gpu_launches": out["launches_g_d_r1"] * a.steps, "step_ms": out["graph_ms"], "eager_step_ms": out["ms"],
             "kernels": out["kernels_g_plus_d"]}
+    # roofline of the dominant kernels: every tcgen05 launch of a G step + D step (forward / input-gradient convolutions =
+    # ppst_conv_tc, weight gradients = ppst_conv_wgrad), CUDA events per launch in the eager profiling pass
+    peaks = load_peaks()
+    k = out["kernels_g_plus_d"]
+    tc_ms = sum(k[n]["ms"] for n in ("conv_tc", "conv_wgrad") if n in k)
+    tc_flop = sum(k[n]["ms"] * 1e-3 * (k[n]["tflops"] or 0.0) * 1e12 for n in ("conv_tc", "conv_wgrad") if n in k)
+    tc_launches = sum(k[n]["launches"] for n in ("conv_tc", "conv_wgrad") if n in k)
+    if tc_ms > 0:
+        ach = tc_flop / (tc_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "ppst_conv_tc + ppst_conv_wgrad (every launch of one G step + one D step)",
+                            "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"],
+                            "traffic": None, "algorithmic_flop_per_launch": tc_flop / max(tc_launches, 1),
+                            "launches_per_iteration": tc_launches,
+                            "peak_source": peaks["source"] + " bf16_tflops_sustained (kernels timed inside a long step)",
+                            "note": "256^2 training shapes: 32x32 .. 256x256 maps, 32 .. 512 channels, batch 8"}
+    line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
 
 

@@ -11,7 +11,8 @@ import argparse, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # the version banner goes to stdout; keep warnings only
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 
 def timed(fn, steps, warm=2):
