@@ -66,6 +66,14 @@ PPST_API int ppst_fused_bias_act(void* y, const void* x, const void* b, const vo
 PPST_API int ppst_bias_grad_reduce(float* out, const void* g, int64_t outer, int64_t size_b, int64_t step_b, int dtype,
                           void* stream);
 
+/* Backward of bias + leaky-ReLU on NHWC activations in one pass (training path): gp = g * (y > 0 ? 1 : alpha) * scale
+ * (FusedLeakyReLUFunctionBackward, fused_act.py:23-43) AND bias_grad[c] = sum over pixels of the stored gp (`grad_input.sum`,
+ * :37-42).  act = 0: no activation, gp is not written (pass NULL), bias_grad = sum of g.  g, y, gp: [pixels, c] bf16 / f32;
+ * scratch: ppst_act_grad_sum_scratch_elems(pixels, c) floats.  Deterministic. */
+PPST_API int64_t ppst_act_grad_sum_scratch_elems(int64_t pixels, int c);
+PPST_API int ppst_act_grad_sum(void* gp, float* bias_grad, const void* g, const void* y, float* scratch, int64_t pixels, int c,
+                      float alpha, float scale, int act, int dtype, void* stream);
+
 /* Replaces `upfirdn2d_op.upfirdn2d(input[major,H,W,minor], kernel, up_x, up_y, down_x, down_y,
  * pad_x0, pad_x1, pad_y0, pad_y1)` (stylegan2_op/upfirdn2d.cpp:12-23, upfirdn2d_kernel.cu:53-137,140-272).
  * Zero-insert upsample, pad (negative pads crop), FIR with the flipped `kernel` (f32 [kh,kw], device

@@ -48,6 +48,8 @@ _SIGS = {
     "ppst_fused_bias_act": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                                     c_float, c_float, c_int, c_void_p]),
     "ppst_bias_grad_reduce": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ppst_act_grad_sum_scratch_elems": (c_i64, [c_i64, c_int]),
+    "ppst_act_grad_sum": (c_int, [c_void_p] * 5 + [c_i64, c_int, c_float, c_float, c_int, c_int, c_void_p]),
     "ppst_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 14 + [c_void_p]),
     "ppst_blur_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 11 + [c_void_p]),
     "ppst_plane_reduce_scratch_elems": (c_i64, [c_i64, c_i64, c_i64, c_int]),

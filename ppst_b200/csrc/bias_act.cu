@@ -176,3 +176,105 @@ extern "C" int ppst_bias_grad_reduce(float* out, const void* g, int64_t outer, i
   PPST_LAUNCH_CHECK("bias_grad_kernel");
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Backward of bias + leaky-ReLU on NHWC activations in ONE pass (training path): gp = g * (y > 0 ? 1 : alpha) * scale
+// (FusedLeakyReLUFunctionBackward, fused_act.py:23-43; act = 0: gp = g, nothing is written) together with the bias gradient
+// sum_[pixels] gp per channel (`grad_input.sum(dim)`, :37-42) -- the reference reads the tensor twice for these.
+// Stage 1: a block owns kAgChunk pixels; thread = (16-byte channel vector, pixel lane); block partials in a fixed order.
+namespace ppst {
+constexpr int kAgChunk = 512;
+template <typename T>
+__global__ void __launch_bounds__(256) act_grad_sum_kernel(T* __restrict__ gp, float* __restrict__ partials,
+                                                           const T* __restrict__ g, const T* __restrict__ y, int64_t pixels,
+                                                           int c, float alpha, float scale, int act) {
+  extern __shared__ float red[];                         // [lanes][c]
+  constexpr int VEC = Vec16<T>::N;
+  const int cols = c / VEC, lanes = 256 / cols;
+  const int col = threadIdx.x % cols, lane = threadIdx.x / cols;
+  const int64_t beg = (int64_t)blockIdx.x * kAgChunk, end = min(beg + (int64_t)kAgChunk, pixels);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  if (lane < lanes) {
+    // four pixels per iteration: every load is issued before the first use
+    for (int64_t p0 = beg + lane; p0 < end; p0 += 4 * (int64_t)lanes) {
+      Vec16<T> gv[4], yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t p = p0 + u * (int64_t)lanes;
+        if (p < end) {
+          const int64_t off = p * c + (int64_t)col * VEC;
+          gv[u] = ld_vec16_stream(g + off);
+          if (act) yv[u] = ld_vec16_stream(y + off);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t p = p0 + u * (int64_t)lanes;
+        if (p >= end) break;
+        const int64_t off = p * c + (int64_t)col * VEC;
+        if (act) {
+          Vec16<T> o;
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float v = Cvt<T>::to_f(gv[u].v[e]);
+            o.v[e] = Cvt<T>::from_f(((Cvt<T>::to_f(yv[u].v[e]) > 0.0f) ? v : v * alpha) * scale);
+            acc[e] += Cvt<T>::to_f(o.v[e]);               // the sum of the STORED (rounded) values
+          }
+          st_vec16(gp + off, o);
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[e] += Cvt<T>::to_f(gv[u].v[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) red[(int64_t)lane * c + col * VEC + e] = acc[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(int64_t)l * c + i];
+    partials[(int64_t)blockIdx.x * c + i] = t;
+  }
+}
+
+__global__ void act_grad_sum_final(float* __restrict__ out, const float* __restrict__ partials, int64_t blocks, int c) {
+  // one warp-sized group of threads per channel would be faster; the partial count is a few thousand at most
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float t = 0.f;
+  for (int64_t b = 0; b < blocks; ++b) t += partials[b * c + ch];
+  out[ch] = t;
+}
+}  // namespace ppst
+
+extern "C" int64_t ppst_act_grad_sum_scratch_elems(int64_t pixels, int c) {
+  return ((pixels + ppst::kAgChunk - 1) / ppst::kAgChunk) * c;
+}
+
+extern "C" int ppst_act_grad_sum(void* gp, float* bias_grad, const void* g, const void* y, float* scratch, int64_t pixels, int c,
+                                 float alpha, float scale, int act, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(bias_grad && g && scratch && pixels > 0 && c > 0 && (!act || (gp && y)), PPST_ERR_ARG, "act_grad_sum: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "act_grad_sum: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0 && c / vec <= 256, PPST_ERR_UNSUPPORTED, "act_grad_sum: c=%d (a multiple of %d, at most %d)", c, vec,
+               256 * vec);
+  const int64_t blocks = (pixels + kAgChunk - 1) / kAgChunk;
+  PPST_REQUIRE(blocks < (1LL << 31), PPST_ERR_ARG, "act_grad_sum: too many pixels");
+  const size_t smem = sizeof(float) * (size_t)(256 / (c / vec)) * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16)
+    act_grad_sum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, smem, st>>>((__nv_bfloat16*)gp, scratch, (const __nv_bfloat16*)g,
+                                                                          (const __nv_bfloat16*)y, pixels, c, alpha, scale, act);
+  else
+    act_grad_sum_kernel<float><<<(unsigned)blocks, 256, smem, st>>>((float*)gp, scratch, (const float*)g, (const float*)y, pixels,
+                                                                  c, alpha, scale, act);
+  PPST_LAUNCH_CHECK("act_grad_sum_kernel");
+  act_grad_sum_final<<<(c + 127) / 128, 128, 0, st>>>(bias_grad, scratch, blocks, c);
+  PPST_LAUNCH_CHECK("act_grad_sum_final");
+  return 0;
+}

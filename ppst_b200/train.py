@@ -238,6 +238,37 @@ class _ActGrad(Function):
         return _ActGrad.apply(gg.to(y.dtype), y), None
 
 
+class _ActGradSum(Function):
+    """(gp, bias_grad) = (leaky-ReLU gradient of g selected by the saved output y, its per-channel sum over all pixels) in
+    ONE pass over the tensor (ppst_act_grad_sum); act = False: gp is g itself and only the sum is computed."""
+
+    @staticmethod
+    def forward(ctx, g, y, act):
+        g = g.contiguous()
+        n, h, w, c = g.shape
+        L = _lib.load()
+        scratch = ops._get_scratch(g.device, L.ppst_act_grad_sum_scratch_elems(n * h * w, c))
+        db = torch.empty(c, device=g.device, dtype=torch.float32)
+        gp = torch.empty_like(g) if act else g
+        with ops._Prof("act_grad_sum", g.numel() * g.element_size() * (3 if act else 1)):
+            check(L.ppst_act_grad_sum(ptr(gp) if act else None, ptr(db), ptr(g), ptr(y) if act else None, ptr(scratch),
+                                      n * h * w, c, 0.2, SQRT2, 1 if act else 0, dt(g), stream()))
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return gp, db                   # act = False: gp IS g (autograd treats a returned input as an identity view)
+
+    @staticmethod
+    def backward(ctx, ggp, gdb):
+        y, = ctx.saved_tensors
+        gg = ggp
+        if gdb is not None:
+            b = gdb.to(y.dtype).view(1, 1, 1, -1)
+            gg = b.expand(y.shape) if gg is None else gg + b
+        if gg is None:
+            return None, None, None
+        return (_ActGrad.apply(gg.contiguous(), y) if ctx.act else gg), None, None
+
+
 class _ChannelSum(Function):
     """NHWC [n,h,w,c] -> f32 [c]: the bias gradient (`grad_input.sum(dim)`, fused_act.py:37-42)."""
 
@@ -273,9 +304,12 @@ class _ConvBiasAct(Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         gy = _nhwc(gy)
-        gp = _ActGrad.apply(gy, y) if ctx.act else gy
         need = ctx.needs_input_grad
         dx = dw = db = dn = None
+        if need[2]:
+            gp, db = _ActGradSum.apply(gy, y, ctx.act)           # activation gradient + bias gradient in one pass
+        else:
+            gp = _ActGrad.apply(gy, y) if ctx.act else gy
         if ctx.transposed:
             if need[0]:
                 dx = _Conv.apply(gp, w, ctx.g)
@@ -286,8 +320,6 @@ class _ConvBiasAct(Function):
                 dx = _ConvT.apply(gp, w, ctx.g, (x.shape[1], x.shape[2]))
             if need[1]:
                 dw = _Wgrad.apply(x, gp, ctx.g, tuple(w.shape))
-        if need[2]:
-            db = _ChannelSum.apply(gp)
         if need[3]:
             dn = gp.sum(dim=3, dtype=torch.float32)              # d(noise)[n,y,x] = sum over channels (one read of gp)
         return dx, dw, db, dn, None, None, None, None
@@ -352,10 +384,13 @@ class _ThinIn(Function):
     def backward(ctx, gy):
         img, w2, y = ctx.saved_tensors
         gy = _nhwc(gy)
-        gp = _ActGrad.apply(gy, y) if ctx.act else gy
+        db = None
+        if ctx.needs_input_grad[2]:
+            gp, db = _ActGradSum.apply(gy, y, ctx.act)
+        else:
+            gp = _ActGrad.apply(gy, y) if ctx.act else gy
         dimg = _ThinOut.apply(gp, w2) if ctx.needs_input_grad[0] else None
         dw = _ThinWgrad.apply(gp, img) if ctx.needs_input_grad[1] else None
-        db = _ChannelSum.apply(gp) if (ctx.needs_input_grad[2]) else None
         return dimg, dw, db, None
 
 
