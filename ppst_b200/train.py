@@ -68,7 +68,11 @@ def _pack(w, slots_key, groups, slots, src, transpose):
     return out
 
 
-def _conv_raw(x, w, g, bias=None, act=False, noise=None):
+def _stats_buf(d, device, want):
+    return torch.empty(ops.conv_tc_stats_elems(d), device=device, dtype=torch.float32) if want else None
+
+
+def _conv_raw(x, w, g, bias=None, act=False, noise=None, want_stats=False):
     """x NHWC bf16 [n,h,w,ci], w f32 [co,ci,k,k] -> NHWC bf16 [n,oh,ow,co]; optional fused bias + per-pixel noise
     (f32 [n,oh,ow], already scaled) + leaky-ReLU(0.2)*sqrt2."""
     n, h, wd, ci = x.shape
@@ -82,8 +86,9 @@ def _conv_raw(x, w, g, bias=None, act=False, noise=None):
                       out_dtype=BF16)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
     nz = None if noise is None else noise.detach().to(torch.float32).contiguous()
-    ops.conv_tc(out, x, wp, b, nz, None, d)
-    return out
+    sbuf = _stats_buf(d, x.device, want_stats)
+    ops.conv_tc(out, x, wp, b, nz, sbuf, d)
+    return (out, sbuf) if want_stats else out
 
 
 def _phase_taps(k, pad, r):
@@ -93,7 +98,7 @@ def _phase_taps(k, pad, r):
     return (max(us), min(us)) if us else (0, 1)
 
 
-def _dgrad_raw(gy, w, g, in_hw, bias=None, act=False, noise=None):
+def _dgrad_raw(gy, w, g, in_hw, bias=None, act=False, noise=None, want_stats=False):
     """dx NHWC bf16 [n, in_h, in_w, ci] of y = conv(x, w) given dy (NHWC bf16 [n,oh,ow,co]) -- equally the FORWARD of
     F.conv_transpose2d(dy, w, stride, padding) (EqualizedConv2d's fused upscale, stylegan2_layers.py:312-321), for which
     the optional bias / noise / leaky-ReLU epilogue exists."""
@@ -111,8 +116,9 @@ def _dgrad_raw(gy, w, g, in_hw, bias=None, act=False, noise=None):
         off = -(k - 1) + g.pad
         d = ops.conv_desc(gy.shape, ci, k, k, stride=1, off=(off, off), out_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16,
                           **epi)
-        ops.conv_tc(out, gy, wp, b, nz, None, d)
-        return out
+        sbuf = _stats_buf(d, gy.device, want_stats)
+        ops.conv_tc(out, gy, wp, b, nz, sbuf, d)
+        return (out, sbuf) if want_stats else out
     assert g.stride == 2 and in_hw[0] % 2 == 0 and in_hw[1] % 2 == 0, "stride-2 input gradient needs even input sizes"
     (hi0, lo0), (hi1, lo1) = _phase_taps(k, g.pad, 0), _phase_taps(k, g.pad, 1)
     J = max(hi0 - lo0, hi1 - lo1) + 1
@@ -128,8 +134,9 @@ def _dgrad_raw(gy, w, g, in_hw, bias=None, act=False, noise=None):
     wp = _pack(w, ("dgrad2", k, g.pad), 4, J * J, src, True)
     d = ops.conv_desc(gy.shape, ci, J, J, stride=1, off=(-hi0, -hi0), out_hw=(in_hw[0] // 2, in_hw[1] // 2), phases=(2, 2),
                       phase_off=(hi0 - hi1, hi0 - hi1), full_hw=tuple(in_hw), in_dtype=BF16, out_dtype=BF16, **epi)
-    ops.conv_tc(out, gy, wp, b, nz, None, d)
-    return out
+    sbuf = _stats_buf(d, gy.device, want_stats)
+    ops.conv_tc(out, gy, wp, b, nz, sbuf, d)
+    return (out, sbuf) if want_stats else out
 
 
 _ws = {}
@@ -290,18 +297,20 @@ class _ConvBiasAct(Function):
     at its input resolution `out_hw` -- F.conv_transpose2d(x, w, stride, padding)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, noise, g, act, transposed, out_hw):
+    def forward(ctx, x, w, b, noise, g, act, transposed, out_hw, want_stats):
         x = _nhwc(x)
         if transposed:
-            y = _dgrad_raw(x, w, g, out_hw, bias=b, act=act, noise=noise)
+            r = _dgrad_raw(x, w, g, out_hw, bias=b, act=act, noise=noise, want_stats=want_stats)
         else:
-            y = _conv_raw(x, w, g, bias=b, act=act, noise=noise)
+            r = _conv_raw(x, w, g, bias=b, act=act, noise=noise, want_stats=want_stats)
+        y, stats = r if want_stats else (r, torch.empty(0, device=x.device))
         ctx.save_for_backward(x, w, y)
         ctx.g, ctx.act, ctx.transposed = g, act, transposed
-        return y
+        ctx.mark_non_differentiable(stats)
+        return y, stats                  # stats: the epilogue's per-tile sum / sum of squares of the stored outputs
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gstats):
         x, w, y = ctx.saved_tensors
         gy = _nhwc(gy)
         need = ctx.needs_input_grad
@@ -322,27 +331,30 @@ class _ConvBiasAct(Function):
                 dw = _Wgrad.apply(x, gp, ctx.g, tuple(w.shape))
         if need[3]:
             dn = gp.sum(dim=3, dtype=torch.float32)              # d(noise)[n,y,x] = sum over channels (one read of gp)
-        return dx, dw, db, dn, None, None, None, None
+        return dx, dw, db, dn, None, None, None, None, None
 
 
-def conv2d(x, w, stride=1, padding=0, bias=None, act=False, noise=None):
+def conv2d(x, w, stride=1, padding=0, bias=None, act=False, noise=None, want_stats=False):
     """F.conv2d on NHWC bf16 activations (x [n,h,w,ci], w f32 [co,ci,k,k]) with the optional fused epilogue
-    (+ bias[co], + noise[n,oh,ow], leaky-ReLU(0.2) * sqrt2); differentiable to second order."""
+    (+ bias[co], + noise[n,oh,ow], leaky-ReLU(0.2) * sqrt2); differentiable to second order.  want_stats: also return the
+    epilogue's partial InstanceNorm statistics of the output (feed them to instance_norm_mod: saves its reduction pass)."""
     g = Geom(w.shape[2], stride, padding)
-    if bias is None and not act and noise is None:
+    if bias is None and not act and noise is None and not want_stats:
         return _Conv.apply(x, w, g)
     if bias is None:
         bias = torch.zeros(w.shape[0], device=w.device, dtype=torch.float32)
-    return _ConvBiasAct.apply(x, w, bias, noise, g, act, False, None)
+    y, stats = _ConvBiasAct.apply(x, w, bias, noise, g, act, False, None, want_stats)
+    return (y, stats) if want_stats else y
 
 
-def conv_transpose2d(x, w, stride, padding, out_hw, bias=None, act=False, noise=None):
+def conv_transpose2d(x, w, stride, padding, out_hw, bias=None, act=False, noise=None, want_stats=False):
     """F.conv_transpose2d(x, w, stride=stride, padding=padding) on NHWC bf16: x [n,h,w,c_in], w f32 [c_in, c_out, k, k] (torch's
     transposed-conv weight layout), result [n, out_hw, c_out]; same optional epilogue as conv2d."""
     g = Geom(w.shape[2], stride, padding)
     if bias is None:
         bias = torch.zeros(w.shape[1], device=w.device, dtype=torch.float32)
-    return _ConvBiasAct.apply(x, w, bias, noise, g, act, True, tuple(out_hw))
+    y, stats = _ConvBiasAct.apply(x, w, bias, noise, g, act, True, tuple(out_hw), want_stats)
+    return (y, stats) if want_stats else y
 
 
 # ------------------------------------------------------------------------------------------------ thin input layer
@@ -562,13 +574,19 @@ class _NormMod(Function):
     ONE apply pass.  Backward: two fused reductions (ppst_plane_dot) and ONE apply pass dx = alpha*g + beta*x + gamma."""
 
     @staticmethod
-    def forward(ctx, x, scale, shift, act):
+    def forward(ctx, x, scale, shift, act, stats):
         x = _nhwc(x)
         n, h, w, c = x.shape
         N = float(h * w)
-        st = ops.plane_reduce(x, channels_last=True, want=("sum", "sumsq"))
-        mean = st["sum"].view(n, c) / N
-        var = (st["sumsq"].view(n, c) / N - mean * mean).clamp_min(0.0)
+        if stats is not None and stats.numel():
+            # the producing convolution's epilogue already summed its stored outputs per tile: [2][n][tiles][c]
+            part = stats.view(2, n, -1, c).sum(dim=2)
+            ssum, ssq = part[0], part[1]
+        else:
+            st = ops.plane_reduce(x, channels_last=True, want=("sum", "sumsq"))
+            ssum, ssq = st["sum"].view(n, c), st["sumsq"].view(n, c)
+        mean = ssum / N
+        var = (ssq / N - mean * mean).clamp_min(0.0)
         rstd = torch.rsqrt(var + 1e-5)
         a = rstd if scale is None else rstd * (1.0 + scale.to(torch.float32))
         b = -mean * a
@@ -602,11 +620,12 @@ class _NormMod(Function):
                                   out_dtype=torch.bfloat16)
         dscale = gxh if (scale is not None and ctx.needs_input_grad[1]) else None
         dshift = sg if (ctx.has_shift and ctx.needs_input_grad[2]) else None
-        return dx, dscale, dshift, None
+        return dx, dscale, dshift, None, None
 
 
-def instance_norm_mod(x, scale=None, shift=None, act=False):
-    return _NormMod.apply(x, scale, shift, act)
+def instance_norm_mod(x, scale=None, shift=None, act=False, stats=None):
+    """stats: the second result of conv2d / conv_transpose2d(..., want_stats=True) that produced x (optional)."""
+    return _NormMod.apply(x, scale, shift, act, stats)
 
 
 class _Affine(Function):

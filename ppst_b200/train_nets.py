@@ -86,32 +86,33 @@ def _res_block(P, p, x, norm):
     Blur(zero pad (1,0)) + 1x1 stride-2 conv = ONE 3x3 stride-2 convolution with zero padding."""
     blur = _k121(x.device)
 
-    def tail(y, name, act):
+    def tail(ys, name, act):
+        y, stats = ys
         b = P[p + name + ".Act.bias"] if act else None
-        if norm:
-            n, c = y.shape[0], y.shape[3]
-            return train.instance_norm_mod(y, None, None if b is None else b.view(1, c).expand(n, c), act=act)
-        return y
+        n, c = y.shape[0], y.shape[3]
+        return train.instance_norm_mod(y, None, None if b is None else b.view(1, c).expand(n, c), act=act, stats=stats)
 
     # conv1: RefPad(1) -> 3x3 -> [IN] -> FusedLeakyReLU
     w1 = _eq(P[p + "conv1.Conv.weight"])
     xp = train.reflect_pad(x, (1, 1, 1, 1))
     if norm:
-        y = tail(train.conv2d(xp, w1, 1, 0), "conv1", True)
+        y = tail(train.conv2d(xp, w1, 1, 0, want_stats=True), "conv1", True)
     else:
         y = train.conv2d(xp, w1, 1, 0, bias=P[p + "conv1.Act.bias"], act=True)
     # conv2: RefPad(2,1) -> Blur -> 3x3 stride 2; one more reflected row / column keeps the size even, no tap reads it
     w2 = train._fold(_eq(P[p + "conv2.Conv.weight"]), blur)                      # [co, ci, 5, 5]
     yp = train.reflect_pad(y, (2, 2, 2, 2))
     if norm:
-        y = tail(train.conv2d(yp, w2, 2, 0), "conv2", True)
+        y = tail(train.conv2d(yp, w2, 2, 0, want_stats=True), "conv2", True)
     else:
         y = train.conv2d(yp, w2, 2, 0, bias=P[p + "conv2.Act.bias"], act=True)
     # skip: Blur(pad (1, 0)) -> 1x1 stride 2, no bias, no activation
     ws = train._fold(_eq(P[p + "skip.Conv.weight"]), blur)                       # [co, ci, 3, 3]
-    sk = train.conv2d(x, ws, 2, 1)
     if norm:
-        sk = train.instance_norm_mod(sk)
+        sk, st = train.conv2d(x, ws, 2, 1, want_stats=True)
+        sk = train.instance_norm_mod(sk, stats=st)
+    else:
+        sk = train.conv2d(x, ws, 2, 1)
     return train.add_scale(y, sk, 1.0 / SQRT2)
 
 
@@ -121,10 +122,10 @@ def encoder_con(P, img):
     for i in (1, 2, 4):
         x = _res_block(P, "DownToSpatialCode.ResBlockDownBy%d." % i, x, norm=True)
     n, c = x.shape[0], x.shape[3]
-    y = train.conv2d(x, _eq(P["ToSpatialCode.0.Conv.weight"]), 1, 0)
-    y = train.instance_norm_mod(y, None, P["ToSpatialCode.0.Act.bias"].view(1, -1).expand(n, -1), act=True)
-    y = train.conv2d(y, _eq(P["ToSpatialCode.1.Conv.weight"]), 1, 0, bias=P["ToSpatialCode.1.Conv.bias"])
-    return train.instance_norm_mod(y)
+    y, st = train.conv2d(x, _eq(P["ToSpatialCode.0.Conv.weight"]), 1, 0, want_stats=True)
+    y = train.instance_norm_mod(y, None, P["ToSpatialCode.0.Act.bias"].view(1, -1).expand(n, -1), act=True, stats=st)
+    y, st = train.conv2d(y, _eq(P["ToSpatialCode.1.Conv.weight"]), 1, 0, bias=P["ToSpatialCode.1.Conv.bias"], want_stats=True)
+    return train.instance_norm_mod(y, stats=st)
 
 
 def _head(P, level, x):
@@ -174,14 +175,14 @@ def _styled(P, p, x, code, upsample, noise_gen, noises=None):
     if upsample and min(h, wd) * 2 >= 128:
         # W' = 2x2 box sum of the zero-padded transposed weight -> conv_transpose2d(stride 2, padding 1) (:312-321)
         wt = train._fold(w.permute(1, 0, 2, 3), _const("box2", w.device, lambda: torch.ones(2, 2)))   # [ci, co, 4, 4]
-        y = train.conv_transpose2d(x, wt, 2, 1, (oh, ow), bias=bias, act=True, noise=noise)
+        y, st = train.conv_transpose2d(x, wt, 2, 1, (oh, ow), bias=bias, act=True, noise=noise, want_stats=True)
     else:
         if upsample:
             x = _resize2(x, "nearest")
-        y = train.conv2d(x, w, 1, w.shape[2] // 2, bias=bias, act=True, noise=noise)
+        y, st = train.conv2d(x, w, 1, w.shape[2] // 2, bias=bias, act=True, noise=noise, want_stats=True)
     lw = P[p + "epi1.style_mod.lin.weight"]
     s = train.linear(code, lw * (lw.shape[1] ** -0.5)) + P[p + "epi1.style_mod.lin.bias"]
-    return train.instance_norm_mod(y, s[:, :co], s[:, co:], act=False)
+    return train.instance_norm_mod(y, s[:, :co], s[:, co:], act=False, stats=st)
 
 
 def generator(P, sp, codes, noise_gen=None, noises=None):

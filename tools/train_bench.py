@@ -84,7 +84,8 @@ def stage1(args):
     prof = ops.profile_summary()
     ops.PROFILE = None
     kern = {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
-                "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1) if k in ("conv_tc", "conv_wgrad") and v["ms"] > 0 else None}
+                "tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1) if k in ("conv_tc", "conv_wgrad") and v["ms"] > 0 else None,
+                "gbs": round(v["work"] / (v["ms"] * 1e-3) / 1e9, 1) if k not in ("conv_tc", "conv_wgrad") and v["ms"] > 0 else None}
             for k, v in prof.items()}
     # the same three steps captured once into CUDA graphs (autograd tape, weight preparation, noise draws, all-reduce and
     # Adam included) and replayed: removes the host gaps between the ~2500 launches of a G step
