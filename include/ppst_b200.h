@@ -343,10 +343,17 @@ PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in
                   int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
                   const float* b, float slope, void* stream);
 
-/* Adjoint of ppst_resample mode 0 at scale exactly 2 (the bilinear x2 skip of UpsamplingResnetBlock, generator.py:75) for
- * the training path: g NHWC [n, 2h, 2w, c] -> gin NHWC [n, h, w, c], as a gather with a fixed summation order
- * (deterministic; ATen's upsample_bilinear2d_backward scatters with atomics).  bf16 (c % 8 == 0) or f32 (c % 4 == 0). */
-PPST_API int ppst_bilinear2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int dtype, void* stream);
+/* Adjoints of the x2 upsamplings and of the reflection pad for the training path, all as gathers with a fixed summation
+ * order (deterministic; ATen's upsample_bilinear2d_backward scatters with atomics).  bf16 (c % 8 == 0) or f32 (c % 4 == 0).
+ *   ppst_upsample2x_backward: g NHWC [n, 2h, 2w, c] -> gin [n, h, w, c]; nearest = 0: adjoint of ppst_resample mode 0 at scale 2
+ *     (the bilinear skip of UpsamplingResnetBlock, generator.py:75); nearest = 1: adjoint of Upscale2d (stylegan2_layers.py:
+ *     88-105) = the 2x2 box sum.
+ *   ppst_reflect_pad_backward: g NHWC [n, h+pt+pb, w+pl+pr, c] -> gin [n, h, w, c], adjoint of nn.ReflectionPad2d
+ *     (ppst_affine_apply with pad_mode 1). */
+PPST_API int ppst_upsample2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int nearest, int dtype,
+                             void* stream);
+PPST_API int ppst_reflect_pad_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int pt, int pb, int pl, int pr,
+                              int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * small dense layers and vector normalisation (f32)

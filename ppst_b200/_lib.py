@@ -84,7 +84,8 @@ _SIGS = {
     "ppst_in_coeffs": (c_int, [c_void_p] * 6 + [c_i64, c_void_p, c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),
     "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p, c_void_p, c_float, c_void_p]),
-    "ppst_bilinear2x_backward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_upsample2x_backward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_reflect_pad_backward": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 8 + [c_void_p]),
     "ppst_linear": (c_int, [c_void_p] * 4 + [c_i64] * 4 + [c_float, c_float, c_int, c_void_p]),
     "ppst_linear_dgrad_scratch_elems": (c_i64, [c_i64, c_i64, c_i64]),
     "ppst_linear_dgrad": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_i64, c_void_p]),

@@ -736,7 +736,7 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
 namespace ppst {
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear2x_backward_kernel(T* __restrict__ gin, const T* __restrict__ g, int64_t n,
-                                                                  int h, int w, int c) {
+                                                                  int h, int w, int c, int nearest) {
   constexpr int VEC = Vec16<T>::N;
   const int cv = c / VEC;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -754,16 +754,18 @@ __global__ void __launch_bounds__(256) bilinear2x_backward_kernel(T* __restrict_
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int oy = 2 * i - 1 + t, ox = 2 * j - 1 + t;
-    const float base = (t == 0 || t == 3) ? 0.25f : 0.75f;
+    const float base = nearest ? ((t == 1 || t == 2) ? 1.0f : 0.0f) : ((t == 0 || t == 3) ? 0.25f : 0.75f);
     ys[t] = oy; xs[t] = ox;
     wy[t] = (oy >= 0 && oy < oh) ? base : 0.0f;
     wx[t] = (ox >= 0 && ox < ow) ? base : 0.0f;
   }
   // clamping: output 0 puts its whole weight on input 0, output 2L-1 on input L-1
-  if (i == 0) wy[1] = 1.0f;
-  if (i == h - 1) wy[2] = 1.0f;
-  if (j == 0) wx[1] = 1.0f;
-  if (j == w - 1) wx[2] = 1.0f;
+  if (!nearest) {
+    if (i == 0) wy[1] = 1.0f;
+    if (i == h - 1) wy[2] = 1.0f;
+    if (j == 0) wx[1] = 1.0f;
+    if (j == w - 1) wx[2] = 1.0f;
+  }
   float acc[VEC];
 #pragma unroll
   for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
@@ -787,7 +789,8 @@ __global__ void __launch_bounds__(256) bilinear2x_backward_kernel(T* __restrict_
 }
 }  // namespace ppst
 
-extern "C" int ppst_bilinear2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int dtype, void* stream) {
+extern "C" int ppst_upsample2x_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int nearest, int dtype,
+                                        void* stream) {
   using namespace ppst;
   PPST_REQUIRE(gin && g && n > 0 && h > 0 && w > 0 && c > 0, PPST_ERR_ARG, "bilinear2x_backward: bad args");
   PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "bilinear2x_backward: dtype %d", dtype);
@@ -797,9 +800,73 @@ extern "C" int ppst_bilinear2x_backward(void* gin, const void* g, int64_t n, int
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == PPST_BF16)
     bilinear2x_backward_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        (__nv_bfloat16*)gin, (const __nv_bfloat16*)g, n, h, w, c);
+        (__nv_bfloat16*)gin, (const __nv_bfloat16*)g, n, h, w, c, nearest);
   else
-    bilinear2x_backward_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((float*)gin, (const float*)g, n, h, w, c);
+    bilinear2x_backward_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((float*)gin, (const float*)g, n, h, w, c,
+                                                                                     nearest);
   PPST_LAUNCH_CHECK("bilinear2x_backward_kernel");
+  return 0;
+}
+
+// Adjoint of nn.ReflectionPad2d on NHWC (the encoders' ConvLayer(reflection_pad=True)) as a gather: input pixel (i, j)
+// collects its own padded position and the mirrored ones (up to 3 per axis when the image is smaller than twice the pad).
+namespace ppst {
+__device__ __forceinline__ int reflect_sources(int i, int len, int p0, int p1, int (&q)[3]) {
+  int m = 0;
+  q[m++] = i + p0;
+  if (i >= 1 && i <= p0) q[m++] = p0 - i;
+  if (i <= len - 2 && i >= len - 1 - p1) q[m++] = p0 + 2 * (len - 1) - i;
+  return m;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) reflect_pad_backward_kernel(T* __restrict__ gin, const T* __restrict__ g, int64_t n,
+                                                                   int h, int w, int c, int pt, int pb, int pl, int pr) {
+  constexpr int VEC = Vec16<T>::N;
+  const int cv = c / VEC;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * h * w * cv) return;
+  const int v = (int)(idx % cv);
+  int64_t r = idx / cv;
+  const int j = (int)(r % w); r /= w;
+  const int i = (int)(r % h);
+  const int64_t ni = r / h;
+  const int ph = h + pt + pb, pw = w + pl + pr;
+  int qy[3], qx[3];
+  const int my = reflect_sources(i, h, pt, pb, qy), mx = reflect_sources(j, w, pl, pr, qx);
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
+  const T* gb = g + ni * ph * pw * (int64_t)c + (int64_t)v * VEC;
+  for (int a = 0; a < my; ++a)
+    for (int b = 0; b < mx; ++b) {
+      const Vec16<T> gv = ld_vec16(gb + ((int64_t)qy[a] * pw + qx[b]) * c);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[e] += Cvt<T>::to_f(gv.v[e]);
+    }
+  Vec16<T> o;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) o.v[e] = Cvt<T>::from_f(acc[e]);
+  st_vec16(gin + ((ni * h + i) * w + j) * (int64_t)c + (int64_t)v * VEC, o);
+}
+}  // namespace ppst
+
+extern "C" int ppst_reflect_pad_backward(void* gin, const void* g, int64_t n, int h, int w, int c, int pt, int pb, int pl,
+                                         int pr, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(gin && g && n > 0 && h > 0 && w > 0 && c > 0, PPST_ERR_ARG, "reflect_pad_backward: bad args");
+  PPST_REQUIRE(pt >= 0 && pb >= 0 && pl >= 0 && pr >= 0 && pt < h && pb < h && pl < w && pr < w, PPST_ERR_ARG,
+               "reflect_pad_backward: pads must be smaller than the image");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "reflect_pad_backward: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0, PPST_ERR_UNSUPPORTED, "reflect_pad_backward: c=%d must be a multiple of %d", c, vec);
+  const int64_t total = n * h * w * (c / vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16)
+    reflect_pad_backward_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (__nv_bfloat16*)gin, (const __nv_bfloat16*)g, n, h, w, c, pt, pb, pl, pr);
+  else
+    reflect_pad_backward_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((float*)gin, (const float*)g, n, h, w,
+                                                                                      c, pt, pb, pl, pr);
+  PPST_LAUNCH_CHECK("reflect_pad_backward_kernel");
   return 0;
 }

@@ -655,7 +655,8 @@ def channel_affine(x, a, b):
 
 class _ReflectPad(Function):
     """nn.ReflectionPad2d on NHWC (the encoders' ConvLayer(reflection_pad=True), stylegan2_layers.py:142-164,525):
-    forward = one ppst_affine_apply pass with reflect addressing; backward folds the border gradients back."""
+    forward = one ppst_affine_apply pass with reflect addressing; backward = its adjoint as a gather
+    (ppst_reflect_pad_backward)."""
 
     @staticmethod
     def forward(ctx, x, pad):
@@ -667,19 +668,12 @@ class _ReflectPad(Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         t, b, l, r = ctx.pad
-        g = g.to(torch.float32)
-        H, W = g.shape[1] - t - b, g.shape[2] - l - r
-        rows = g[:, t:t + H].clone()
-        if t:
-            rows[:, 1:t + 1] += g[:, :t].flip(1)
-        if b:
-            rows[:, H - 1 - b:H - 1] += g[:, t + H:].flip(1)
-        out = rows[:, :, l:l + W].clone()
-        if l:
-            out[:, :, 1:l + 1] += rows[:, :, :l].flip(2)
-        if r:
-            out[:, :, W - 1 - r:W - 1] += rows[:, :, l + W:].flip(2)
-        return out.to(torch.bfloat16), None
+        g = _nhwc(g)
+        n, c = g.shape[0], g.shape[3]
+        h, w = g.shape[1] - t - b, g.shape[2] - l - r
+        gin = torch.empty((n, h, w, c), device=g.device, dtype=torch.bfloat16)
+        check(_lib.load().ppst_reflect_pad_backward(ptr(gin), ptr(g), n, h, w, c, t, b, l, r, dt(g), stream()))
+        return gin, None
 
 
 def reflect_pad(x, pad):
@@ -717,14 +711,17 @@ def blur(x, k, pad):
     return _Blur.apply(x, k, int(pad[0]), int(pad[1]), True)
 
 
-class _Bilinear2x(Function):
-    """F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) on NHWC bf16 (the skip of UpsamplingResnetBlock,
-    generator.py:63-77): forward ppst_resample, backward its adjoint as a deterministic gather (ppst_bilinear2x_backward)."""
+class _Upsample2x(Function):
+    """x2 upsampling on NHWC bf16: bilinear, align_corners=False (the skip of UpsamplingResnetBlock, generator.py:63-77:
+    forward ppst_resample) or nearest (Upscale2d, stylegan2_layers.py:88-105: forward ppst_affine_apply with up = 2); the
+    backward is the adjoint as a deterministic gather (ppst_upsample2x_backward)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, nearest):
         x = _nhwc(x)
-        ctx.shape = x.shape
+        ctx.shape, ctx.nearest = x.shape, nearest
+        if nearest:
+            return ops.affine_apply(x, x.shape[3], up=2, out_dtype=torch.bfloat16)
         return ops.resample(x, (2 * x.shape[1], 2 * x.shape[2]), 0, out_dtype=torch.bfloat16)
 
     @staticmethod
@@ -733,12 +730,16 @@ class _Bilinear2x(Function):
         g = _nhwc(g)
         n, h, w, c = ctx.shape
         gin = torch.empty((n, h, w, c), device=g.device, dtype=torch.bfloat16)
-        check(_lib.load().ppst_bilinear2x_backward(ptr(gin), ptr(g), n, h, w, c, dt(g), stream()))
-        return gin
+        check(_lib.load().ppst_upsample2x_backward(ptr(gin), ptr(g), n, h, w, c, 1 if ctx.nearest else 0, dt(g), stream()))
+        return gin, None
+
+
+def nearest2x(x):
+    return _Upsample2x.apply(x, True)
 
 
 def bilinear2x(x):
-    return _Bilinear2x.apply(x)
+    return _Upsample2x.apply(x, False)
 
 
 # ------------------------------------------------------------------------------------------------ discriminator

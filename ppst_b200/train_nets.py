@@ -6,9 +6,10 @@ Same networks as the inference engine, but laid out for autograd: parameters are
 state_dict keys (E1.* / E2.* / G.*), activations are NHWC bf16, and every activation-sized operator
 is a differentiable wrapper around the C-ABI kernels (ppst_b200/train.py): tcgen05 convolution forward / input gradient /
 weight gradient (plain, strided with the blur folded in, transposed for the fused upscale), InstanceNorm + StyleMod as
-statistics + one apply pass each way, the thin RGB layers, the residual joins.  What still runs as ATen kernels on
-channels-last views: the nearest x2 of the one block below the fused-upscale threshold, the global average / max pooling of the colour
-encoder's heads, and everything that is [n, c]-sized (style linears' bias adds, normalisations, losses).
+statistics + one apply pass each way, the thin RGB layers, the residual joins, the x2 upsamplings and the reflection pads
+with their adjoints.  What still runs as ATen kernels: the global average / max pooling of the colour encoder's heads
+(on the NHWC tensors), the ToRGB instance norm on the 3-channel image, and everything that is [n, c]- or parameter-sized
+(style linears' bias adds, weight scaling, normalisations, losses, Adam).
 
 Covers what training stage 1 executes: E1, E2 without the correlation / mask branches, G without feature extraction.
 """
@@ -152,13 +153,6 @@ def encoder_col(P, img):
 
 
 # ------------------------------------------------------------------------------------------------ generator
-def _resize2(x, mode):
-    """x2 nearest (Upscale2d, stylegan2_layers.py:88-105: the 32 -> 64 block below the fused-upscale threshold) of an NHWC
-    tensor through a channels-last view (ATen; forward and backward are gathers)."""
-    assert mode == "nearest"
-    return F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
-
-
 def _styled(P, p, x, code, upsample, noise_gen, noises=None):
     """StyledConv (stylegan2_layers.py:439-475): conv (+ fused upscale) + noise + biases + leaky-ReLU in one launch, then
     InstanceNorm + StyleMod."""
@@ -178,7 +172,7 @@ def _styled(P, p, x, code, upsample, noise_gen, noises=None):
         y, st = train.conv_transpose2d(x, wt, 2, 1, (oh, ow), bias=bias, act=True, noise=noise, want_stats=True)
     else:
         if upsample:
-            x = _resize2(x, "nearest")
+            x = train.nearest2x(x)              # Upscale2d below the fused-upscale threshold (stylegan2_layers.py:322-323)
         y, st = train.conv2d(x, w, 1, w.shape[2] // 2, bias=bias, act=True, noise=noise, want_stats=True)
     lw = P[p + "epi1.style_mod.lin.weight"]
     s = train.linear(code, lw * (lw.shape[1] ** -0.5)) + P[p + "epi1.style_mod.lin.bias"]

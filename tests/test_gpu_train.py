@@ -317,7 +317,17 @@ def test_norm_mod_affine_reflect_pad_gradients():
     xb, ab, bb = x.to(torch.bfloat16).requires_grad_(True), sc.clone().requires_grad_(True), sh.clone().requires_grad_(True)
     train.channel_affine(xb, ab, bb).backward(gy.to(torch.bfloat16))
     assert rel_l2(xb.grad, xr.grad) <= 5e-3 and rel_l2(ab.grad, ar.grad) <= 5e-3 and rel_l2(bb.grad, br.grad) <= 5e-3
-    # reflection pad, asymmetric
+    # reflection pad, asymmetric; also an image smaller than twice the pad (a pixel mirrored from both sides)
+    for pad, xs in (((2, 1, 2, 2), x), ((2, 2, 2, 2), x[:, :3, :4].contiguous())):
+        xr = xs.clone().requires_grad_(True)
+        yr = F.pad(xr.permute(0, 3, 1, 2), (pad[2], pad[3], pad[0], pad[1]), mode="reflect").permute(0, 2, 3, 1)
+        gp = _bf(torch.randn(yr.shape, generator=g)).cuda()
+        yr.backward(gp)
+        xb = xs.to(torch.bfloat16).requires_grad_(True)
+        y = train.reflect_pad(xb, pad)
+        assert torch.equal(y.float(), yr.detach())
+        y.backward(gp.to(torch.bfloat16))
+        assert rel_l2(xb.grad, xr.grad) <= 5e-3, pad
     pad = (2, 1, 2, 2)
     xr = x.clone().requires_grad_(True)
     yr = F.pad(xr.permute(0, 3, 1, 2), (pad[2], pad[3], pad[0], pad[1]), mode="reflect").permute(0, 2, 3, 1)
@@ -535,6 +545,14 @@ def test_bilinear2x_forward_and_deterministic_adjoint():
         xb.grad = None
         train.bilinear2x(xb).backward(gy.to(torch.bfloat16))
         assert torch.equal(g2, xb.grad)
+        # nearest x2 (Upscale2d) and its 2x2 box-sum adjoint
+        xr2 = _nchw(x).requires_grad_(True)
+        yr2 = F.interpolate(xr2, scale_factor=2, mode="nearest")
+        yr2.backward(_nchw(gy))
+        xb2 = x.to(torch.bfloat16).requires_grad_(True)
+        y2 = train.nearest2x(xb2)
+        y2.backward(gy.to(torch.bfloat16))
+        assert torch.equal(_nchw(y2), yr2.detach()) and rel_l2(_nchw(xb2.grad), xr2.grad) <= 5e-3
 
 
 def test_discriminator_512_and_stage1_256_forward_match_oracle():
