@@ -476,21 +476,33 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(T* __restrict__ out, con
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[j][e] = 0.0f;
   const T* base = in + ni * in_h * in_w * (int64_t)c + (int64_t)v * VEC;
+  // branch-free taps: out-of-range rows / columns load a clamped (valid) address and get weight 0, so the KW loads of a
+  // row -- and the next row's -- are all in flight together
+  int cx[KW];
+  float vx[KW];
+#pragma unroll
+  for (int kx = 0; kx < KW; ++kx) {
+    const int ix = ox + kx - px0;
+    vx[kx] = (ix >= 0 && ix < in_w) ? 1.0f : 0.0f;
+    cx[kx] = min(max(ix, 0), in_w - 1);
+  }
 #pragma unroll
   for (int rr = 0; rr < kBlurRows + KH - 1; ++rr) {
     const int iy = oy0 + rr - py0;
-    if (iy < 0 || iy >= in_h) continue;
+    const float vy = (iy >= 0 && iy < in_h) ? 1.0f : 0.0f;
+    const T* row = base + (int64_t)min(max(iy, 0), in_h - 1) * in_w * c;
+    Vec16<T> xv[KW];
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) xv[kx] = ld_vec16(row + (int64_t)cx[kx] * c);
 #pragma unroll
     for (int kx = 0; kx < KW; ++kx) {
-      const int ix = ox + kx - px0;
-      if (ix < 0 || ix >= in_w) continue;
-      const Vec16<T> xv = ld_vec16(base + ((int64_t)iy * in_w + ix) * c);
       float xf[VEC];
+      const bool valid = (vy * vx[kx]) != 0.0f;
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) xf[e] = Cvt<T>::to_f(xv.v[e]);
+      for (int e = 0; e < VEC; ++e) xf[e] = valid ? Cvt<T>::to_f(xv[kx].v[e]) : 0.0f;
 #pragma unroll
       for (int j = 0; j < kBlurRows; ++j) {
-        const int ky = rr - j;                       // input row rr is tap ky of output row j
+        const int ky = rr - j;                       // input row rr is tap ky of output row j (compile-time after unrolling)
         if (ky < 0 || ky >= KH) continue;
         const float w = sk[ky * KW + kx];
 #pragma unroll
