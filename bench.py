@@ -25,8 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # NCCL prints its version banner to STDOUT at this level;
-    os.environ["NCCL_DEBUG"] = "WARN"                          # stdout must carry exactly one JSON line (warnings stay on)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # NCCL prints its version banner to STDOUT at the VERSION and
+    del os.environ["NCCL_DEBUG"]                               # WARN levels; stdout must carry exactly one JSON line
 
 import torch  # noqa: E402
 

@@ -11,8 +11,8 @@ import argparse, json, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # the version banner goes to stdout; keep warnings only
-    os.environ["NCCL_DEBUG"] = "WARN"
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # NCCL prints its version banner to stdout at VERSION / WARN
+    del os.environ["NCCL_DEBUG"]
 
 
 def timed(fn, steps, warm=2):
