@@ -139,6 +139,15 @@ PPST_API int64_t ppst_plane_dot_scratch_elems(int64_t n, int64_t c, int64_t hw);
 PPST_API int ppst_plane_dot(float* sum_g, float* sum_gx, const void* g, const void* x, float* scratch, int64_t n, int64_t c,
                    int64_t hw, int dtype, void* stream);
 
+/* Backward of the GAP || GMP pooling of the colour encoder's heads (encoder_col.py:39-40,160-161) for the training path;
+ * the forward is ppst_plane_reduce (sum, vmax).  ppst_plane_count_eq: cnt[n,c] = number of pixels with x == mx[n,c] (ties
+ * share the maximum's gradient, as torch.amax does); scratch: ppst_plane_dot_scratch_elems(n, c, hw) floats.
+ * ppst_pool_backward: dx[n,p,c] = ga[n,c] + (x[n,p,c] == mx[n,c] ? gm[n,c] : 0) with ga = grad_gap / hw, gm = grad_gmp / cnt. */
+PPST_API int ppst_plane_count_eq(float* cnt, const void* x, const float* mx, float* scratch, int64_t n, int64_t c, int64_t hw,
+                        int dtype, void* stream);
+PPST_API int ppst_pool_backward(void* dx, const void* x, const float* ga, const float* gm, const float* mx, int64_t n, int64_t c,
+                       int64_t hw, int dtype, void* stream);
+
 /* uint8 label map [n, hw] -> one-hot f32 [n, n_labels, hw]  (CelebAMaskDataset._mask_labels,
  * data/CelebAMask_dataset.py:54-60; bit-exact membership test label == i). */
 PPST_API int ppst_labels_to_onehot(float* onehot, const uint8_t* labels, int64_t n, int64_t hw, int n_labels, void* stream);

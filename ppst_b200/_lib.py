@@ -58,6 +58,8 @@ _SIGS = {
     "ppst_upsample_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 6 + [c_void_p, c_void_p]),
     "ppst_plane_dot_scratch_elems": (c_i64, [c_i64, c_i64, c_i64]),
     "ppst_plane_dot": (c_int, [c_void_p] * 5 + [c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ppst_plane_count_eq": (c_int, [c_void_p] * 4 + [c_i64, c_i64, c_i64, c_int, c_void_p]),
+    "ppst_pool_backward": (c_int, [c_void_p] * 5 + [c_i64, c_i64, c_i64, c_int, c_void_p]),
     "ppst_labels_pool_or": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_labels_to_onehot": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_int, c_void_p]),
     "ppst_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),

@@ -568,3 +568,107 @@ extern "C" int ppst_plane_dot(float* sum_g, float* sum_gx, const void* g, const 
   PPST_LAUNCH_CHECK("plane_dot_final");
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Backward of the global average / max pooling pair of the colour encoder's heads (GAP || GMP, encoder_col.py:39-40,
+// 160-161) for the training path: dx[n,p,c] = ga[n,c] + (x[n,p,c] == mx[n,c] ? gm[n,c] : 0), where the caller passes
+// ga = grad_gap / (h*w) and gm = grad_gmp / count and count = the number of pixels that attain the maximum (torch.amax
+// spreads the gradient evenly over ties).  ppst_plane_count_eq produces that count (two stages, fixed order).
+namespace ppst {
+template <typename T>
+__global__ void __launch_bounds__(256) plane_count_eq_kernel(float* __restrict__ partials, const T* __restrict__ x,
+                                                             const float* __restrict__ mx, int64_t c, int64_t hw, int chunks) {
+  extern __shared__ float red[];                         // [pixel lanes][c]
+  constexpr int VEC = Vec16<T>::N;
+  const int cols = (int)(c / VEC), lanes = 256 / cols;
+  const int col = threadIdx.x % cols, lane = threadIdx.x / cols;
+  const int64_t ni = blockIdx.y;
+  const int64_t beg = (int64_t)blockIdx.x * kDotChunk, end = min(beg + (int64_t)kDotChunk, hw);
+  float cnt[VEC], m[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { cnt[e] = 0.f; m[e] = (lane < lanes) ? mx[ni * c + (int64_t)col * VEC + e] : 0.f; }
+  if (lane < lanes) {
+    const T* xb = x + ni * hw * c + (int64_t)col * VEC;
+    for (int64_t p = beg + lane; p < end; p += lanes) {
+      const Vec16<T> xv = ld_vec16_stream(xb + p * c);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) cnt[e] += (Cvt<T>::to_f(xv.v[e]) == m[e]) ? 1.0f : 0.0f;
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) red[(int64_t)lane * c + col * VEC + e] = cnt[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(int64_t)l * c + i];
+    partials[(ni * chunks + blockIdx.x) * c + i] = t;
+  }
+}
+
+__global__ void plane_count_final(float* __restrict__ cnt, const float* __restrict__ partials, int64_t n, int64_t c, int chunks) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * c) return;
+  const int64_t ni = t / c, ch = t - ni * c;
+  float a = 0.f;
+  for (int k = 0; k < chunks; ++k) a += partials[(ni * chunks + k) * c + ch];
+  cnt[t] = a;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool_backward_kernel(T* __restrict__ dx, const T* __restrict__ x,
+                                                            const float* __restrict__ ga, const float* __restrict__ gm,
+                                                            const float* __restrict__ mx, int64_t c, int64_t hw, int64_t total) {
+  constexpr int VEC = Vec16<T>::N;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over n*hw*(c/VEC)
+  if (idx >= total) return;
+  const int64_t cv = c / VEC;
+  const int64_t v = idx % cv, pix = idx / cv, ni = pix / hw;
+  const int64_t off = pix * c + v * VEC, co = ni * c + v * VEC;
+  const Vec16<T> xv = ld_vec16_stream(x + off);
+  Vec16<T> o;
+#pragma unroll
+  for (int e = 0; e < VEC; ++e)
+    o.v[e] = Cvt<T>::from_f(ga[co + e] + ((Cvt<T>::to_f(xv.v[e]) == mx[co + e]) ? gm[co + e] : 0.0f));
+  st_vec16(dx + off, o);
+}
+}  // namespace ppst
+
+extern "C" int ppst_plane_count_eq(float* cnt, const void* x, const float* mx, float* scratch, int64_t n, int64_t c, int64_t hw,
+                                   int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(cnt && x && mx && scratch && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "plane_count_eq: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "plane_count_eq: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0 && c / vec <= 256, PPST_ERR_UNSUPPORTED, "plane_count_eq: c=%lld", (long long)c);
+  const int chunks = (int)((hw + kDotChunk - 1) / kDotChunk);
+  const size_t smem = sizeof(float) * (size_t)(256 / (c / vec)) * c;
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16)
+    plane_count_eq_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(scratch, (const __nv_bfloat16*)x, mx, c, hw, chunks);
+  else
+    plane_count_eq_kernel<float><<<grid, 256, smem, st>>>(scratch, (const float*)x, mx, c, hw, chunks);
+  PPST_LAUNCH_CHECK("plane_count_eq_kernel");
+  plane_count_final<<<ceil_div(n * c, 256), 256, 0, st>>>(cnt, scratch, n, c, chunks);
+  PPST_LAUNCH_CHECK("plane_count_final");
+  return 0;
+}
+
+extern "C" int ppst_pool_backward(void* dx, const void* x, const float* ga, const float* gm, const float* mx, int64_t n, int64_t c,
+                                  int64_t hw, int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(dx && x && ga && gm && mx && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "pool_backward: bad args");
+  PPST_REQUIRE(dtype == PPST_BF16 || dtype == PPST_F32, PPST_ERR_DTYPE, "pool_backward: dtype %d", dtype);
+  const int vec = dtype == PPST_BF16 ? 8 : 4;
+  PPST_REQUIRE(c % vec == 0, PPST_ERR_UNSUPPORTED, "pool_backward: c=%lld", (long long)c);
+  const int64_t total = n * hw * (c / vec);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PPST_BF16)
+    pool_backward_kernel<__nv_bfloat16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)x,
+                                                                                        ga, gm, mx, c, hw, total);
+  else
+    pool_backward_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((float*)dx, (const float*)x, ga, gm, mx, c, hw, total);
+  PPST_LAUNCH_CHECK("pool_backward_kernel");
+  return 0;
+}

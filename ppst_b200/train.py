@@ -628,6 +628,41 @@ def instance_norm_mod(x, scale=None, shift=None, act=False, stats=None):
     return _NormMod.apply(x, scale, shift, act, stats)
 
 
+class _GapGmp(Function):
+    """(global average, global max) over H*W of an NHWC tensor -> two f32 [n, c] (the colour encoder's heads,
+    encoder_col.py:39-40,160-161): forward ppst_plane_reduce, backward ONE pass (ppst_pool_backward) after counting the
+    pixels that attain the maximum (ties share its gradient, torch.amax's rule)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _nhwc(x)
+        n, h, w, c = x.shape
+        st = ops.plane_reduce(x, channels_last=True, want=("sum", "max"))
+        gap = st["sum"].view(n, c) / float(h * w)
+        gmp = st["max"].view(n, c).contiguous()
+        ctx.save_for_backward(x, gmp)
+        return gap, gmp
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_gap, g_gmp):
+        x, gmp = ctx.saved_tensors
+        n, h, w, c = x.shape
+        L = _lib.load()
+        scratch = ops._get_scratch(x.device, L.ppst_plane_dot_scratch_elems(n, c, h * w))
+        cnt = torch.empty((n, c), device=x.device, dtype=torch.float32)
+        check(L.ppst_plane_count_eq(ptr(cnt), ptr(x), ptr(gmp), ptr(scratch), n, c, h * w, dt(x), stream()))
+        ga = (g_gap.to(torch.float32) / float(h * w)).contiguous()
+        gm = (g_gmp.to(torch.float32) / cnt).contiguous()
+        dx = torch.empty_like(x)
+        check(L.ppst_pool_backward(ptr(dx), ptr(x), ptr(ga), ptr(gm), ptr(gmp), n, c, h * w, dt(x), stream()))
+        return dx
+
+
+def gap_gmp(x):
+    return _GapGmp.apply(x)
+
+
 class _Affine(Function):
     """y = x * a + b per (sample, channel) (GeneratorModulation, generator.py:80-91): a, b f32 [n, c]."""
 

@@ -7,8 +7,8 @@ state_dict keys (E1.* / E2.* / G.*), activations are NHWC 
 is a differentiable wrapper around the C-ABI kernels (ppst_b200/train.py): tcgen05 convolution forward / input gradient /
 weight gradient (plain, strided with the blur folded in, transposed for the fused upscale), InstanceNorm + StyleMod as
 statistics + one apply pass each way, the thin RGB layers, the residual joins, the x2 upsamplings and the reflection pads
-with their adjoints.  What still runs as ATen kernels: the global average / max pooling of the colour encoder's heads
-(on the NHWC tensors), the ToRGB instance norm on the 3-channel image, and everything that is [n, c]- or parameter-sized
+with their adjoints, the global average / max pooling of the colour encoder's heads.  What still runs as ATen kernels:
+the ToRGB instance norm on the 3-channel image and everything that is [n, c]- or parameter-sized
 (style linears' bias adds, weight scaling, normalisations, losses, Adam).
 
 Covers what training stage 1 executes: E1, E2 without the correlation / mask branches, G without feature extraction.
@@ -131,8 +131,7 @@ def encoder_con(P, img):
 
 def _head(P, level, x):
     """GAP || GMP -> conv1x1 -> projector MLP -> F.normalize (encoder_col.py:39-40,50-86,160-166)."""
-    gap = torch.mean(x, dim=(1, 2), dtype=torch.float32)
-    gmp = torch.amax(x, dim=(1, 2)).to(torch.float32)
+    gap, gmp = train.gap_gmp(x)
     v = torch.cat([gap, gmp], 1)
     w = P["conv1x1_%s.weight" % level]
     v = train.linear(v, w.view(w.shape[0], -1)) + P["conv1x1_%s.bias" % level]

@@ -601,3 +601,21 @@ def test_blur_nhwc_matches_upfirdn2d_and_is_self_adjoint_to_second_order():
         gx2, = torch.autograd.grad(train.blur(xb, k.cuda(), pad), [xb], gyb, create_graph=True)
         d, = torch.autograd.grad((gx2.float() * R).sum(), [gyb])
         assert rel_l2(_nchw(d), O.upfirdn2d(R.cpu().permute(0, 3, 1, 2), k, pad=pad)) <= 5e-3
+
+
+def test_gap_gmp_heads_pooling_with_ties():
+    from ppst_b200 import train
+    g = torch.Generator().manual_seed(16)
+    x = _bf(torch.randn(2, 20, 12, 64, generator=g))
+    x[0, 3, 4, :8] = 9.0                         # a tie for the maximum: two pixels attain it in 8 channels
+    x[0, 7, 1, :8] = 9.0
+    x = x.cuda()
+    xr = x.clone().requires_grad_(True)
+    gap_r, gmp_r = xr.mean(dim=(1, 2)), xr.amax(dim=(1, 2))
+    ga, gm = torch.randn(2, 64, generator=g).cuda(), torch.randn(2, 64, generator=g).cuda()
+    ((gap_r * ga).sum() + (gmp_r * gm).sum()).backward()
+    xb = x.to(torch.bfloat16).requires_grad_(True)
+    gap, gmp = train.gap_gmp(xb)
+    assert rel_l2(gap, gap_r) <= 1e-5 and torch.equal(gmp, gmp_r.detach())
+    ((gap * ga).sum() + (gmp * gm).sum()).backward()
+    assert rel_l2(xb.grad, xr.grad) <= 5e-3
