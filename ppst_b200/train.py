@@ -6,7 +6,8 @@ here on the tcgen05 convolution kernel of the inference path:
     forward   y  = conv(x, w)                     ppst_conv_tc                      (bf16 operands, fp32 accumulate)
     dgrad     dx = conv(dy, flip(w)^T)            ppst_conv_tc again: stride 1 = one plain convolution with the rotated,
                                                   transposed weights; stride 2 = four sub-pixel phases (no zero insertion)
-    wgrad     dw = sum_pixels dy (x) shift(x)     ppst_conv_wgrad (pixel-major operands, K-split tensor-core GEMM)
+    wgrad     dw = sum_pixels dy (x) shift(x)     ppst_conv_wgrad (MN-major tcgen05 operands read straight from NHWC by TMA,
+                                                  pixel chunks -> fp32 partials -> fixed-order reduce)
 
 The three maps are bilinear and closed under differentiation, so each is a torch.autograd.Function whose backward calls
 the other two: first AND second derivatives (the R1 penalty, models/ppst_model.py:139-156, differentiates the input
@@ -274,20 +275,6 @@ class _ActGradSum(Function):
         if gg is None:
             return None, None, None
         return (_ActGrad.apply(gg.contiguous(), y) if ctx.act else gg), None, None
-
-
-class _ChannelSum(Function):
-    """NHWC [n,h,w,c] -> f32 [c]: the bias gradient (`grad_input.sum(dim)`, fused_act.py:37-42)."""
-
-    @staticmethod
-    def forward(ctx, g):
-        ctx.shape, ctx.dtype = g.shape, g.dtype
-        s = ops.plane_reduce(g.contiguous(), channels_last=True, want=("sum",))["sum"]      # [n, 1, c]
-        return s.sum(dim=(0, 1))
-
-    @staticmethod
-    def backward(ctx, gb):
-        return gb.to(ctx.dtype).view(1, 1, 1, -1).expand(ctx.shape)
 
 
 class _ConvBiasAct(Function):
