@@ -11,6 +11,7 @@ import sys
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
@@ -377,10 +378,42 @@ def gen_discriminator():
     print("discriminator.npz", store["D_real"], store["D_rec"], store["r1/penalty"])
 
 
+def gen_rscl():
+    """networks/rscl.py (aliased as models.networks.rscl) on deterministic queues / features (oracle.rscl_oracle.make_*):
+    loss values with and without feat_k0 on every level, before and after the reference's enqueue sequence
+    (ppst_model.py:214-219 pattern: six single-row calls per level), pointers, and a checksum of each queue."""
+    RH.install()
+    import types
+    from oracle import rscl_oracle as RO
+    rscl = sys.modules["models.networks.rscl"]
+    crit = rscl.rsclLoss(types.SimpleNamespace(nce_T=0.07, num_gpus=1))
+    store = {}
+    for layer in range(4):
+        getattr(crit, "queue_data_A%d" % layer).copy_(RO.make_queue(layer))
+    for layer in range(4):
+        q, k, k0 = RO.make_feats(3 * layer), RO.make_feats(3 * layer + 1), RO.make_feats(3 * layer + 2)
+        store["loss/%d" % layer] = np.float64(crit(q, k, None, layer).item())
+        store["loss_k0/%d" % layer] = np.float64(crit(q, k, k0, layer).item())
+        for j in range(3):
+            crit.dequeue_and_enqueue(k[j:j + 1], layer)
+        for j in range(3):
+            crit.dequeue_and_enqueue(k0[j:j + 1], layer)
+        store["loss_after/%d" % layer] = np.float64(crit(q, k, k0, layer).item())
+    for i in range(4):
+        qd = getattr(crit, "queue_data_A%d" % i)
+        store["queue_head/%d" % i] = qd[:, :8].numpy().copy()                 # the written columns (+2 untouched)
+        store["queue_sum/%d" % i] = np.float64(qd.double().sum().item())
+        store["ptr/%d" % i] = np.int64(int(getattr(crit, "queue_ptr_A%d" % i)))
+    np.savez_compressed(os.path.join(OUT, "rscl.npz"), **store)
+    print("rscl.npz", [float(store["loss/%d" % i]) for i in range(4)])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["ops", "layers", "function", "nets", "discriminator"]
+    which = sys.argv[1:] or ["ops", "layers", "function", "nets", "discriminator", "rscl"]
+    if "rscl" in which:
+        gen_rscl()
     if "discriminator" in which:
         gen_discriminator()
     if "ops" in which:
