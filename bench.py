@@ -172,6 +172,64 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_train(args):
+    """--impl reference --workload train: the reference's CPU path for the stage-1 iteration (oracle port: its fp32 torch
+    expression of E1 / E2 / G / D under torch.autograd, all host threads), each step a bounded sample: ONE iteration
+    (generator step with the L1 + GAN losses, discriminator step) on 2 images at 256^2."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ppst_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    size, batch = 256, 2
+
+    def leaf(sd):
+        return {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and not k.endswith("kernel")) else v) for k, v in sd.items()}
+    sdE1, sdE2, sdG = O.make_networks(0)
+    for k in sdG:
+        if k.endswith("noise.weight"):
+            sdG[k] = torch.zeros_like(sdG[k])
+    rE1, rE2, rG, rD = leaf(sdE1), leaf(sdE2), leaf(sdG), leaf(O.make_discriminator(size, seed=0))
+    gp = [v for d in (rE1, rE2, rG) for v in d.values() if v.requires_grad]
+    dp = [v for v in rD.values() if v.requires_grad]
+    og = torch.optim.Adam(gp, lr=2e-3, betas=(0.0, 0.99))
+    od = torch.optim.Adam(dp, lr=2e-3, betas=(0.0, 0.99))
+    real = O.make_portraits(batch, size, size, seed=77, smooth=True)
+
+    def rec(x):
+        return O.generator(rG, O.encoder_con(rE1, x), O.encoder_col(rE2, x)[0])
+
+    def iteration():
+        og.zero_grad(set_to_none=True)
+        r = rec(real)
+        ((r - real).abs().mean() + 0.5 * O.gan_loss(O.discriminator(rD, r), True)).backward()
+        og.step()
+        od.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            r = rec(real[: batch // 2])
+        sum(O.d_losses(rD, real, r).values()).backward()
+        od.step()
+    steps, warm = max(1, min(args.steps, 3)), 1
+    for _ in range(warm):
+        iteration()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        iteration()
+    dt = (time.perf_counter() - t0) / steps
+    v = batch / dt
+    line = {"impl": "reference", "metric": "training images/s @256^2 (stage 1: G step + D step + R1/16)", "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5 stage-1 training @256^2; reference arm = bounded sample of 2 images per iteration on host "
+                                   "cores (oracle port of the reference's pure-PyTorch CPU path; R1 step not included)",
+                       "batch": batch, "size": size},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": "1 iteration (G step + D step) on 2 images @256^2 per step, %d step(s)" % steps},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def run_train(args):
     """BASELINE configs[4] (training step, DDP with NCCL gradient all-reduce at 1/2/4/8 GPUs): training stage 1 at 256^2,
     8 images per GPU (weak scaling) -- generator step (E1, E2, G forward + backward, D forward + input gradient), discriminator
@@ -227,7 +285,7 @@ def main():
                     help="swap: the headline metric (BASELINE configs[1]); train: configs[4], training stage 1 at 256^2")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference_train(args) if args.workload == "train" else run_reference(args)
     if args.workload == "train":
         return run_train(args)
 
