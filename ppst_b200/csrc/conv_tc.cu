@@ -217,14 +217,20 @@ __device__ __forceinline__ void epilogue_rows_bf16(uint32_t taddr, uint32_t bias
   const uint32_t my_row = stage_u32 + (uint32_t)lane * 64u;
   const uint32_t wsw = (uint32_t)(lane >> 1) & 3u;                 // swizzle of the row this lane writes
   const int rpar = lane >> 4, cp = lane & 15;                     // statistics: row parity, channel pair
+  // software pipeline over the 32-column chunks: the TMEM load of chunk c0 + 32 is in flight while chunk c0 is converted,
+  // staged and stored (tcgen05.wait::ld waits for every outstanding load, so the next one is issued right after the wait)
+  uint32_t rn[32];
+  tmem_ld32(taddr, rn);
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     uint32_t r[32];
-    tmem_ld32(taddr + (uint32_t)c0, r);
     uint32_t bb[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) lds128(bias_u32 + (uint32_t)(c0 + 4 * j) * 4u, *reinterpret_cast<uint32_t(*)[4]>(&bb[4 * j]));
     tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = rn[j];
+    if (c0 + 32 < BN) tmem_ld32(taddr + (uint32_t)(c0 + 32), rn);
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
