@@ -112,7 +112,7 @@ def load_traffic():
 
 
 def make_inputs(pairs, rank):
-    from oracle import ppst_oracle as O     # seeded synthetic portraits only (input generation, not compute)
+    from ppst_b200 import synthetic as O    # seeded synthetic portraits
     c = O.make_portraits(pairs, SIZE, SIZE, seed=1234 + rank)
     s = O.make_portraits(pairs, SIZE, SIZE, seed=4321 + rank, smooth=True)
     return c, s
@@ -294,8 +294,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device: there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    from oracle import ppst_oracle as O          # weights/inputs generator + the cpu_baseline leg ONLY
     import ppst_b200
+    from ppst_b200 import synthetic as O         # seeded weights / inputs (the oracle is only touched by the CPU legs)
     from ppst_b200 import _lib, ops
 
     warm = max(3, args.warmup)

@@ -113,11 +113,13 @@ PPST_API int ppst_blur_nhwc(void* out, const void* in, const float* kernel, int6
  *   vmax  = max over ALL pixels of (x if pixel in region r else 0)   == amax(x * onehot_r)
  *           (with n_regions == 1 and labels == NULL: plain max)
  * scratch: f32 workspace of ppst_plane_reduce_scratch_elems(n, c, hw, n_regions) elements.
+ * border > 0 (channels_last only; w_row = row width, hw % w_row == 0): x is [n, hw/w_row + 2*border, w_row + 2*border, c] and only its
+ * interior is reduced (labels stay [n, hw]).
  * Deterministic (no floating-point atomics). */
 PPST_API int64_t ppst_plane_reduce_scratch_elems(int64_t n, int64_t c, int64_t hw, int n_regions);
 PPST_API int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const void* x, const uint8_t* labels,
                       const float* shift, float* scratch, int64_t n, int64_t c, int64_t hw, int n_regions,
-                      int label_mode, int channels_last, int dtype, void* stream);
+                      int label_mode, int channels_last, int dtype, int w_row, int border, void* stream);
 
 /* GAP / GMP of a bilinear (align_corners=False) x`scale` upsampling of an f32 NHWC map without materialising it:
  * the correlation branch of the colour encoder interpolates the warped 64x64 features back to the level's resolution
@@ -206,6 +208,11 @@ typedef struct {
      convolution then reads the padded buffer as is.  bias_img_stride > 0: image i adds bias[i*bias_img_stride + c]
      (a per-sample bias, see ppst_modulate_weights). */
   int32_t out_pad, bias_img_stride;
+  /* out_pad_trim (0 .. out_pad): the bottom / right border is out_pad - out_pad_trim pixels wide, i.e. the buffer is
+     [n, full_h + 2*out_pad - out_pad_trim, full_w + 2*out_pad - out_pad_trim, cout_stride] -- the asymmetric
+     (2, 1, 2, 1) reflection padding in front of the blurred stride-2 convolutions (stylegan2_layers.py:517-523);
+     the border itself is written by ppst_pad_border. */
+  int32_t out_pad_trim;
 } ppst_conv_desc;
 
 /* CUDA-core implicit GEMM (fp32 accumulate; any channel counts).  fp32 mode and the thin layers
@@ -226,11 +233,13 @@ PPST_API int ppst_conv_tc(void* out, const void* in, const void* weight, const f
  * ppst_conv1x1_in_nchw : FromRGB = ConvLayer(3, 32, 1) + FusedLeakyReLU (stylegan2_layers.py:497-555;
  *   encoder_con.py:26, encoder_col.py:27).  x is the NCHW f32 image [n, cin<=4, hw] (the layout conversion is fused),
  *   out NHWC [n, hw, cout_stride] slice [c_off, c_off+cout); w f32 [cout][cin]; v = lrelu(x.w + bias) * gain.
+ *   out_border > 0 (needs the row width w_row, hw % w_row == 0): out is [n, hw/w_row + 2*out_border, w_row + 2*out_border, cout_stride]
+ *   and the result goes to its interior (border: ppst_pad_border).
  * ppst_conv1x1_thin_out: ToRGB's EqualConv2d(128, 3, 1) (stylegan2_layers.py:484): x NHWC [pixels, cin],
  *   out f32 [pixels, cout], w f32 [cout][cin]. */
 PPST_API int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, const float* bias, int64_t n, int cin,
                          int64_t hw, int cout, int cout_stride, int c_off, int has_act, float slope, float gain,
-                         int out_dtype, void* stream);
+                         int out_dtype, int w_row, int out_border, void* stream);
 PPST_API int ppst_conv1x1_thin_out(float* out, const void* x, const float* w, const float* bias, int64_t pixels, int cin,
                           int cout, int in_dtype, void* stream);
 
@@ -260,6 +269,14 @@ PPST_API int ppst_modulate_weights(void* out_w, float* out_bias, const float* w,
                           const float* base_bias, int64_t n, int64_t rows, int taps, int cin, void* stream);
 PPST_API int ppst_fill_border(void* buf, const float* a, const float* b, int64_t n, int h, int w, int c, int pad, int dtype,
                      void* stream);
+
+/* Border of a padded NHWC buffer [n, pt + h + pb, pl + w + pr, c] from its own interior: mode 1 reflect
+ * (nn.ReflectionPad2d, stylegan2_layers.py:517), 2 replicate (nn.ReplicationPad2d, generator.py:12-26,180-231), 0 zero.
+ * Producers write the interior (ppst_conv_desc.out_pad, ppst_apply_desc.out_border, ppst_resample out_border, ...), so
+ * padding costs one pass over the BORDER instead of a read + write of the whole tensor.  bf16 (c % 8 == 0) or f32
+ * (c % 4 == 0), dense channels. */
+PPST_API int ppst_pad_border(void* buf, int64_t n, int h, int w, int c, int pt, int pb, int pl, int pr, int mode, int dtype,
+                    void* stream);
 
 /* Weight gradient of a convolution on the tcgen05 path -- the training step's share of the convolution work
  * (SURVEY.md 8(f)4).  Replaces what torch.autograd / cuDNN compute for the `weight` of F.conv2d in EqualConv2d
@@ -326,6 +343,9 @@ typedef struct {
   int32_t res_mode;               /* 0 none, 1 same size, 2 bilinear x2 from [n, h/2, w/2, c] */
   int32_t x_dtype, res_dtype, out_dtype;
   int32_t out_c_stride, out_c_off; /* destination channel stride / offset (concat) */
+  /* out_border > 0: `out` is [n, OH + 2*out_border, OW + 2*out_border, out_c_stride] and the (OH x OW) result goes to
+     its interior (border: ppst_pad_border).  res_border > 0: `res` carries such a border and is read at its interior. */
+  int32_t out_border, res_border;
 } ppst_apply_desc;
 
 /* out: [n, h*up + pad_t + pad_b, w*up + pad_l + pad_r, out_c_stride]; a,b,ra,rb: f32 [n, c] or NULL (1 / 0). */
@@ -347,10 +367,12 @@ PPST_API int ppst_affine_apply_torgb(void* out, float* rgb_out, const void* x, c
  *         F.adaptive_avg_pool2d encoder_col.py:119-122) -- requires in % out == 0
  * a, b: NULL, or f32 [n, c] (b may be NULL = 0): every SOURCE sample is first mapped to lrelu(x*a + b, slope) -- the
  *       InstanceNorm + PReLU that ends a feature head (generator.py:180-231) applied on load, so the normalised map
- *       that generator.py:272-278 pools and interpolates is never written to memory. */
+ *       that generator.py:272-278 pools and interpolates is never written to memory.
+ * in_border / out_border: x / out carry a border of that many pixels (buffers [n, H + 2*border, W + 2*border, .])
+ *       and are addressed at their interiors. */
 PPST_API int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
                   int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
-                  const float* b, float slope, void* stream);
+                  const float* b, float slope, int in_border, int out_border, void* stream);
 
 /* Adjoints of the x2 upsamplings and of the reflection pad for the training path, all as gathers with a fixed summation
  * order (deterministic; ATen's upsample_bilinear2d_backward scatters with atomics).  bf16 (c % 8 == 0) or f32 (c % 4 == 0).

@@ -25,7 +25,7 @@ class ConvDesc(ctypes.Structure):
                 ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
                 ("in_row_pitch", ctypes.c_int64), ("in_img_pitch", ctypes.c_int64),
                 ("w_img_rows", ctypes.c_int32), ("split_terms", ctypes.c_int32),
-                ("out_pad", ctypes.c_int32), ("bias_img_stride", ctypes.c_int32)]
+                ("out_pad", ctypes.c_int32), ("bias_img_stride", ctypes.c_int32), ("out_pad_trim", ctypes.c_int32)]
 
 
 class WgradDesc(ctypes.Structure):
@@ -38,7 +38,7 @@ class ApplyDesc(ctypes.Structure):
                 ("n", "h", "w", "c", "up", "pad_t", "pad_b", "pad_l", "pad_r", "pad_mode")] + \
                [("pre_slope", c_float), ("pre_gain", c_float), ("post_slope", c_float), ("post_gain", c_float)] + \
                [(n, ctypes.c_int32) for n in ("res_mode", "x_dtype", "res_dtype", "out_dtype", "out_c_stride",
-                                              "out_c_off")]
+                                              "out_c_off", "out_border", "res_border")]
 
 
 _SIGS = {
@@ -53,7 +53,7 @@ _SIGS = {
     "ppst_upfirdn2d": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 14 + [c_void_p]),
     "ppst_blur_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 11 + [c_void_p]),
     "ppst_plane_reduce_scratch_elems": (c_i64, [c_i64, c_i64, c_i64, c_int]),
-    "ppst_plane_reduce": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_plane_reduce": (c_int, [c_void_p] * 7 + [c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_upsample_reduce_scratch_elems": (c_i64, [c_i64, c_int, c_int]),
     "ppst_upsample_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64] + [c_int] * 6 + [c_void_p, c_void_p]),
     "ppst_plane_dot_scratch_elems": (c_i64, [c_i64, c_i64, c_i64]),
@@ -78,14 +78,16 @@ _SIGS = {
     "ppst_scale_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_modulate_weights": (c_int, [c_void_p] * 6 + [c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_fill_border": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ppst_pad_border": (c_int, [c_void_p, c_i64] + [c_int] * 9 + [c_void_p]),
     "ppst_conv1x1_in_nchw": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_i64, c_int, c_int, c_int, c_int, c_float, c_float,
-                                                     c_int, c_void_p]),
+                                                     c_int, c_int, c_int, c_void_p]),
     "ppst_conv1x1_thin_wgrad_scratch_elems": (c_i64, [c_i64, c_i64, c_int]),
     "ppst_conv1x1_thin_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "ppst_conv1x1_thin_out": (c_int, [c_void_p] * 4 + [c_i64, c_int, c_int, c_int, c_void_p]),
     "ppst_in_coeffs": (c_int, [c_void_p] * 6 + [c_i64, c_void_p, c_i64, c_i64, c_i64, c_double, c_float, c_int, c_void_p]),
     "ppst_affine_apply": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p]),
-    "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p, c_void_p, c_float, c_void_p]),
+    "ppst_resample": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 10 + [c_void_p, c_void_p, c_float, c_int, c_int,
+                                                                           c_void_p]),
     "ppst_upsample2x_backward": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ppst_reflect_pad_backward": (c_int, [c_void_p, c_void_p, c_i64] + [c_int] * 8 + [c_void_p]),
     "ppst_linear": (c_int, [c_void_p] * 4 + [c_i64] * 4 + [c_float, c_float, c_int, c_void_p]),
@@ -153,9 +155,20 @@ def stream():
 
 
 def require_cuda(*tensors):
+    """Every tensor of a launch must live on the CURRENT CUDA device: the launch goes to that device's current stream
+    with raw pointers (SwapModel / Engine enter `torch.cuda.device(self.device)` themselves; direct callers of the
+    operators set the device as they would for any torch op)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("ppst_b200: expected a CUDA tensor (there is no CPU fallback); got device %s" % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError("ppst_b200: tensor on %s but the current CUDA device is cuda:%d -- wrap the call in "
+                               "torch.cuda.device(tensor.device)" % (t.device, cur))
 
 
 def launch_count():

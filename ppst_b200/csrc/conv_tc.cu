@@ -52,6 +52,7 @@ struct Params {
   int w_img_rows;                       // weight rows per image (0: one weight matrix for the whole batch)
   int split_seg_kb;                     // 3-term split GEMM: k-blocks per [hi]/[lo] segment (0: plain)
   int out_pad;                          // border (pixels) of the output buffer: stores go to its interior
+  int out_pad_trim;                     // the bottom / right border is out_pad - out_pad_trim pixels
   int bias_img_stride;                  // > 0: image i adds bias[i * bias_img_stride + c] (per-sample bias)
   int stages, kps;                      // pipeline depth; k-blocks per pipeline stage (one barrier round trip each)
   // halo kernel only
@@ -442,7 +443,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = q * 32 + lane;                       // row of the 128-pixel tile
     const int ety = row / p.tw, etx = row - ety * p.tw;
     float* s_bias_g = s_bias + group * kBiasSmem;
-    const int fh_pad = p.full_h + 2 * p.out_pad, fw_pad = p.full_w + 2 * p.out_pad;
+    const int fh_pad = p.full_h + 2 * p.out_pad - p.out_pad_trim, fw_pad = p.full_w + 2 * p.out_pad - p.out_pad_trim;
     int it = 0, cur_img = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != group) continue;
@@ -704,7 +705,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int row = q * 32 + lane;
     const int ety = row / p.tw, etx = row - ety * p.tw;
     float* s_bias_g = s_bias + group * kBiasSmem;
-    const int fh_pad = p.full_h + 2 * p.out_pad, fw_pad = p.full_w + 2 * p.out_pad;
+    const int fh_pad = p.full_h + 2 * p.out_pad - p.out_pad_trim, fw_pad = p.full_w + 2 * p.out_pad - p.out_pad_trim;
     int it = 0, cur_img = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != group) continue;
@@ -953,7 +954,7 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  uint64_t v[12];
+  uint64_t v[13];
   bool operator==(const MapKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
 };
 struct MapKeyHash {
@@ -977,7 +978,8 @@ static int encode_map(CUtensorMap* out, const void* base, int rank, const uint64
     key.v[6 + i] = ((uint64_t)box[i] << 32) | estr[i];
   }
   key.v[10] = strides_b[0];
-  key.v[11] = rank > 2 ? (strides_b[1] ^ (strides_b[2] << 1)) : 0;
+  key.v[11] = rank > 2 ? strides_b[1] : 0;
+  key.v[12] = rank > 3 ? strides_b[2] : 0;
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(key);
@@ -1008,15 +1010,22 @@ static void pick_tile(int out_h, int out_w, int& th, int& tw) {
   th = BM / tw;
 }
 
-static int g_num_sms = 0;
+// per-device state: SM count and "dynamic shared memory attribute already set" flags (cudaFuncSetAttribute is per device)
+constexpr int kMaxDevices = 64;
+static int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+static int g_num_sms[kMaxDevices] = {0};
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  const int dev = cur_device();
+  if (g_num_sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms[dev] = v > 0 ? v : 148;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 template <int BN, int BKC, bool OUT_F32>
@@ -1052,7 +1061,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
   }
   const int smem_total = p.stages * p.kps * S::kKblockBytes + S::kFixedBytes;
   p.w_img_rows = d.w_img_rows;
-  p.out_pad = d.out_pad; p.bias_img_stride = d.bias_img_stride;
+  p.out_pad = d.out_pad; p.out_pad_trim = d.out_pad_trim; p.bias_img_stride = d.bias_img_stride;
   p.split_seg_kb = d.split_terms == 3 ? (d.cin / 2) / BKC : 0;
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
   p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
@@ -1078,12 +1087,12 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     if (rc) return rc;
   }
   auto kern = conv_tc_kernel<BN, BKC, OUT_F32>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};
+  if (!attr_set[cur_device()]) {
     int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kMaxDynamic),
                         "cudaFuncSetAttribute(conv_tc)");
     if (rc) return rc;
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   float* ssum = stats;
@@ -1150,14 +1159,14 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
     if (rc) return rc;
   }
   p.w_img_rows = d.w_img_rows;
-  p.out_pad = d.out_pad; p.bias_img_stride = d.bias_img_stride;
+  p.out_pad = d.out_pad; p.out_pad_trim = d.out_pad_trim; p.bias_img_stride = d.bias_img_stride;
   auto kern = conv_tc_halo_kernel<BN, BKC, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {false};
+  if (!attr_set[cur_device()]) {
     int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kMaxDynamic),
                         "cudaFuncSetAttribute(conv_tc_halo)");
     if (rc) return rc;
-    attr_set = true;
+    attr_set[cur_device()] = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   float* ssum = stats;
@@ -1226,12 +1235,12 @@ int tc_wgrad_mn(float* partials, const void* dy, const void* x, const ppst_wgrad
 #define PPST_WG(BN_)                                                                                              \
   do {                                                                                                            \
     auto kern = tc::conv_wgrad_mn_kernel<BN_>;                                                                    \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
+    static bool attr_set[tc::kMaxDevices] = {false};                                                              \
+    if (!attr_set[tc::cur_device()]) {                                                                            \
       int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024), \
                           "cudaFuncSetAttribute(conv_wgrad_mn)");                                                 \
       if (rc) return rc;                                                                                          \
-      attr_set = true;                                                                                            \
+      attr_set[tc::cur_device()] = true;                                                                          \
     }                                                                                                             \
     kern<<<grid, 192, smem_total, st>>>(map_dy, map_x, partials, p);                                              \
   } while (0)
@@ -1273,7 +1282,8 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
   PPST_REQUIRE(d.w_img_rows == 0 || (d.phases_y * d.phases_x == 1 && d.w_img_rows >= d.cout), PPST_ERR_ARG,
                "conv_tc: per-image weights need a single phase and w_img_rows >= cout");
   PPST_REQUIRE(d.out_dtype == PPST_BF16 || stats == nullptr, PPST_ERR_UNSUPPORTED, "conv_tc: statistics need bf16 output");
-  PPST_REQUIRE(d.out_pad >= 0 && d.out_pad <= 8, PPST_ERR_ARG, "conv_tc: out_pad %d", d.out_pad);
+  PPST_REQUIRE(d.out_pad >= 0 && d.out_pad <= 8 && d.out_pad_trim >= 0 && d.out_pad_trim <= d.out_pad, PPST_ERR_ARG,
+               "conv_tc: out_pad %d / out_pad_trim %d", d.out_pad, d.out_pad_trim);
   PPST_REQUIRE(d.bias_img_stride == 0 || (bias != nullptr && d.bias_img_stride >= d.cout && d.cout <= tc::kBiasSmem),
                PPST_ERR_ARG, "conv_tc: per-sample bias needs bias_img_stride >= cout and cout <= %d", tc::kBiasSmem);
   PPST_REQUIRE(d.cin % 32 == 0, PPST_ERR_UNSUPPORTED, "conv_tc: cin=%d must be a multiple of 32", d.cin);

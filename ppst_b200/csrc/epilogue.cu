@@ -187,17 +187,18 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(TO* __restrict__ out,
       for (int e = 0; e < V; ++e) y[e] = lrelu_slope(fmaf(xv[e], av[e], bv[e]), d.pre_slope) * d.pre_gain;
       if (d.res_mode != 0) {
         float rv[V];
+        const int rbd = d.res_border;
         if (d.res_mode == 1) {
-          load_ch<TX, V>(rv, res + (((int64_t)ni * hu + uy) * wu + ux) * d.c + ch);
+          load_ch<TX, V>(rv, res + (((int64_t)ni * (hu + 2 * rbd) + uy + rbd) * (wu + 2 * rbd) + ux + rbd) * d.c + ch);
         } else {
-          const int lh = hu / 2, lw = wu / 2;
+          const int lh = hu / 2, lw = wu / 2, lwp = lw + 2 * rbd;
           const Bilin2 by = bilin_x2(uy, lh), bx = bilin_x2(ux, lw);
           float v00[V], v01[V], v10[V], v11[V];
-          const TX* rp = res + (int64_t)ni * lh * lw * d.c + ch;
-          load_ch<TX, V>(v00, rp + ((int64_t)by.i0 * lw + bx.i0) * d.c);
-          load_ch<TX, V>(v01, rp + ((int64_t)by.i0 * lw + bx.i1) * d.c);
-          load_ch<TX, V>(v10, rp + ((int64_t)by.i1 * lw + bx.i0) * d.c);
-          load_ch<TX, V>(v11, rp + ((int64_t)by.i1 * lw + bx.i1) * d.c);
+          const TX* rp = res + ((int64_t)ni * (lh + 2 * rbd) + rbd) * lwp * d.c + (int64_t)rbd * d.c + ch;
+          load_ch<TX, V>(v00, rp + ((int64_t)by.i0 * lwp + bx.i0) * d.c);
+          load_ch<TX, V>(v01, rp + ((int64_t)by.i0 * lwp + bx.i1) * d.c);
+          load_ch<TX, V>(v10, rp + ((int64_t)by.i1 * lwp + bx.i0) * d.c);
+          load_ch<TX, V>(v11, rp + ((int64_t)by.i1 * lwp + bx.i1) * d.c);
 #pragma unroll
           for (int e = 0; e < V; ++e)
             rv[e] = by.l0 * (bx.l0 * v00[e] + bx.l1 * v01[e]) + by.l1 * (bx.l0 * v10[e] + bx.l1 * v11[e]);
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(256) affine_apply_kernel(TO* __restrict__ out,
 #pragma unroll
       for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], d.post_slope) * d.post_gain;
     }
-    store_ch<TO, V>(out + (((int64_t)ni * oh + oy) * ow + ox) * d.out_c_stride + d.out_c_off + ch, y);
+    const int ob = d.out_border;
+    store_ch<TO, V>(out + (((int64_t)ni * (oh + 2 * ob) + oy + ob) * (ow + 2 * ob) + ox + ob) * d.out_c_stride + d.out_c_off + ch, y);
   }
 }
 
@@ -292,18 +294,19 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
   bool zero_row = false;
   const int uy = map_pad(oy - d.pad_t, hu, d.pad_mode, zero_row);
   const TX* xrow = x + (((int64_t)ni * d.h + uy / d.up) * d.w) * d.c + ch;
-  TO* orow = out + (((int64_t)ni * oh + oy) * ow) * d.out_c_stride + d.out_c_off + ch;
+  const int ob = d.out_border, rbd = d.res_border;
+  TO* orow = out + (((int64_t)ni * (oh + 2 * ob) + oy + ob) * (ow + 2 * ob) + ob) * d.out_c_stride + d.out_c_off + ch;
   const TX* r0 = nullptr;
   const TX* r1 = nullptr;
   Bilin2 by{0, 0, 1.f, 0.f};
   const int lw = wu / 2;
   if (RES == 1) {
-    r0 = res + (((int64_t)ni * hu + uy) * wu) * d.c + ch;
+    r0 = res + (((int64_t)ni * (hu + 2 * rbd) + uy + rbd) * (wu + 2 * rbd) + rbd) * d.c + ch;
   } else if (RES == 2) {
     const int lh = hu / 2;
     by = bilin_x2(uy, lh);
-    r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
-    r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
+    r0 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i0 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
+    r1 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i1 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
   }
   const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
   for (int ox0 = lane; ox0 < ow; ox0 += U * lanes) {
@@ -411,9 +414,10 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
   }
   const Bilin2 by = bilin_x2(oy, lh);
   const TX* xrow = x + (((int64_t)ni * h + oy) * w) * d.c + ch;
-  TO* orow = out + (((int64_t)ni * h + oy) * w) * d.out_c_stride + d.out_c_off + ch;
-  const TX* r0 = res + (((int64_t)ni * lh + by.i0) * lw) * d.c + ch;
-  const TX* r1 = res + (((int64_t)ni * lh + by.i1) * lw) * d.c + ch;
+  const int ob = d.out_border, rbd = d.res_border;
+  TO* orow = out + (((int64_t)ni * (h + 2 * ob) + oy + ob) * (w + 2 * ob) + ob) * d.out_c_stride + d.out_c_off + ch;
+  const TX* r0 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i0 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
+  const TX* r1 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i1 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
   const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
   float wr[RGB ? 3 : 1][RGB ? V : 1];
   float* rgb_row = nullptr;
@@ -513,9 +517,11 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
                                                        int in_h, int in_w, int out_h, int out_w, int c,
                                                        int out_c_stride, int out_c_off, int mode,
                                                        const float* __restrict__ a, const float* __restrict__ b,
-                                                       float slope) {
+                                                       float slope, int ib, int ob) {
+  // ib / ob: border (pixels) of the input / output buffers; both are addressed at their interiors
   const int cv = c / V;
   const int64_t total = n * out_h * out_w * cv;
+  const int in_wp = in_w + 2 * ib;
   const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(t % cv);
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
     const int oy = (int)(r % out_h);
     const int64_t ni = r / out_h;
     const int ch = cg * V;
-    const TX* base = x + ni * in_h * in_w * (int64_t)c + ch;
+    const TX* base = x + ((ni * (in_h + 2 * ib) + ib) * in_wp + ib) * (int64_t)c + ch;
     float y[V];
     // optional per-(n, c) affine + leaky/PReLU slope applied to every SOURCE sample (the normalisation + activation of
     // the tensor being resampled, so that it never has to be materialised)
@@ -548,10 +554,10 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
       const int y1 = y0 + ((y0 < in_h - 1) ? 1 : 0), x1 = x0 + ((x0 < in_w - 1) ? 1 : 0);
       const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
       float v00[V], v01[V], v10[V], v11[V];
-      load_ch<TX, V>(v00, base + ((int64_t)y0 * in_w + x0) * c);
-      load_ch<TX, V>(v01, base + ((int64_t)y0 * in_w + x1) * c);
-      load_ch<TX, V>(v10, base + ((int64_t)y1 * in_w + x0) * c);
-      load_ch<TX, V>(v11, base + ((int64_t)y1 * in_w + x1) * c);
+      load_ch<TX, V>(v00, base + ((int64_t)y0 * in_wp + x0) * c);
+      load_ch<TX, V>(v01, base + ((int64_t)y0 * in_wp + x1) * c);
+      load_ch<TX, V>(v10, base + ((int64_t)y1 * in_wp + x0) * c);
+      load_ch<TX, V>(v11, base + ((int64_t)y1 * in_wp + x1) * c);
       xf(v00); xf(v01); xf(v10); xf(v11);
 #pragma unroll
       for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
@@ -562,7 +568,7 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
       for (int dy = 0; dy < fh; ++dy)
         for (int dx = 0; dx < fw; ++dx) {
           float v[V];
-          load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_w + (ox * fw + dx)) * c);
+          load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_wp + (ox * fw + dx)) * c);
           xf(v);
 #pragma unroll
           for (int e = 0; e < V; ++e) y[e] += v[e];
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
 #pragma unroll
       for (int e = 0; e < V; ++e) y[e] *= inv;
     }
-    store_ch<TO, V>(out + ((ni * out_h + oy) * out_w + ox) * (int64_t)out_c_stride + out_c_off + ch, y);
+    store_ch<TO, V>(out + ((ni * (out_h + 2 * ob) + oy + ob) * (out_w + 2 * ob) + ox + ob) * (int64_t)out_c_stride + out_c_off + ch, y);
   }
 }
 
@@ -619,6 +625,8 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
   PPST_REQUIRE(d.res_mode == 0 || d.res_dtype == d.x_dtype, PPST_ERR_UNSUPPORTED,
                "affine_apply: residual dtype must equal x dtype");
   PPST_REQUIRE(d.out_c_off >= 0 && d.out_c_off + d.c <= d.out_c_stride, PPST_ERR_ARG, "affine_apply: channel slice");
+  PPST_REQUIRE(d.out_border >= 0 && d.out_border <= 8 && d.res_border >= 0 && d.res_border <= 8, PPST_ERR_ARG,
+               "affine_apply: out_border / res_border");
   const bool vec = (d.c % 8 == 0) && (d.out_c_stride % 8 == 0) && (d.out_c_off % 8 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                      reinterpret_cast<uintptr_t>(res)) & 15) == 0;
@@ -694,10 +702,10 @@ extern "C" int ppst_affine_apply_torgb(void* out, float* rgb_out, const void* x,
 
 extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
                              int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
-                             const float* b, float slope, void* stream) {
+                             const float* b, float slope, int in_border, int out_border, void* stream) {
   using namespace ppst;
-  PPST_REQUIRE(out && x && n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && c > 0, PPST_ERR_ARG,
-               "resample: bad args");
+  PPST_REQUIRE(out && x && n > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && c > 0 && in_border >= 0 &&
+               out_border >= 0, PPST_ERR_ARG, "resample: bad args");
   PPST_REQUIRE(mode == 0 || (mode == 1 && in_h % out_h == 0 && in_w % out_w == 0), PPST_ERR_UNSUPPORTED,
                "resample: adaptive average needs integer windows (%dx%d -> %dx%d)", in_h, in_w, out_h, out_w);
   PPST_REQUIRE(out_c_off >= 0 && out_c_off + c <= out_c_stride, PPST_ERR_ARG, "resample: channel slice");
@@ -710,10 +718,12 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
   do {                                                                                                         \
     if (vec)                                                                                                   \
       resample_kernel<TX, TO, 8><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
-                                                       out_c_stride, out_c_off, mode, a, b, slope);            \
+                                                       out_c_stride, out_c_off, mode, a, b, slope, in_border,  \
+                                                       out_border);                                            \
     else                                                                                                       \
       resample_kernel<TX, TO, 1><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, n, in_h, in_w, out_h, out_w, c, \
-                                                       out_c_stride, out_c_off, mode, a, b, slope);            \
+                                                       out_c_stride, out_c_off, mode, a, b, slope, in_border,  \
+                                                       out_border);                                            \
   } while (0)
   if (in_dtype == PPST_F32 && out_dtype == PPST_F32) PPST_RS(float, float);
   else if (in_dtype == PPST_BF16 && out_dtype == PPST_BF16) PPST_RS(__nv_bfloat16, __nv_bfloat16);

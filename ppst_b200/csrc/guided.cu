@@ -219,15 +219,13 @@ extern "C" int ppst_guided_smooth(float* out, const float* src, const float* gui
   int32_t* bufB = bufA + n * kGfP1 * hw;
   const double inv_area = 1.0 / ((double)(2 * radius + 1) * (2 * radius + 1));
   const int seg = h >= 512 ? 64 : 32;
-  static bool attr = false;
-  if (!attr) {
+  {                                  // per device, so set on every call (a cheap host-side attribute write)
     int rc = cuda_check(cudaFuncSetAttribute(gf_box_h_kernel<float, double, float>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "guided attr");
     if (rc) return rc;
     rc = cuda_check(cudaFuncSetAttribute(gf_box_h_kernel<int32_t, int32_t, int32_t>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "guided attr");
     if (rc) return rc;
-    attr = true;
   }
   gf_products_kernel<<<gf_grid(n * hw), 256, 0, st>>>(bufA, src, guide, n, hw);
   PPST_LAUNCH_CHECK("gf_products_kernel");

@@ -194,7 +194,68 @@ __global__ void __launch_bounds__(256) fill_border_kernel(__nv_bfloat16* __restr
     *reinterpret_cast<uint4*>(buf + ((ni * hp + y) * wp + x) * (int64_t)c + cg * 8) = pk.u;
   }
 }
+
+// Border of a padded NHWC buffer from its own interior (reflect / replicate / zero): one 16-byte vector per thread.
+// Border pixel index k: the pt top rows, the pb bottom rows (full width), then the pl + pr side pixels of the h middle rows.
+template <typename T>
+__global__ void __launch_bounds__(256) pad_border_kernel(T* __restrict__ buf, int h, int w, int c, int pt, int pb, int pl,
+                                                         int pr, int mode) {
+  constexpr int V = 16 / sizeof(T);
+  const int hp = h + pt + pb, wp = w + pl + pr;
+  const int64_t border = (int64_t)(pt + pb) * wp + (int64_t)h * (pl + pr);
+  const int cv = c / V;
+  const int64_t ni = blockIdx.y;
+  T* img = buf + ni * hp * wp * (int64_t)c;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < border * cv; t += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(t % cv);
+    int64_t k = t / cv;
+    int y, x;
+    if (k < (int64_t)pt * wp) { y = (int)(k / wp); x = (int)(k - (int64_t)y * wp); }
+    else if (k < (int64_t)(pt + pb) * wp) { k -= (int64_t)pt * wp; y = pt + h + (int)(k / wp); x = (int)(k % wp); }
+    else {
+      k -= (int64_t)(pt + pb) * wp;
+      y = pt + (int)(k / (pl + pr));
+      const int sx = (int)(k % (pl + pr));
+      x = sx < pl ? sx : w + sx;
+    }
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (mode != 0) {
+      int sy = y - pt, sx = x - pl;
+      if (mode == 1) {                                   // reflect (no edge repeat)
+        sy = sy < 0 ? -sy : (sy >= h ? 2 * (h - 1) - sy : sy);
+        sx = sx < 0 ? -sx : (sx >= w ? 2 * (w - 1) - sx : sx);
+      } else {                                           // replicate
+        sy = sy < 0 ? 0 : (sy >= h ? h - 1 : sy);
+        sx = sx < 0 ? 0 : (sx >= w ? w - 1 : sx);
+      }
+      v = *reinterpret_cast<const uint4*>(img + ((int64_t)(sy + pt) * wp + sx + pl) * c + cg * V);
+    }
+    *reinterpret_cast<uint4*>(img + ((int64_t)y * wp + x) * c + cg * V) = v;
+  }
+}
 }  // namespace ppst
+
+extern "C" int ppst_pad_border(void* buf, int64_t n, int h, int w, int c, int pt, int pb, int pl, int pr, int mode,
+                               int dtype, void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(buf && n > 0 && n <= 65535 && h > 0 && w > 0 && c > 0 && pt >= 0 && pb >= 0 && pl >= 0 && pr >= 0 &&
+               pt + pb + pl + pr > 0, PPST_ERR_ARG, "pad_border: bad args");
+  PPST_REQUIRE(mode >= 0 && mode <= 2, PPST_ERR_ARG, "pad_border: mode %d (0 zero, 1 reflect, 2 replicate)", mode);
+  PPST_REQUIRE(mode != 1 || (pt < h && pb < h && pl < w && pr < w), PPST_ERR_ARG, "pad_border: reflect pad >= size");
+  PPST_REQUIRE((dtype == PPST_BF16 && c % 8 == 0) || (dtype == PPST_F32 && c % 4 == 0), PPST_ERR_UNSUPPORTED,
+               "pad_border: bf16 with c %% 8 == 0 or f32 with c %% 4 == 0");
+  PPST_REQUIRE((reinterpret_cast<uintptr_t>(buf) & 15) == 0, PPST_ERR_ARG, "pad_border: buffer must be 16-byte aligned");
+  const int64_t border = (int64_t)(pt + pb) * (w + pl + pr) + (int64_t)h * (pl + pr);
+  const int64_t vecs = border * (c / (dtype == PPST_BF16 ? 8 : 4));
+  const int64_t blocks = (vecs + 255) / 256;
+  const dim3 grid((unsigned)(blocks < 2048 ? blocks : 2048), (unsigned)n);
+  if (dtype == PPST_BF16)
+    pad_border_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf, h, w, c, pt, pb, pl, pr, mode);
+  else
+    pad_border_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)buf, h, w, c, pt, pb, pl, pr, mode);
+  PPST_LAUNCH_CHECK("pad_border_kernel");
+  return 0;
+}
 
 extern "C" int ppst_modulate_weights(void* out_w, float* out_bias, const float* w, const float* a, const float* b,
                                      const float* base_bias, int64_t n, int64_t rows, int taps, int cin, void* stream) {

@@ -121,7 +121,7 @@ template <typename T, int VEC, int R>
 __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
     float* __restrict__ scratch, const T* __restrict__ x, const uint8_t* __restrict__ labels,
     const float* __restrict__ shift, int64_t c, int64_t hw, int64_t chunk_len, int chunks, int tcols,
-    int label_mode) {
+    int label_mode, int w_row, int border) {
   extern __shared__ float red[];                       // [plane_lanes][tcols*VEC][R][3] -> reduced in place
   const int64_t nidx = blockIdx.x;
   const int chunk = blockIdx.y;
@@ -140,16 +140,21 @@ __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
     for (int r = 0; r < R; ++r) { s[r][e] = 0.f; q[r][e] = 0.f; m[r][e] = -FLT_MAX; }
   }
   if (active) {
-    const T* base = x + (nidx * hw) * c + ch0;
+    // border > 0: x is [n, hw/w_row + 2*border, w_row + 2*border, c]; pixel p = (y, x) of the interior
+    const int64_t wp = w_row + 2 * border;
+    const T* base = border ? x + ((nidx * (hw / w_row + 2 * border) + border) * wp + border) * c + ch0
+                           : x + (nidx * hw) * c + ch0;
     const uint8_t* pl = labels ? labels + nidx * hw : nullptr;
     for (int64_t p = beg + lane_p; p < end; p += planes) {
       float xv[VEC];
+      int64_t po = p;
+      if (border) { const int64_t yy = p / w_row; po = yy * wp + (p - yy * w_row); }
       if (VEC > 1) {
-        Vec16<T> v = ld_vec16_stream(base + p * c);
+        Vec16<T> v = ld_vec16_stream(base + po * c);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) xv[e] = Cvt<T>::to_f(v.v[e]);
       } else {
-        xv[0] = Cvt<T>::to_f(base[p * c]);
+        xv[0] = Cvt<T>::to_f(base[po * c]);
       }
       const int L = (R > 1) ? pl[p] : 0;
 #pragma unroll
@@ -217,7 +222,8 @@ __global__ void plane_reduce_nhwc_final(float* __restrict__ sum, float* __restri
 
 template <typename T, int R>
 static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, const uint8_t* labels, const float* shift,
-                         float* scratch, int64_t n, int64_t c, int64_t hw, int label_mode, int channels_last, cudaStream_t st) {
+                         float* scratch, int64_t n, int64_t c, int64_t hw, int label_mode, int channels_last, int w_row,
+                         int border, cudaStream_t st) {
   const ReducePlan pl = plan_reduce(n, c, hw, channels_last);
   if (!channels_last) {
     dim3 grid((unsigned)(n * c), pl.chunks);
@@ -246,10 +252,11 @@ static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, cons
       if (rc) return rc;
     }
     kern<<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw, pl.chunk_len, pl.chunks, tcols,
-                                             label_mode);
+                                             label_mode, w_row, border);
   } else {
     plane_reduce_nhwc_kernel<T, 1, R><<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw,
-                                                                          pl.chunk_len, pl.chunks, tcols, label_mode);
+                                                                          pl.chunk_len, pl.chunks, tcols, label_mode,
+                                                                          w_row, border);
   }
   PPST_LAUNCH_CHECK("plane_reduce_nhwc_kernel");
   const int64_t tot = n * c * R;
@@ -391,9 +398,11 @@ extern "C" int64_t ppst_plane_reduce_scratch_elems(int64_t n, int64_t c, int64_t
 
 extern "C" int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const void* x, const uint8_t* labels,
                                  const float* shift, float* scratch, int64_t n, int64_t c, int64_t hw, int n_regions,
-                                 int label_mode, int channels_last, int dtype, void* stream) {
+                                 int label_mode, int channels_last, int dtype, int w_row, int border, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(x && scratch && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "plane_reduce: bad args");
+  PPST_REQUIRE(border == 0 || (border > 0 && border <= 8 && channels_last && w_row > 0 && hw % w_row == 0), PPST_ERR_ARG,
+               "plane_reduce: a border needs channels_last and the row width");
   PPST_REQUIRE(n_regions >= 1 && n_regions <= kMaxRegions, PPST_ERR_UNSUPPORTED, "plane_reduce: n_regions=%d (1..%d)",
                n_regions, kMaxRegions);
   PPST_REQUIRE((n_regions == 1) == (labels == nullptr), PPST_ERR_ARG,
@@ -401,7 +410,8 @@ extern "C" int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const vo
   cudaStream_t st = (cudaStream_t)stream;
 #define PPST_RED(R_)                                                                                      \
   PPST_DISPATCH_DTYPE(dtype, T, return launch_reduce<T, R_>(sum, sumsq, vmax, (const T*)x, labels, shift, \
-                                                            scratch, n, c, hw, label_mode, channels_last, st))
+                                                            scratch, n, c, hw, label_mode, channels_last, w_row,   \
+                                                            border, st))
   switch (n_regions) {
     case 1: PPST_RED(1);
     case 2: PPST_RED(2);

@@ -5,10 +5,29 @@ extract_feat_from_image / Rselfcorr / corrm / warp -- with the reference's tenso
 and out) and its `model(*args, command="...")` dispatch, so the evaluators' call sequences run unchanged on
 top of it.  `swap()` is the same sequence kept on the device in NHWC end to end (the benchmarked path).
 """
+import functools
+
 import torch
 
 from . import ops
 from .engine import Engine
+
+
+def _on_own_device(cls):
+    """Every public method runs with the model's device current: launches go to the current device's stream with raw
+    pointers, so SwapModel(device="cuda:1") must not depend on the caller's torch.cuda.set_device()."""
+    def wrap(fn):
+        @functools.wraps(fn)
+        def inner(self, *a, **kw):
+            if torch.cuda.current_device() == self.device.index:
+                return fn(self, *a, **kw)
+            with torch.cuda.device(self.device):
+                return fn(self, *a, **kw)
+        return inner
+    for name, fn in list(vars(cls).items()):
+        if callable(fn) and not name.startswith("_") and not isinstance(fn, (staticmethod, classmethod, property)):
+            setattr(cls, name, wrap(fn))
+    return cls
 
 
 def split_state_dict(sd):
@@ -21,36 +40,76 @@ def split_state_dict(sd):
     return out["E1"], out["E2"], out["G"]
 
 
+@_on_own_device
 class SwapModel:
-    def __init__(self, sdE1, sdE2, sdG, device="cuda", mode="bf16"):
+    def __init__(self, sdE1, sdE2, sdG, device="cuda", mode="bf16", noise_seed=None):
         if not torch.cuda.is_available():
             raise RuntimeError("ppst_b200.SwapModel needs a CUDA device (there is no CPU fallback)")
-        self.engine = Engine(sdE1, sdE2, sdG, device=device, mode=mode)
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            self.engine = Engine(sdE1, sdE2, sdG, device=dev, mode=mode)
         self.device = self.engine.device
         self._noises = None
+        self._noise_gen = None
+        self._noise_rep = {}
         self._graphs = {}
         self._pipes = {}
+        if noise_seed is not None:
+            self.noises = "random"
+            self._noise_gen.manual_seed(int(noise_seed))
 
     @property
     def noises(self):
-        """Optional dict '<block>.conv{1,2}' -> [B,1,H,W] NoiseInjection inputs (stylegan2_layers.py:376-399).  None:
-        the noise term is skipped (the reference would draw fresh N(0,1) noise; its weight is 0 at init)."""
+        """NoiseInjection inputs (stylegan2_layers.py:376-399).
+          None      -- the noise term is OFF (exact for random-init / noise.weight == 0 networks; NOT a sample of the
+                       reference's output distribution for a trained checkpoint);
+          dict      -- '<block>.conv{1,2}' -> [B,1,H,W] explicit maps (parity tests, reproducible outputs);
+          "random"  -- what the reference does (its evaluators leave fix_noise commented out): fresh N(0,1) maps on every
+                       generator pass, drawn on the device from a generator seeded by `noise_seed` (SwapModel(...,
+                       noise_seed=s)).  swap_graph / swap_pipelined capture the draws, so a replay re-uses the maps
+                       drawn at capture time's generator offsets (torch's graph-safe Philox state advances per replay)."""
         return self._noises
 
     @noises.setter
     def noises(self, value):
-        self._noises = None if value is None else {
-            k: v.to(self.device, torch.float32).contiguous() for k, v in value.items()}
+        if isinstance(value, str):
+            if value != "random":
+                raise ValueError("noises: None, a dict of maps, or 'random'")
+            self._noises = "random"
+            if self._noise_gen is None:
+                self._noise_gen = torch.Generator(device=self.device)
+        else:
+            self._noises = None if value is None else {
+                k: v.to(self.device, torch.float32).contiguous() for k, v in value.items()}
         self._graphs.clear()
         self._pipes.clear()
+        self._noise_rep = {}
 
-    def _noises_for(self, rows):
+    def _noises_for(self, rows, sp_hw=None):
         """The noise dict for a pass over `rows` samples: the user's [B,...] maps repeated when the content and style
-        rows are batched together (rows = 2B)."""
+        rows are batched together (rows = 2B); fresh draws in "random" mode (sp_hw = spatial-code size, default 64x64)."""
         if self._noises is None:
             return None
-        return {k: (v if v.shape[0] == rows else v.repeat(rows // v.shape[0], 1, 1, 1))
-                for k, v in self._noises.items()}
+        if isinstance(self._noises, str):
+            sh, sw = sp_hw or (64, 64)
+            out = {}
+            for i in range(4):
+                for c in ("conv1", "conv2"):
+                    out["HeadResnetBlock%d.%s" % (i, c)] = torch.randn(rows, 1, sh, sw, device=self.device,
+                                                                        generator=self._noise_gen)
+            for j, res in enumerate((16, 32, 64)):
+                f = 2 ** (j + 1)
+                for c in ("conv1", "conv2"):
+                    out["UpsamplingResBlock%d.%s" % (res, c)] = torch.randn(rows, 1, sh * f, sw * f, device=self.device,
+                                                                             generator=self._noise_gen)
+            return out
+        hit = self._noise_rep.get(rows)
+        if hit is None:                                  # repeated once per batch size, not once per pass
+            hit = self._noise_rep[rows] = {k: (v if v.shape[0] == rows else v.repeat(rows // v.shape[0], 1, 1, 1))
+                                           for k, v in self._noises.items()}
+        return hit
 
     @classmethod
     def from_model_state_dict(cls, sd, **kw):
@@ -112,7 +171,7 @@ class SwapModel:
         goes through the guided-filter smoothing of photo_gif.GIFSmoothing(r=30, eps=(0.02*255)**2) -- on the device,
         without the reference's host round trip."""
         sp = self.engine.to_nhwc(spatial_code)
-        rgb = self.engine.generator(sp, global_code, noises=self._noises_for(sp.shape[0]), nchw_out=True)
+        rgb = self.engine.generator(sp, global_code, noises=self._noises_for(sp.shape[0], sp.shape[1:3]), nchw_out=True)
         if target is not None:
             rgb = ops.guided_smooth(rgb, self._in(target))
         return rgb
@@ -120,7 +179,8 @@ class SwapModel:
     def extract_feat(self, spatial_code, global_code):
         """ppst_model.py:308-309 -> (rgb, fea, fea1)."""
         sp = self.engine.to_nhwc(spatial_code)
-        rgb, fea, fea1 = self.engine.generator(sp, global_code, extract_features=True, noises=self.noises, nchw_out=True)
+        rgb, fea, fea1 = self.engine.generator(sp, global_code, extract_features=True,
+                                               noises=self._noises_for(sp.shape[0], sp.shape[1:3]), nchw_out=True)
         return rgb, self._out(fea), self._out(fea1)
 
     def extract_feat_from_image(self, img):
@@ -128,7 +188,8 @@ class SwapModel:
         x = self._in(img)
         sp = self.engine.encoder_con(x)
         gl, _ = self.engine.encoder_col(x)
-        _, fea, fea1 = self.engine.generator(sp, gl, extract_features=True, noises=self.noises)
+        _, fea, fea1 = self.engine.generator(sp, gl, extract_features=True,
+                                             noises=self._noises_for(sp.shape[0], sp.shape[1:3]), need_rgb=False)
         return self._out(fea), self._out(fea1)
 
     def Rselfcorr(self, fea):
@@ -174,10 +235,12 @@ class SwapModel:
         # are kept for the correlation branch, which the reference recomputes from the image (encode2).
         x2 = torch.cat([xc, xs], 0)
         noises2 = self._noises_for(2 * n)
-        sp2 = e.encoder_con(x2)
+        # E2 first: its code heads and the style linears (chains of tiny dependent kernels) run on a side stream under E1
         levels = []
-        gl2, _ = e.encoder_col(x2, levels_out=levels)
-        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=noises2)
+        gl2, _ = e.encoder_col(x2, levels_out=levels, defer_join=True)
+        st2 = e.styles_async(gl2)
+        sp2 = e.encoder_con(x2)
+        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=noises2, styles=st2, need_rgb=False)
         sp_c, gl_c = sp2[:n], [v[:n] for v in gl2]
         fea_c, fea_s, fea_c1, fea_s1 = fea2[:n], fea2[n:], fea21[:n], fea21[n:]
         fc = torch.empty((n, 64, 64, 512), device=self.device, dtype=torch.float32)
@@ -187,7 +250,7 @@ class SwapModel:
         ops.rselfcorr(fea_c1, out=fc, out_c_off=256)
         ops.rselfcorr(fea_s1, out=fs, out_c_off=256)
         corr = e.corrm(fs, fc, split_out=e.use_tc)
-        gl_w = e.encoder_col_warp([x[n:] for x in levels], corr)
+        gl_w = e.encoder_col_warp([(x[0][n:], x[1]) if isinstance(x, tuple) else x[n:] for x in levels], corr)
         codes = gl_w if alpha == 1.0 else [ops.lerp(a, b, alpha) for a, b in zip(gl_c, gl_w)]
         return e.generator(sp_c, codes, noises=self._noises_for(n), nchw_out=not return_nhwc)
 
@@ -198,7 +261,7 @@ class SwapModel:
         e = self.engine
         sp = e.encoder_con(self._in(content))
         gl, _ = e.encoder_col(self._in(style))
-        return e.generator(sp, gl, noises=self._noises_for(sp.shape[0]), nchw_out=not return_nhwc)
+        return e.generator(sp, gl, noises=self._noises_for(sp.shape[0], sp.shape[1:3]), nchw_out=not return_nhwc)
 
     def swap_grid(self, contents, styles, cell_batch=8, smooth=False):
         """Every (content i, style j) cell of evaluation/content_style_grid_generation_evaluator.py:57-91 in one call:
@@ -211,15 +274,17 @@ class SwapModel:
         xc, xs = self._in(contents), self._in(styles)
         nc, ns = xc.shape[0], xs.shape[0]
         x2 = torch.cat([xc, xs], 0)
-        sp2 = e.encoder_con(x2)
         levels = []
-        gl2, _ = e.encoder_col(x2, levels_out=levels)
-        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=self._noises_for(nc + ns))
+        gl2, _ = e.encoder_col(x2, levels_out=levels, defer_join=True)
+        st2 = e.styles_async(gl2)
+        sp2 = e.encoder_con(x2)
+        _, fea2, fea21 = e.generator(sp2, gl2, extract_features=True, noises=self._noises_for(nc + ns), styles=st2,
+                                     need_rgb=False)
         f2 = torch.empty((nc + ns, 64, 64, 512), device=self.device, dtype=torch.float32)
         ops.affine_apply(fea2, 256, out=f2, out_c_off=0)
         ops.rselfcorr(fea21, out=f2, out_c_off=256)
         sp_c = sp2[:nc]
-        lv_s = [x[nc:] for x in levels]
+        lv_s = [(x[0][nc:], x[1]) if isinstance(x, tuple) else (x[nc:], 0) for x in levels]
         out = torch.empty((nc, ns, 3) + tuple(xc.shape[2:]), device=self.device, dtype=torch.float32)
         cells = [(i, j) for i in range(nc) for j in range(ns)]
         for k0 in range(0, len(cells), cell_batch):
@@ -227,7 +292,7 @@ class SwapModel:
             ci = torch.tensor([c[0] for c in chunk], device=self.device)
             sj = torch.tensor([c[1] for c in chunk], device=self.device)
             corr = e.corrm(f2.index_select(0, sj + nc), f2.index_select(0, ci), split_out=e.use_tc)
-            gl_w = e.encoder_col_warp([x.index_select(0, sj) for x in lv_s], corr)
+            gl_w = e.encoder_col_warp([(x.index_select(0, sj), b) for x, b in lv_s], corr)
             rgb = e.generator(sp_c.index_select(0, ci), gl_w, noises=self._noises_for(len(chunk)), nchw_out=True)
             if smooth:
                 rgb = ops.guided_smooth(rgb, xc.index_select(0, ci))

@@ -105,14 +105,18 @@ def _get_scratch(device, elems):
     return buf
 
 
-def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift=None, want=("sum", "sumsq", "max")):
+def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift=None, want=("sum", "sumsq", "max"),
+                 border=0):
     """Per-(n, region, c) sum / sumsq / max over H*W.  x: [n,c,h,w] (channels_last False) or [n,h,w,c] (True).
+    border > 0 (channels_last): x is [n, h + 2*border, w + 2*border, c] and only its interior is reduced.
     Returns dict of f32 [n, n_regions, c] tensors."""
     require_cuda(x, labels, shift)
     assert x.is_contiguous()
     if channels_last:
         n, h, w, c = x.shape
+        h, w = h - 2 * border, w - 2 * border
     else:
+        assert border == 0
         n, c, h, w = x.shape
     hw = h * w
     L = _L()
@@ -123,7 +127,7 @@ def plane_reduce(x, channels_last, labels=None, n_regions=1, label_mode=0, shift
     with _Prof("plane_reduce", x.numel() * x.element_size(), "n%d hw%d c%d cl%d %s" % (n, hw, c, int(channels_last), str(x.dtype)[6:])):
         check(L.ppst_plane_reduce(ptr(outs.get("sum")), ptr(outs.get("sumsq")), ptr(outs.get("max")), ptr(x),
                                   ptr(labels), ptr(shift), ptr(scratch), n, c, hw, n_regions, label_mode,
-                                  1 if channels_last else 0, dt(x), stream()))
+                                  1 if channels_last else 0, dt(x), w, border, stream()))
     return outs
 
 
@@ -162,7 +166,7 @@ def labels_pool_or(labels, factor, in_mode):
 def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(1, 1), phase_off=(0, 0),
               full_hw=None, cout_stride=None, c_off=0, act=False, slope=0.2, gain=1.0, noise_w=0.0,
               in_dtype=F32, out_dtype=F32, in_row_pitch=0, in_img_pitch=0, w_img_rows=0, split_terms=0, out_pad=0,
-              bias_img_stride=0):
+              bias_img_stride=0, out_pad_trim=0):
     n, in_h, in_w, cin = x_shape
     d = ConvDesc()
     d.n, d.in_h, d.in_w, d.cin = n, in_h, in_w, cin
@@ -180,7 +184,7 @@ def conv_desc(x_shape, cout, kh, kw, stride=1, off=(0, 0), out_hw=None, phases=(
     d.in_dtype, d.out_dtype = in_dtype, out_dtype
     d.in_row_pitch, d.in_img_pitch = in_row_pitch, in_img_pitch
     d.w_img_rows, d.split_terms = w_img_rows, split_terms
-    d.out_pad, d.bias_img_stride = out_pad, bias_img_stride
+    d.out_pad, d.bias_img_stride, d.out_pad_trim = out_pad, bias_img_stride, out_pad_trim
     return d
 
 
@@ -205,16 +209,17 @@ def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
     return out
 
 
-def conv1x1_in_nchw(x_nchw, w, bias, act, out_dtype, slope=0.2, gain=SQRT2):
-    """FromRGB: NCHW f32 image -> NHWC [n,h,w,cout]."""
+def conv1x1_in_nchw(x_nchw, w, bias, act, out_dtype, slope=0.2, gain=SQRT2, out_border=0):
+    """FromRGB: NCHW f32 image -> NHWC [n,h,w,cout] (out_border: the interior of [n, h+2b, w+2b, cout], border unwritten)."""
     require_cuda(x_nchw, w, bias)
     x_nchw = x_nchw.contiguous()
     n, cin, h, wd = x_nchw.shape
     cout = w.shape[0]
-    out = torch.empty((n, h, wd, cout), device=x_nchw.device, dtype=out_dtype)
+    out = torch.empty((n, h + 2 * out_border, wd + 2 * out_border, cout), device=x_nchw.device, dtype=out_dtype)
     with _Prof("conv1x1_in_nchw", x_nchw.numel() * 4 + out.numel() * out.element_size()):
         check(_L().ppst_conv1x1_in_nchw(ptr(out), ptr(x_nchw), ptr(w), ptr(bias), n, cin, h * wd, cout, cout, 0,
-                                        1 if act else 0, float(slope), float(gain if act else 1.0), dt(out), stream()))
+                                        1 if act else 0, float(slope), float(gain if act else 1.0), dt(out), wd, out_border,
+                                        stream()))
     return out
 
 
@@ -250,15 +255,21 @@ def in_coeffs(n, c, sum_=None, sumsq=None, count=1.0, shift=None, style=None, bi
 
 
 def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0, pre_gain=1.0, post_slope=1.0,
-                 post_gain=1.0, res_mode=0, up=1, pad=(0, 0, 0, 0), pad_mode=0, out=None, out_dtype=None, out_c_off=0):
-    """x NHWC [n,h,w,c] (dense); see ppst_affine_apply.  pad = (top, bottom, left, right)."""
+                 post_gain=1.0, res_mode=0, up=1, pad=(0, 0, 0, 0), pad_mode=0, out=None, out_dtype=None, out_c_off=0,
+                 out_border=0, res_border=0):
+    """x NHWC [n,h,w,c] (dense); see ppst_affine_apply.  pad = (top, bottom, left, right).
+    out_border: the result goes to the interior of [n, oh + 2b, ow + 2b, c] (border: pad_border); res_border: `res` has
+    such a border and is read at its interior."""
     require_cuda(x, a, b, res, ra, rb)
     n, h, w, cs = x.shape
     assert cs == c and x.is_contiguous()
     oh, ow = h * up + pad[0] + pad[1], w * up + pad[2] + pad[3]
     if out is None:
-        out = torch.empty((n, oh, ow, c), device=x.device, dtype=out_dtype or x.dtype)
-    assert out.shape[:3] == (n, oh, ow)
+        out = torch.empty((n, oh + 2 * out_border, ow + 2 * out_border, c), device=x.device, dtype=out_dtype or x.dtype)
+    assert out.shape[:3] == (n, oh + 2 * out_border, ow + 2 * out_border)
+    if res is not None:
+        rh, rw = (oh - pad[0] - pad[1], ow - pad[2] - pad[3]) if res_mode == 1 else ((oh - pad[0] - pad[1]) // 2, (ow - pad[2] - pad[3]) // 2)
+        assert res.is_contiguous() and tuple(res.shape[1:3]) == (rh + 2 * res_border, rw + 2 * res_border), (res.shape, rh, rw)
     d = ApplyDesc()
     d.n, d.h, d.w, d.c, d.up = n, h, w, c, up
     d.pad_t, d.pad_b, d.pad_l, d.pad_r = pad
@@ -268,6 +279,7 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
     d.x_dtype, d.out_dtype = dt(x), dt(out)
     d.res_dtype = dt(res) if res is not None else dt(x)
     d.out_c_stride, d.out_c_off = out.shape[3], out_c_off
+    d.out_border, d.res_border = out_border, res_border
     nbytes = x.numel() * x.element_size() + n * oh * ow * c * out.element_size()
     if res is not None:
         nbytes += (res.numel() if res_mode == 1 else n * oh * ow * c) * res.element_size()
@@ -300,20 +312,25 @@ def affine_apply_torgb(x, a, b, res, rgb_w, rgb_bias, post_gain=1.0, write_out=T
     return out, rgb
 
 
-def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0, a=None, b=None, slope=1.0):
+def resample(x, out_hw, mode, out=None, out_dtype=None, out_c_off=0, a=None, b=None, slope=1.0, in_border=0,
+             out_border=0):
     """mode 0 bilinear (align_corners False), 1 adaptive average.  x NHWC dense.
-    a / b (f32 [n, c]) + slope: every source sample is first mapped to lrelu(x*a + b, slope)."""
+    a / b (f32 [n, c]) + slope: every source sample is first mapped to lrelu(x*a + b, slope).
+    in_border / out_border: x / out carry a border of that many pixels and are addressed at their interiors."""
     require_cuda(x, a, b)
     n, h, w, c = x.shape
+    h, w = h - 2 * in_border, w - 2 * in_border
     if out is None:
-        out = torch.empty((n, out_hw[0], out_hw[1], c), device=x.device, dtype=out_dtype or x.dtype)
+        out = torch.empty((n, out_hw[0] + 2 * out_border, out_hw[1] + 2 * out_border, c), device=x.device,
+                          dtype=out_dtype or x.dtype)
+    assert tuple(out.shape[1:3]) == (out_hw[0] + 2 * out_border, out_hw[1] + 2 * out_border)
     if a is not None:
         assert a.dtype == torch.float32 and a.is_contiguous() and a.shape == (n, c)
         assert b is None or (b.dtype == torch.float32 and b.is_contiguous() and b.shape == (n, c))
     with _Prof("resample", x.numel() * x.element_size() + n * out_hw[0] * out_hw[1] * c * out.element_size(),
                "n%d %dx%d->%dx%d c%d m%d" % (n, h, w, out_hw[0], out_hw[1], c, mode)):
         check(_L().ppst_resample(ptr(out), ptr(x), n, h, w, out_hw[0], out_hw[1], c, out.shape[3], out_c_off, mode,
-                                 dt(x), dt(out), ptr(a), ptr(b), float(slope), stream()))
+                                 dt(x), dt(out), ptr(a), ptr(b), float(slope), in_border, out_border, stream()))
     return out
 
 
@@ -452,6 +469,17 @@ def fill_border(buf, a, b, pad=1):
     n, hp, wp, c = buf.shape
     assert buf.is_contiguous() and a.is_contiguous() and b.is_contiguous()
     check(_L().ppst_fill_border(ptr(buf), ptr(a), ptr(b), n, hp - 2 * pad, wp - 2 * pad, c, pad, dt(buf), stream()))
+    return buf
+
+
+def pad_border(buf, pad, mode):
+    """Border of the padded NHWC buffer [n, pt + h + pb, pl + w + pr, c] from its interior: mode 1 reflect, 2 replicate,
+    0 zero.  pad = (top, bottom, left, right)."""
+    require_cuda(buf)
+    n, hp, wp, c = buf.shape
+    assert buf.is_contiguous()
+    pt, pb, pl, pr = pad
+    check(_L().ppst_pad_border(ptr(buf), n, hp - pt - pb, wp - pl - pr, c, pt, pb, pl, pr, mode, dt(buf), stream()))
     return buf
 
 

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from oracle import ppst_oracle as O  # noqa: E402  (weights / inputs only)
+from ppst_b200 import synthetic as O  # noqa: E402  (seeded weights / inputs)
 import ppst_b200  # noqa: E402
 
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
-from oracle import ppst_oracle as O  # noqa: E402  (weights / inputs only)
+from ppst_b200 import synthetic as O  # noqa: E402  (seeded weights / inputs)
 import ppst_b200  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 8
