@@ -352,6 +352,15 @@ typedef struct {
 PPST_API int ppst_affine_apply(void* out, const void* x, const float* a, const float* b, const void* res,
                       const float* ra, const float* rb, const ppst_apply_desc* d, void* stream);
 
+/* ppst_affine_apply that ALSO emits the instance-norm statistics of what it writes: stats f32 [2][n][OH][c] = per output
+ * row (of the padded output, OH = h + pad_t + pad_b) and channel the sum / the sum of squares of the stored (rounded)
+ * values -- feed to ppst_in_coeffs with n_partials = OH, count = OH * OW.  The feature heads of the generator
+ * (generator.py:180-231: ReplicationPad2d -> InstanceNorm2d -> conv) normalise the tensor this pass produces, so neither a
+ * padding pass nor a reduction pass over it is needed.  bf16, c % 8 == 0, up == 1; res_mode 0 / 1 with any padding mode;
+ * res_mode 2 (bilinear-x2 skip) with no padding or a replicated 1-pixel border (written by the kernel itself). */
+PPST_API int ppst_affine_apply_stats(void* out, const void* x, const float* a, const float* b, const void* res,
+                            const float* ra, const float* rb, const ppst_apply_desc* d, float* stats, void* stream);
+
 /* ppst_affine_apply with a bilinear-x2 skip (the end of UpsamplingResBlock64, generator.py:63-77) fused with the ToRGB
  * 1x1 convolution that follows it (stylegan2_layers.py:477-495, conv only: 128 -> 3 channels + bias):
  *   rgb_out f32 [n, h, w, 3] = conv1x1(bf16(apply(x, a, b, res)), rgb_w [3, 128]) + rgb_bias [3]

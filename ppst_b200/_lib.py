@@ -65,6 +65,7 @@ _SIGS = {
     "ppst_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p]),
     "ppst_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p]),
+    "ppst_affine_apply_stats": (c_int, [c_void_p] * 7 + [ctypes.POINTER(ApplyDesc), c_void_p, c_void_p]),
     "ppst_affine_apply_torgb": (c_int, [c_void_p] * 8 + [ctypes.POINTER(ApplyDesc), c_void_p]),
     "ppst_conv_simt": (c_int, [c_void_p] * 5 + [ctypes.POINTER(ConvDesc), c_void_p]),
     "ppst_conv_tc_stats_elems": (c_i64, [ctypes.POINTER(ConvDesc)]),

@@ -11,7 +11,7 @@ namespace ppst {
 // plane length allows), then thread -> (pixel, group of 8 output channels): COUT/8 consecutive lanes write one pixel's
 // channel vector, so a warp store covers 8 pixels x 64 contiguous bytes (bf16) instead of 32 scattered pieces.
 constexpr int kPixBlock = 1024;
-template <typename TO, int COUT>
+template <typename TO, int COUT, bool BORDER = false>
 __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ out, const float* __restrict__ x,
                                                               const float* __restrict__ w, const float* __restrict__ bias,
                                                               int64_t n, int cin, int64_t hw, int cout_stride, int c_off,
@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ o
     }
     __syncthreads();
     // ob > 0: the output carries a border of ob pixels; pixel p = (y, x) lands at (y + ob, x + ob) of the padded grid
-    const int64_t wp = w_row + 2 * ob;
-    TO* obase = ob ? out + (ni * (hw / w_row + 2 * ob) * wp) * cout_stride + c_off
-                   : out + (ni * hw + p0) * cout_stride + c_off;
+    const int wp = w_row + 2 * ob;
+    TO* obase = BORDER ? out + (ni * (hw / w_row + 2 * ob) * wp) * cout_stride + c_off
+                       : out + (ni * hw + p0) * cout_stride + c_off;
     // 256 % G == 0: a thread always serves the same channel group, whose weights / bias live in registers
     for (int item = threadIdx.x; item < np * G; item += 256) {
       const int pix = item / G;
@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(256) conv1x1_in_nchw_kernel(TO* __restrict__ o
         v[e] = acc * gain;
       }
       int64_t opix = pix;
-      if (ob) {
-        const int64_t pp = p0 + pix;
-        const int64_t yy = pp / w_row;
-        opix = (yy + ob) * wp + (pp - yy * w_row) + ob;
+      if (BORDER) {                                    // hw < 2^31 (host-checked): 32-bit division
+        const int pp = (int)p0 + pix;
+        const int yy = pp / w_row;
+        opix = (int64_t)(yy + ob) * wp + (pp - yy * w_row) + ob;
       }
       TO* o = obase + opix * cout_stride + g * 8;
       if (sizeof(TO) == 2) {
@@ -242,6 +242,7 @@ extern "C" int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, c
   PPST_REQUIRE(out && x && w && n > 0 && hw > 0 && cin >= 1 && cin <= 4, PPST_ERR_ARG, "conv1x1_in_nchw: bad args");
   PPST_REQUIRE(out_border == 0 || (out_border > 0 && out_border <= 8 && w_row > 0 && hw % w_row == 0), PPST_ERR_ARG,
                "conv1x1_in_nchw: out_border needs the row width");
+  PPST_REQUIRE(out_border == 0 || hw < (1LL << 31), PPST_ERR_ARG, "conv1x1_in_nchw: image too large for a bordered output");
   PPST_REQUIRE(cout == 32 || cout == 64 || cout == 128, PPST_ERR_UNSUPPORTED,
                "conv1x1_in_nchw: cout=%d (32: FromRGB of the encoders; 64 / 128: the discriminator's first layer)", cout);
   PPST_REQUIRE(c_off % 8 == 0 && cout_stride % 8 == 0 && c_off + cout <= cout_stride, PPST_ERR_ARG,
@@ -249,8 +250,15 @@ extern "C" int ppst_conv1x1_in_nchw(void* out, const float* x, const float* w, c
   const int64_t tiles = n * ((hw + kPixBlock - 1) / kPixBlock);
   const int blocks = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define PPST_IN_NCHW(TO, CO) \
-  conv1x1_in_nchw_kernel<TO, CO><<<blocks, 256, 0, st>>>((TO*)out, x, w, bias, n, cin, hw, cout_stride, c_off, has_act, slope, gain, w_row, out_border)
+#define PPST_IN_NCHW(TO, CO)                                                                                             \
+  do {                                                                                                                   \
+    if (out_border)                                                                                                      \
+      conv1x1_in_nchw_kernel<TO, CO, true><<<blocks, 256, 0, st>>>((TO*)out, x, w, bias, n, cin, hw, cout_stride, c_off, \
+                                                                   has_act, slope, gain, w_row, out_border);             \
+    else                                                                                                                 \
+      conv1x1_in_nchw_kernel<TO, CO, false><<<blocks, 256, 0, st>>>((TO*)out, x, w, bias, n, cin, hw, cout_stride,       \
+                                                                    c_off, has_act, slope, gain, w_row, out_border);     \
+  } while (0)
   PPST_REQUIRE(out_dtype == PPST_BF16 || out_dtype == PPST_F32, PPST_ERR_DTYPE, "conv1x1_in_nchw: out dtype %d", out_dtype);
   if (out_dtype == PPST_BF16) {
     if (cout == 32) PPST_IN_NCHW(__nv_bfloat16, 32);

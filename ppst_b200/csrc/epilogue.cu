@@ -264,21 +264,49 @@ __device__ __forceinline__ void cvt8(const Raw8<float>& r, float (&f)[8]) {
 // one 16-byte store; no integer division, no coefficient reloads.  U pixels are in flight per thread (loads issued
 // before any use, data kept packed) and the residual mode is a template parameter so that the common no-residual
 // instance stays small enough for 3+ resident blocks per SM.
-template <typename TX, typename TO, int RES>
+// Block-level tail of the STATS variants: every thread holds sum / sum of squares of the (rounded) values it stored for its
+// 8 channels; the `lanes` threads that share a channel group are combined in a fixed order through shared memory and the
+// row's partial is written to stats[(0|1)][n][rows][c] (reduced later by ppst_in_coeffs, n_partials = rows).
+__device__ __forceinline__ void row_stats_store(float* __restrict__ stats, const float (&s1)[8], const float (&s2)[8], int c,
+                                                int cg, int lane, int lanes, int64_t row_index, int64_t half_elems) {
+  __shared__ float red[2][2048];                       // lanes * c == 256 * 8
+  if (lane < lanes) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[0][lane * c + cg * 8 + e] = s1[e];
+      red[1][lane * c + cg * 8 + e] = s2[e];
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int l = 0; l < lanes; ++l) { t1 += red[0][l * c + ch]; t2 += red[1][l * c + ch]; }
+    stats[row_index * c + ch] = t1;
+    stats[half_elems + row_index * c + ch] = t2;
+  }
+}
+
+template <typename TX, typename TO, int RES, bool STATS = false>
 __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
                                                                    const float* __restrict__ a, const float* __restrict__ b,
                                                                    const TX* __restrict__ res, const float* __restrict__ ra,
-                                                                   const float* __restrict__ rb, ppst_apply_desc d) {
+                                                                   const float* __restrict__ rb, ppst_apply_desc d,
+                                                                   float* __restrict__ stats = nullptr) {
   constexpr int V = 8;
   constexpr int U = RES == 2 ? 2 : 4;        // RES == 2 also keeps 4 bilinear neighbours per pixel in flight
   const int cv = d.c / V;
   const int lanes = 256 / cv;
   const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
-  if (lane >= lanes) return;
+  if (!STATS && lane >= lanes) return;
   const int oy = blockIdx.x, ni = blockIdx.y;
   const int ch = cg * V;
   const int hu = d.h * d.up, wu = d.w * d.up;
   const int oh = hu + d.pad_t + d.pad_b, ow = wu + d.pad_l + d.pad_r;
+  float s1[STATS ? V : 1], s2[STATS ? V : 1];
+  if (STATS) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s1[STATS ? e : 0] = 0.f; s2[STATS ? e : 0] = 0.f; }
+  }
   float av[V], bv[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; }
@@ -309,7 +337,7 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
     r1 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i1 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
   }
   const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
-  for (int ox0 = lane; ox0 < ow; ox0 += U * lanes) {
+  for (int ox0 = lane; ox0 < ow && lane < lanes; ox0 += U * lanes) {
     Raw8<TX> xr[U], rr[RES == 1 ? U : 1], qq[RES == 2 ? U : 1][4];
     Bilin2 bxs[RES == 2 ? U : 1];
     int uxs[U];
@@ -370,8 +398,19 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
         for (int e = 0; e < V; ++e) y[e] = lrelu_slope(y[e], post_slope) * post_gain;
       }
       store_ch<TO, V>(orow + (int64_t)(ox0 + u * lanes) * d.out_c_stride, y);
+      if (STATS) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float yq = Cvt<TO>::to_f(Cvt<TO>::from_f(y[e]));            // the stored (rounded) value
+          s1[STATS ? e : 0] += yq;
+          s2[STATS ? e : 0] = fmaf(yq, yq, s2[STATS ? e : 0]);
+        }
+      }
     }
   }
+  if (STATS)
+    row_stats_store(stats, *reinterpret_cast<const float(*)[8]>(s1), *reinterpret_cast<const float(*)[8]>(s2), d.c, cg, lane,
+                    lanes, (int64_t)ni * oh + oy, (int64_t)d.n * oh * d.c);
 }
 
 // Bilinear-x2 skip variant of the row kernel (generator.py:75, the end of every UpsamplingResnetBlock), no padding / no
@@ -384,22 +423,34 @@ __global__ void __launch_bounds__(256, RES == 0 ? 3 : 2) affine_apply_rows_kerne
 // is computed on the fly from the ROUNDED values -- 24 FMAs per thread, then a 15-shuffle reduction of the 4 pixels x 3
 // outputs over the 16 lanes that share a pixel -- so ToRGB never re-reads the 512^2 x 128 activation; RGB == 2 does not
 // even write it (plain decode: nothing else consumes the last block's output).
-template <typename TX, typename TO, bool RAB, int RGB>
+// STATS (RGB == 0 only): d.pad_* = P in {0, 1} is a REPLICATED border written by this kernel (a block per row of the padded
+// output; the first / last pixel of a row is stored twice), and every row's per-channel sum / sum of squares of the stored
+// values goes to stats[2][n][h + 2P][c] -- the instance-norm statistics of the PADDED tensor that generator.py:180-231
+// normalises, without the padding pass and without the reduction pass over it.
+template <typename TX, typename TO, bool RAB, int RGB, bool STATS = false>
 __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __restrict__ out, const TX* __restrict__ x,
                                                                          const float* __restrict__ a, const float* __restrict__ b,
                                                                          const TX* __restrict__ res, const float* __restrict__ ra,
                                                                          const float* __restrict__ rb, ppst_apply_desc d,
                                                                          float* __restrict__ rgb_out,
                                                                          const float* __restrict__ rgb_w,
-                                                                         const float* __restrict__ rgb_bias) {
+                                                                         const float* __restrict__ rgb_bias,
+                                                                         float* __restrict__ stats = nullptr) {
   constexpr int V = 8;
   const int cv = d.c / V;
   const int lanes = 256 / cv;
   const int cg = threadIdx.x % cv, lane = threadIdx.x / cv;
-  if (RGB == 0 && lane >= lanes) return;              // RGB: cv == 16, every thread is live (warp shuffles below)
-  const int oy = blockIdx.x, ni = blockIdx.y;
-  const int ch = cg * V;
+  if (RGB == 0 && !STATS && lane >= lanes) return;    // RGB: cv == 16, every thread is live (warp shuffles below)
+  const int P = STATS ? d.pad_t : 0;
   const int h = d.h, w = d.w, lh = h / 2, lw = w / 2;
+  const int oyp = blockIdx.x, ni = blockIdx.y;
+  const int oy = STATS ? min(max(oyp - P, 0), h - 1) : oyp;
+  const int ch = cg * V;
+  float s1[STATS ? V : 1], s2[STATS ? V : 1];
+  if (STATS) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s1[STATS ? e : 0] = 0.f; s2[STATS ? e : 0] = 0.f; }
+  }
   float av[V], bv[V];
 #pragma unroll
   for (int e = 0; e < V; ++e) { av[e] = 1.0f; bv[e] = 0.0f; }
@@ -414,8 +465,8 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
   }
   const Bilin2 by = bilin_x2(oy, lh);
   const TX* xrow = x + (((int64_t)ni * h + oy) * w) * d.c + ch;
-  const int ob = d.out_border, rbd = d.res_border;
-  TO* orow = out + (((int64_t)ni * (h + 2 * ob) + oy + ob) * (w + 2 * ob) + ob) * d.out_c_stride + d.out_c_off + ch;
+  const int ob = d.out_border + P, rbd = d.res_border;
+  TO* orow = out + (((int64_t)ni * (h + 2 * ob) + oyp + d.out_border) * (w + 2 * ob) + ob) * d.out_c_stride + d.out_c_off + ch;
   const TX* r0 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i0 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
   const TX* r1 = res + (((int64_t)ni * (lh + 2 * rbd) + by.i1 + rbd) * (lw + 2 * rbd) + rbd) * d.c + ch;
   const float pre_slope = d.pre_slope, pre_gain = d.pre_gain, post_slope = d.post_slope, post_gain = d.post_gain;
@@ -429,7 +480,7 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
   const int sweeps = (lw + 2 * lanes - 1) / (2 * lanes);       // uniform trip count (the RGB reduction shuffles)
   for (int sw = 0; sw < sweeps; ++sw) {
     const int j0 = 2 * lane + sw * 2 * lanes;
-    if (j0 >= lw) continue;                                    // never taken with RGB (w % 64 == 0, host-checked)
+    if (j0 >= lw || (STATS && lane >= lanes)) continue;        // never taken with RGB (w % 64 == 0, host-checked)
     // low-res columns j0-1 .. j0+2 (clamped) serve output pixels 2*j0 .. 2*j0+3
     int col[4];
     col[0] = max(j0 - 1, 0); col[1] = j0; col[2] = min(j0 + 1, lw - 1); col[3] = min(j0 + 2, lw - 1);
@@ -469,6 +520,17 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
         y[e] = lrelu_slope(y[e], post_slope) * post_gain;
       }
       if (RGB != 2) store_ch<TO, V>(orow + (int64_t)(ox0 + u) * d.out_c_stride, y);
+      if (STATS) {
+        float wgt = 1.0f;
+        if (P && ox0 + u == 0) { store_ch<TO, V>(orow - (int64_t)d.out_c_stride, y); wgt += 1.0f; }
+        if (P && ox0 + u == w - 1) { store_ch<TO, V>(orow + (int64_t)w * d.out_c_stride, y); wgt += 1.0f; }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float yq = Cvt<TO>::to_f(Cvt<TO>::from_f(y[e]));            // the stored (rounded) value
+          s1[STATS ? e : 0] = fmaf(wgt, yq, s1[STATS ? e : 0]);
+          s2[STATS ? e : 0] = fmaf(wgt * yq, yq, s2[STATS ? e : 0]);
+        }
+      }
       if (RGB) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
@@ -509,6 +571,9 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
       }
     }
   }
+  if (STATS)
+    row_stats_store(stats, *reinterpret_cast<const float(*)[8]>(s1), *reinterpret_cast<const float(*)[8]>(s2), d.c, cg, lane,
+                    lanes, (int64_t)ni * (h + 2 * P) + oyp, (int64_t)d.n * (h + 2 * P) * d.c);
 }
 
 // mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows)
@@ -668,6 +733,53 @@ extern "C" int ppst_affine_apply(void* out, const void* x, const float* a, const
   else PPST_REQUIRE(false, PPST_ERR_DTYPE, "affine_apply: dtype combination %d -> %d", d.x_dtype, d.out_dtype);
 #undef PPST_APPLY
   PPST_LAUNCH_CHECK("affine_apply_kernel");
+  return 0;
+}
+
+extern "C" int ppst_affine_apply_stats(void* out, const void* x, const float* a, const float* b, const void* res,
+                                       const float* ra, const float* rb, const ppst_apply_desc* dp, float* stats,
+                                       void* stream) {
+  using namespace ppst;
+  PPST_REQUIRE(out && x && dp && stats, PPST_ERR_ARG, "affine_apply_stats: null argument");
+  const ppst_apply_desc d = *dp;
+  PPST_REQUIRE(d.n > 0 && d.n <= 65535 && d.h > 0 && d.w > 0 && d.c > 0 && d.c % 8 == 0 && d.c <= 2048 && d.up == 1,
+               PPST_ERR_ARG, "affine_apply_stats: bad geometry (c a multiple of 8, at most 2048; no upsampling)");
+  PPST_REQUIRE(d.x_dtype == PPST_BF16 && d.out_dtype == PPST_BF16 && (d.res_mode == 0 || d.res_dtype == PPST_BF16),
+               PPST_ERR_DTYPE, "affine_apply_stats: bf16 activations");
+  PPST_REQUIRE(d.res_mode == 0 || res != nullptr, PPST_ERR_ARG, "affine_apply_stats: residual missing");
+  PPST_REQUIRE(d.out_c_stride % 8 == 0 && d.out_c_off % 8 == 0 && d.out_c_off + d.c <= d.out_c_stride, PPST_ERR_ARG,
+               "affine_apply_stats: channel slice");
+  PPST_REQUIRE(d.out_border >= 0 && d.out_border <= 8 && d.res_border >= 0 && d.res_border <= 8, PPST_ERR_ARG,
+               "affine_apply_stats: out_border / res_border");
+  PPST_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res) |
+                 reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(ra) |
+                 reinterpret_cast<uintptr_t>(rb)) & 15) == 0, PPST_ERR_ARG, "affine_apply_stats: buffers must be 16-byte aligned");
+  PPST_REQUIRE(d.pad_mode >= 0 && d.pad_mode <= 2, PPST_ERR_ARG, "affine_apply_stats: pad_mode");
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 T;
+  const int oh = d.h + d.pad_t + d.pad_b;
+  if (d.res_mode == 2) {
+    const int P = d.pad_t;
+    PPST_REQUIRE(d.h % 2 == 0 && d.w % 2 == 0 && (P == 0 || P == 1) && d.pad_b == P && d.pad_l == P && d.pad_r == P &&
+                 (P == 0 || d.pad_mode == 2), PPST_ERR_UNSUPPORTED,
+                 "affine_apply_stats: the bilinear-x2 skip takes no padding or a replicated 1-pixel border");
+    if (ra || rb)
+      affine_apply_bilin_rows_kernel<T, T, true, 0, true><<<dim3(oh, d.n), 256, 0, st>>>(
+          (T*)out, (const T*)x, a, b, (const T*)res, ra, rb, d, nullptr, nullptr, nullptr, stats);
+    else
+      affine_apply_bilin_rows_kernel<T, T, false, 0, true><<<dim3(oh, d.n), 256, 0, st>>>(
+          (T*)out, (const T*)x, a, b, (const T*)res, ra, rb, d, nullptr, nullptr, nullptr, stats);
+  } else {
+    PPST_REQUIRE(d.pad_mode != 1 || (d.pad_t < d.h && d.pad_b < d.h && d.pad_l < d.w && d.pad_r < d.w), PPST_ERR_ARG,
+                 "affine_apply_stats: reflect pad >= size");
+    if (d.res_mode == 0)
+      affine_apply_rows_kernel<T, T, 0, true><<<dim3(oh, d.n), 256, 0, st>>>((T*)out, (const T*)x, a, b, (const T*)res, ra,
+                                                                              rb, d, stats);
+    else
+      affine_apply_rows_kernel<T, T, 1, true><<<dim3(oh, d.n), 256, 0, st>>>((T*)out, (const T*)x, a, b, (const T*)res, ra,
+                                                                              rb, d, stats);
+  }
+  PPST_LAUNCH_CHECK("affine_apply_stats");
   return 0;
 }
 

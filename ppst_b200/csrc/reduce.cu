@@ -117,7 +117,7 @@ __global__ void plane_reduce_nchw_final(float* __restrict__ sum, float* __restri
 
 // ------------------------------------------------------------------------------------------------
 // NHWC: grid = (n, chunks, channel groups).  A block is TCOLS channel-vector columns x (256/TCOLS) pixel lanes.
-template <typename T, int VEC, int R>
+template <typename T, int VEC, int R, bool BORDER = false>
 __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
     float* __restrict__ scratch, const T* __restrict__ x, const uint8_t* __restrict__ labels,
     const float* __restrict__ shift, int64_t c, int64_t hw, int64_t chunk_len, int chunks, int tcols,
@@ -141,14 +141,21 @@ __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
   }
   if (active) {
     // border > 0: x is [n, hw/w_row + 2*border, w_row + 2*border, c]; pixel p = (y, x) of the interior
-    const int64_t wp = w_row + 2 * border;
-    const T* base = border ? x + ((nidx * (hw / w_row + 2 * border) + border) * wp + border) * c + ch0
+    const int wp = w_row + 2 * border;
+    const T* base = BORDER ? x + ((nidx * (hw / w_row + 2 * border) + border) * wp + border) * c + ch0
                            : x + (nidx * hw) * c + ch0;
     const uint8_t* pl = labels ? labels + nidx * hw : nullptr;
+    // BORDER: (yy, xx) of pixel p tracked incrementally -- one division per thread, none per pixel (hw < 2^31, host-checked)
+    int yy = BORDER ? (int)(beg + lane_p) / w_row : 0;
+    int xx = BORDER ? (int)(beg + lane_p) - yy * w_row : 0;
     for (int64_t p = beg + lane_p; p < end; p += planes) {
       float xv[VEC];
       int64_t po = p;
-      if (border) { const int64_t yy = p / w_row; po = yy * wp + (p - yy * w_row); }
+      if (BORDER) {
+        po = (int64_t)yy * wp + xx;
+        xx += planes;
+        while (xx >= w_row) { xx -= w_row; ++yy; }
+      }
       if (VEC > 1) {
         Vec16<T> v = ld_vec16_stream(base + po * c);
 #pragma unroll
@@ -244,7 +251,16 @@ static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, cons
   const int vecn = vec ? VECF : 1;
   const size_t smem = sizeof(float) * (size_t)kReduceThreads * vecn * R * 3;
   dim3 grid((unsigned)n, pl.chunks, ceil_div(cols, tcols));
-  if (vec) {
+  if (vec && border) {
+    auto kern = plane_reduce_nhwc_kernel<T, VECF, R, true>;
+    if (smem > 48 * 1024) {
+      int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(plane_reduce)");
+      if (rc) return rc;
+    }
+    kern<<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw, pl.chunk_len, pl.chunks, tcols,
+                                             label_mode, w_row, border);
+  } else if (vec) {
     auto kern = plane_reduce_nhwc_kernel<T, VECF, R>;
     if (smem > 48 * 1024) {
       int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
@@ -253,6 +269,10 @@ static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, cons
     }
     kern<<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw, pl.chunk_len, pl.chunks, tcols,
                                              label_mode, w_row, border);
+  } else if (border) {
+    plane_reduce_nhwc_kernel<T, 1, R, true><<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw,
+                                                                                pl.chunk_len, pl.chunks, tcols, label_mode,
+                                                                                w_row, border);
   } else {
     plane_reduce_nhwc_kernel<T, 1, R><<<grid, kReduceThreads, smem, st>>>(scratch, x, labels, shift, c, hw,
                                                                           pl.chunk_len, pl.chunks, tcols, label_mode,
@@ -401,7 +421,7 @@ extern "C" int ppst_plane_reduce(float* sum, float* sumsq, float* vmax, const vo
                                  int label_mode, int channels_last, int dtype, int w_row, int border, void* stream) {
   using namespace ppst;
   PPST_REQUIRE(x && scratch && n > 0 && c > 0 && hw > 0, PPST_ERR_ARG, "plane_reduce: bad args");
-  PPST_REQUIRE(border == 0 || (border > 0 && border <= 8 && channels_last && w_row > 0 && hw % w_row == 0), PPST_ERR_ARG,
+  PPST_REQUIRE(border == 0 || (border > 0 && border <= 8 && channels_last && w_row > 0 && hw % w_row == 0 && hw < (1LL << 31)), PPST_ERR_ARG,
                "plane_reduce: a border needs channels_last and the row width");
   PPST_REQUIRE(n_regions >= 1 && n_regions <= kMaxRegions, PPST_ERR_UNSUPPORTED, "plane_reduce: n_regions=%d (1..%d)",
                n_regions, kMaxRegions);

@@ -526,13 +526,13 @@ class Engine:
         a, b = self.coeffs(y, st, style=s, c=y.shape[3])
         return y, a, b
 
-    def _feature_head(self, P, x, border=0):
+    def _feature_head(self, P, x, border=0, stats=None):
         """layer32/64/128/256 (generator.py:180-231): [ReplPad] -> IN (on the padded tensor) -> conv -> IN -> PReLU
         -> [ReplPad] -> conv -> IN -> PReLU.  border = 1: x already sits inside its replicated 1-pixel border."""
         pad = (1, 1, 1, 1) if P["k"] == 3 else (0, 0, 0, 0)
         assert border == (1 if P["k"] == 3 else 0) or border == 0
         xp = x if border else (self.apply(x, pad=pad, pad_mode=2) if P["k"] == 3 else x)
-        a, b = self.coeffs(xp)
+        a, b = self.coeffs(xp, stats)
         if self.use_tc and xp.dtype == torch.bfloat16:
             # IN -> conv -> IN: the first normalisation's scale goes into per-sample weights, its shift is a constant
             # per (sample, output channel) that the second normalisation removes -- no pass over the activation
@@ -589,15 +589,18 @@ class Engine:
             h = self.apply(y, a, b)
             y, a, b = self._styled(B["conv2"], h, st["head%d.conv2" % i], noises.get(name + ".conv2"))
             xb = 1 if (pad_heads and i == len(HEAD_CH) - 1) else 0
-            x = self.apply(y, a, b, res=skip, res_mode=1, post_gain=INV_SQRT2, out_border=xb)
+            xst = None                                      # statistics of (the padded) x, when its producer emitted them
             if xb:
-                ops.pad_border(x, (1, 1, 1, 1), 2)
+                x, xst = ops.affine_apply_stats(y, y.shape[3], a, b, res=skip, res_mode=1, post_gain=INV_SQRT2,
+                                                pad=(1, 1, 1, 1), pad_mode=2)
+            else:
+                x = self.apply(y, a, b, res=skip, res_mode=1, post_gain=INV_SQRT2)
             if taps is not None:
                 taps[name] = x
         feas = []
         if extract_features:
             pool_hw = (x.shape[1] - 2 * xb, x.shape[2] - 2 * xb)
-            feas.append(self._feature_head(G["layer32"], x, border=xb))
+            feas.append(self._feature_head(G["layer32"], x, border=xb, stats=xst))
         for j, (res, ci, co) in enumerate(UP_CH):
             B = G["up%d" % res]
             name = "UpsamplingResBlock%d" % res
@@ -622,15 +625,19 @@ class Engine:
                 # last block: ToRGB's 1x1 conv rides on the pass that writes x; plain decode does not write x at all
                 x, yrgb = ops.affine_apply_torgb(y, a, b, skip, G["rgb"].w32[0], G["rgb"].bias, post_gain=INV_SQRT2,
                                                  write_out=extract_features)
+                xst = None
+            elif pad_heads:
+                # the pass that forms the block output also replicates its border (layer64 / layer128 start with
+                # ReplicationPad2d) and emits the statistics of the padded tensor for the head's first InstanceNorm
+                x, xst = ops.affine_apply_stats(y, y.shape[3], a, b, res=skip, res_mode=2, post_gain=INV_SQRT2,
+                                                pad=(xb,) * 4, pad_mode=2, res_border=sb)
             else:
-                x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2, out_border=xb,
-                               res_border=sb)                                          # bilinear x2 skip, generator.py:75
-                if xb:
-                    ops.pad_border(x, (1, 1, 1, 1), 2)
+                x = self.apply(y, a, b, res=skip, res_mode=2, post_gain=INV_SQRT2, res_border=sb)   # bilinear x2 skip, generator.py:75
+                xst = None
             if taps is not None:
                 taps[name] = x
             if extract_features:
-                feas.append(self._feature_head(G["layer%d" % (2 ** (j + 6))], x, border=xb))
+                feas.append(self._feature_head(G["layer%d" % (2 ** (j + 6))], x, border=xb, stats=xst))
         # ToRGB (stylegan2_layers.py:477-495); fp32 from here on (3-channel IN is sensitive).  need_rgb=False: the caller
         # only wants the feature maps (PPSTModel.extract_feat_from_image discards the image, ppst_model.py:311-315)
         rgb = None

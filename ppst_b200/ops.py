@@ -289,6 +289,35 @@ def affine_apply(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0
     return out
 
 
+def affine_apply_stats(x, c, a=None, b=None, res=None, ra=None, rb=None, pre_slope=1.0, pre_gain=1.0, post_slope=1.0,
+                       post_gain=1.0, res_mode=0, pad=(0, 0, 0, 0), pad_mode=0, res_border=0):
+    """affine_apply that also returns the instance-norm statistics of the (padded) tensor it writes
+    (ppst_affine_apply_stats): -> (out bf16 [n, oh, ow, c], stats dict for in_coeffs)."""
+    require_cuda(x, a, b, res, ra, rb)
+    n, h, w, cs = x.shape
+    assert cs == c and x.is_contiguous() and x.dtype == torch.bfloat16
+    oh, ow = h + pad[0] + pad[1], w + pad[2] + pad[3]
+    out = torch.empty((n, oh, ow, c), device=x.device, dtype=torch.bfloat16)
+    sbuf = torch.empty((2, n, oh, c), device=x.device, dtype=torch.float32)
+    d = ApplyDesc()
+    d.n, d.h, d.w, d.c, d.up = n, h, w, c, 1
+    d.pad_t, d.pad_b, d.pad_l, d.pad_r = pad
+    d.pad_mode = pad_mode
+    d.pre_slope, d.pre_gain, d.post_slope, d.post_gain = pre_slope, pre_gain, post_slope, post_gain
+    d.res_mode = res_mode
+    d.x_dtype = d.out_dtype = d.res_dtype = dt(x)
+    d.out_c_stride, d.out_c_off = c, 0
+    d.out_border, d.res_border = 0, res_border
+    nbytes = x.numel() * 2 + out.numel() * 2
+    if res is not None:
+        assert res.is_contiguous() and res.dtype == torch.bfloat16
+        nbytes += res.numel() * 2
+    with _Prof("affine_apply", nbytes, "n%d %dx%d c%d pad%s res%d +stats" % (n, h, w, c, "".join(map(str, pad)), res_mode)):
+        check(_L().ppst_affine_apply_stats(ptr(out), ptr(x), ptr(a), ptr(b), ptr(res), ptr(ra), ptr(rb), ctypes.byref(d),
+                                           ptr(sbuf), stream()))
+    return out, {"sum": sbuf[0], "sumsq": sbuf[1], "n_partials": oh, "count": oh * ow}
+
+
 def affine_apply_torgb(x, a, b, res, rgb_w, rgb_bias, post_gain=1.0, write_out=True):
     """The last UpsamplingResBlock tail + ToRGB's 1x1 conv in one pass (ppst_affine_apply_torgb).
     x bf16 NHWC [n,h,w,128], res bf16 [n,h/2,w/2,128] -> (out bf16 [n,h,w,128] or None, rgb f32 [n,h,w,3])."""
