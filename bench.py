@@ -2,7 +2,8 @@
 """Benchmark of the PPST swap hot path (BASELINE.json metric: swapped images/s @512^2 at 1/2/4/8 B200).
 
     python bench.py --gpus N --steps K --warmup W            # ours (ppst_b200, bf16 tensor-core mode)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own modules on the host cores (staged copy
+                                                             # oracle/_ref/reference; the oracle port if it is absent)
 
 Workload (config.workload): BASELINE configs[1] "batched swap inference at 512^2, batch 64 ... sharded over
 8xB200" = 8 (content, style) pairs per GPU per step, weak scaling (per-GPU work fixed, 64 pairs at N=8).
@@ -33,6 +34,8 @@ import torch  # noqa: E402
 PAIRS_PER_GPU = 8
 SIZE = 512
 FLOP_PER_IMAGE = 2.143e12            # conv + GEMM 2*MAC of the minimal swap unit at 512^2
+FLOP_PER_IMAGE_RUN = 2.143e12 - 22.65e9   # what the engine runs: E2(style)'s trunk is computed once, not again inside
+                                          # E2(style, corr) as encode2 does (E2 plain = 22.65 GF)
 METRIC = "swapped images/s @512^2"
 
 
@@ -118,55 +121,69 @@ def make_inputs(pairs, rank):
     return c, s
 
 
-def cpu_baseline_sample(threads):
-    """The oracle port of the reference's CPU path on a bounded sample: ONE pair at 512^2 (2.143 TFLOP), all host
-    threads.  Returns (images/s, seconds)."""
+def _cpu_reference(threads):
+    """The reference's CPU implementation of one swap unit: a callable() -> image, plus its `kind`.
+    "reference": the UNMODIFIED reference modules and PPSTModel methods (oracle/ref_harness.RefModel over the staged copy
+    oracle/_ref/reference, use_custom_kernel = False -> upfirdn2d_native / F.leaky_relu, fp32, all host threads) on the
+    same seeded weights / inputs as the GPU arm; "port": the oracle's restatement, if the staged tree is absent."""
+    import contextlib
     from oracle import ppst_oracle as O
+    from oracle import ref_harness as RH
     torch.set_num_threads(threads)
-    sdE1, sdE2, sdG = O.make_networks(0)
+    sds = O.make_networks(0)
     c = O.make_portraits(1, SIZE, SIZE, seed=1234)
     s = O.make_portraits(1, SIZE, SIZE, seed=4321, smooth=True)
     noises = O.make_noises(1, SIZE, SIZE)
-    reps = 3
-    with torch.no_grad():
-        O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)          # warm-up (allocator, oneDNN primitive caches)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
-        dt = (time.perf_counter() - t0) / reps
-    return 1.0 / dt, dt * (reps + 1)
+    if RH.available():
+        with contextlib.redirect_stdout(sys.stderr):           # the reference prints while it initialises its networks
+            m = RH.RefModel(sds, device="cpu", noises=noises)
+        return (lambda: m.swap_unit(c, s)), "reference"
+
+    def port():
+        with torch.no_grad():
+            return O.swap_pair(*sds, c, s, noises=noises)
+    return port, "port"
+
+
+def cpu_baseline_sample(threads):
+    """The reference's CPU path on a bounded sample: ONE pair at 512^2 (2.143 TFLOP), all host threads.
+    Returns (images/s, seconds of CPU work, kind)."""
+    fn, kind = _cpu_reference(threads)
+    reps = 2
+    fn()                                                       # warm-up (allocator, oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    dt = (time.perf_counter() - t0) / reps
+    return 1.0 / dt, dt * (reps + 1), kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: /root/reference does not
-    exist on the GPU box and is Python, so nothing can be compiled into oracle/_ref), all host threads, each step a
-    bounded sample of the workload (one pair)."""
+    """--impl reference: the reference's own CPU implementation of the path (its unmodified modules from the staged copy
+    oracle/_ref/reference; the oracle port only if that copy is absent), all host threads, each step a bounded sample of
+    the workload (one pair)."""
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import ppst_oracle as O
     threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    sdE1, sdE2, sdG = O.make_networks(0)
-    c = O.make_portraits(1, SIZE, SIZE, seed=1234)
-    s = O.make_portraits(1, SIZE, SIZE, seed=4321, smooth=True)
-    noises = O.make_noises(1, SIZE, SIZE)
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    with torch.no_grad():
-        for _ in range(warm):
-            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            O.swap_pair(sdE1, sdE2, sdG, c, s, noises=noises)
-        dt = (time.perf_counter() - t0) / steps
+    fn, kind = _cpu_reference(threads)
+    steps, warm = max(1, min(args.steps, 4)), max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
     v = 1.0 / dt
+    what = ("the reference's own modules and PPSTModel methods, use_custom_kernel=False (upfirdn2d_native / F.leaky_relu)"
+            if kind == "reference" else "oracle port of the reference's pure-PyTorch CPU path (staged reference tree absent)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C2 swap @512^2; reference arm = bounded sample of 1 (content, style) pair per step "
-                                   "on host cores (oracle port of the reference's pure-PyTorch CPU path)",
+                                   "on host cores: " + what,
                        "pairs_per_step": 1, "size": SIZE},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": kind,
                              "sample": "1 pair @512^2 per step, %d step(s)" % steps},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -368,19 +385,50 @@ def main():
     total_pairs = pairs * world
     value = total_pairs * args.steps / (ms * 1e-3)
     e2e = total_pairs * args.steps / (ms_e2e * 1e-3)
-    # every ppst_conv_tc launch of a step: the convolutions and the two split GEMMs (corrm logits, corr @ features)
-    tc = {"work": 0.0, "ms": 0.0, "launches": 0, "aux": 0.0}
+    # every ppst_conv_tc launch of a step: the convolutions and the two split GEMMs (corrm logits, corr @ features).
+    # "alg" = ALGORITHMIC FLOPs of the reference op each launch stands for (3x3 / 1x1 taps for the layers
+    # whose Blur is folded into 5x5 / 3x3 taps, 1 x K for the 3-term split GEMMs); "work" = executed FLOPs.
+    tc = {"work": 0.0, "alg": 0.0, "ms": 0.0, "launches": 0, "aux": 0.0}
     for key in ("conv_tc", "gemm_split_tc"):
         for f in tc:
             tc[f] += prof.get(key, {}).get(f, 0)
     if tc["ms"] <= 0:
         tc["ms"] = 1.0
-    achieved_tf = tc["work"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
     step_ms_prof = sum(v["ms"] for v in prof.values()) / max(prof_steps, 1)
+    # share of the step spent in the tensor-core kernel UNDER GRAPH REPLAY: kernel activity records (CUPTI through
+    # torch.profiler) of two replays; the share, not the absolute (activity tracing perturbs absolute times slightly)
+    tc_share = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as kprof:
+            for _ in range(2):
+                step_device()
+            torch.cuda.synchronize()
+        tc_us = all_us = 0.0
+        for e in kprof.events():
+            if e.device_type != torch.autograd.DeviceType.CUDA:
+                continue
+            d_us = e.time_range.end - e.time_range.start
+            all_us += d_us
+            if "conv_tc" in e.name:
+                tc_us += d_us
+        if all_us > 0:
+            tc_share = tc_us / all_us
+    except Exception:
+        tc_share = None
+    share_source = "kernel activity records of 2 graph replays (torch.profiler / CUPTI)"
+    if tc_share is None:                                   # fall back to the eager event profile (wrapped launches only)
+        tc_share = (tc["ms"] / max(prof_steps, 1)) / step_ms_prof if step_ms_prof else 0.0
+        share_source = "eager per-launch CUDA events (wrapped launches only)"
+    achieved_eager = tc["alg"] / (tc["ms"] * 1e-3) / 1e12
+    ms_step = ms / args.steps
+    tc_ms_in_step = tc_share * ms_step
+    achieved_tf = (tc["alg"] / max(prof_steps, 1)) / (tc_ms_in_step * 1e-3) / 1e12 if tc_ms_in_step > 0 else 0.0
+    executed_tf = (tc["work"] / max(prof_steps, 1)) / (tc_ms_in_step * 1e-3) / 1e12 if tc_ms_in_step > 0 else 0.0
     kernels = {k: {"launches_per_step": v["launches"] // max(prof_steps, 1), "ms_per_step": v["ms"] / max(prof_steps, 1),
                    "share": (v["ms"] / max(prof_steps, 1)) / step_ms_prof if step_ms_prof else None,
                    ("tflops" if k in ("conv_tc", "conv_simt", "gemm_f32", "gemm_split_tc") else "gbs"):
-                       v["work"] / (v["ms"] * 1e-3) / (1e12 if k in ("conv_tc", "conv_simt", "gemm_f32", "gemm_split_tc") else 1e9)
+                       v["alg"] / (v["ms"] * 1e-3) / (1e12 if k in ("conv_tc", "conv_simt", "gemm_f32", "gemm_split_tc") else 1e9)
                        if v["ms"] > 0 else None}
                for k, v in prof.items()}
 
@@ -395,8 +443,10 @@ def main():
                                "correlation swap (2.143 TFLOP/image)" % pairs,
                    "pairs_per_gpu": pairs, "size": SIZE, "parallelism": "pairs partitioned, no collective",
                    "l2": "working set per step >> 126 MB L2 (activations ~ GBs); no explicit flush needed",
-                   "whole_swap_tflops": value * FLOP_PER_IMAGE / 1e12 / world,
-                   "whole_swap_frac_of_bf16_sustained": value * FLOP_PER_IMAGE / 1e12 / world / peaks["tf_sustained"]},
+                   "flop_per_image": FLOP_PER_IMAGE_RUN,
+                   "flop_per_image_note": "SURVEY 8(d) unit (2.143 TF) minus the E2(style) trunk the engine does not recompute",
+                   "whole_swap_tflops": value * FLOP_PER_IMAGE_RUN / 1e12 / world,
+                   "whole_swap_frac_of_bf16_sustained": value * FLOP_PER_IMAGE_RUN / 1e12 / world / peaks["tf_sustained"]},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(2 * c_pin.numel() * 4),
                 "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -407,19 +457,24 @@ def main():
                      "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
                      "traffic_source": traffic_src,
-                     "algorithmic_flop_per_launch": tc["work"] / max(tc["launches"], 1),
+                     "how": "ALGORITHMIC FLOPs of all launches of one step / (their share of the CUDA-event-timed kernel "
+                            "time x the graph-replayed step time of `value`)",
+                     "algorithmic_flop_per_launch": tc["alg"] / max(tc["launches"], 1),
+                     "executed_flop_per_launch": tc["work"] / max(tc["launches"], 1),
+                     "executed_tflops_in_step": executed_tf,
+                     "achieved_eager_launches": achieved_eager,
+                     "frac_eager_launches": achieved_eager / peaks["tf_sustained"],
                      "algorithmic_bytes_per_launch": tc.get("aux", 0.0) / max(tc["launches"], 1),
                      "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "launches_per_step": tc["launches"] // max(prof_steps, 1),
-                     "share_of_step": (kernels.get("conv_tc", {}).get("share") or 0.0) +
-                                      (kernels.get("gemm_split_tc", {}).get("share") or 0.0)},
+                     "share_of_step": tc_share, "share_source": share_source, "ms_in_step": tc_ms_in_step},
         "kernels": kernels,
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        v, secs = cpu_baseline_sample(threads)
-        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": "1 pair @512^2 (2.143 TFLOP) per run; 1 warm-up + 3 timed runs, %.1f s of CPU "
+        v, secs, kind = cpu_baseline_sample(threads)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": kind,
+                                "sample": "1 pair @512^2 (2.143 TFLOP) per run; 1 warm-up + 2 timed runs, %.1f s of CPU "
                                           "work in total" % secs}
     else:
         line["cpu_baseline"] = None

@@ -576,7 +576,9 @@ __global__ void __launch_bounds__(256, 2) affine_apply_bilin_rows_kernel(TO* __r
                     lanes, (int64_t)ni * (h + 2 * P) + oyp, (int64_t)d.n * (h + 2 * P) * d.c);
 }
 
-// mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows)
+// mode 0 bilinear (align_corners False), mode 1 adaptive average (integer windows).
+// One block per output row of one image (grid = (out_h, n)); a thread owns one group of V channels -- its affine
+// coefficients stay in registers -- and walks along the row: no integer division per element, 32-bit index math.
 template <typename TX, typename TO, int V>
 __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, const TX* __restrict__ x, int64_t n,
                                                        int in_h, int in_w, int out_h, int out_w, int c,
@@ -585,22 +587,26 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
                                                        float slope, int ib, int ob) {
   // ib / ob: border (pixels) of the input / output buffers; both are addressed at their interiors
   const int cv = c / V;
-  const int64_t total = n * out_h * out_w * cv;
+  const int oy = blockIdx.x;
+  const int64_t ni = blockIdx.y;
   const int in_wp = in_w + 2 * ib;
   const float sh = (float)in_h / (float)out_h, sw = (float)in_w / (float)out_w;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(t % cv);
-    int64_t r = t / cv;
-    const int ox = (int)(r % out_w); r /= out_w;
-    const int oy = (int)(r % out_h);
-    const int64_t ni = r / out_h;
+  TO* orow = out + ((ni * (out_h + 2 * ob) + oy + ob) * (out_w + 2 * ob) + ob) * (int64_t)out_c_stride + out_c_off;
+  const TX* img = x + ((ni * (in_h + 2 * ib) + ib) * in_wp + ib) * (int64_t)c;
+  const bool tf = (a != nullptr);
+  // vertical part of the bilinear stencil is the same for the whole row
+  float sy = sh * ((float)oy + 0.5f) - 0.5f;
+  if (sy < 0.f) sy = 0.f;
+  const int y0 = min((int)sy, in_h - 1);
+  const int y1 = y0 + ((y0 < in_h - 1) ? 1 : 0);
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+  const int fh = in_h / out_h, fw = in_w / out_w;          // adaptive-average window (mode 1)
+  const int cvb = cv < 256 ? cv : 256;                      // channel groups served concurrently
+  const int lanes = 256 / cvb, lane = threadIdx.x / cvb;
+  if (lane >= lanes) return;
+  for (int cg = threadIdx.x % cvb; cg < cv; cg += cvb) {
     const int ch = cg * V;
-    const TX* base = x + ((ni * (in_h + 2 * ib) + ib) * in_wp + ib) * (int64_t)c + ch;
-    float y[V];
-    // optional per-(n, c) affine + leaky/PReLU slope applied to every SOURCE sample (the normalisation + activation of
-    // the tensor being resampled, so that it never has to be materialised)
     float av[V], bv[V];
-    const bool tf = (a != nullptr);
     if (tf) {
 #pragma unroll
       for (int e = 0; e < V; ++e) { av[e] = a[ni * c + ch + e]; bv[e] = b ? b[ni * c + ch + e] : 0.0f; }
@@ -611,38 +617,40 @@ __global__ void __launch_bounds__(256) resample_kernel(TO* __restrict__ out, con
         for (int e = 0; e < V; ++e) v[e] = lrelu_slope(fmaf(v[e], av[e], bv[e]), slope);
       }
     };
-    if (mode == 0) {
-      float sy = sh * ((float)oy + 0.5f) - 0.5f, sx = sw * ((float)ox + 0.5f) - 0.5f;
-      if (sy < 0.f) sy = 0.f;
-      if (sx < 0.f) sx = 0.f;
-      const int y0 = min((int)sy, in_h - 1), x0 = min((int)sx, in_w - 1);
-      const int y1 = y0 + ((y0 < in_h - 1) ? 1 : 0), x1 = x0 + ((x0 < in_w - 1) ? 1 : 0);
-      const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-      float v00[V], v01[V], v10[V], v11[V];
-      load_ch<TX, V>(v00, base + ((int64_t)y0 * in_wp + x0) * c);
-      load_ch<TX, V>(v01, base + ((int64_t)y0 * in_wp + x1) * c);
-      load_ch<TX, V>(v10, base + ((int64_t)y1 * in_wp + x0) * c);
-      load_ch<TX, V>(v11, base + ((int64_t)y1 * in_wp + x1) * c);
-      xf(v00); xf(v01); xf(v10); xf(v11);
+    const TX* base = img + ch;
+    for (int ox = lane; ox < out_w; ox += lanes) {
+      float y[V];
+      if (mode == 0) {
+        float sx = sw * ((float)ox + 0.5f) - 0.5f;
+        if (sx < 0.f) sx = 0.f;
+        const int x0 = min((int)sx, in_w - 1);
+        const int x1 = x0 + ((x0 < in_w - 1) ? 1 : 0);
+        const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+        float v00[V], v01[V], v10[V], v11[V];
+        load_ch<TX, V>(v00, base + ((int64_t)y0 * in_wp + x0) * c);
+        load_ch<TX, V>(v01, base + ((int64_t)y0 * in_wp + x1) * c);
+        load_ch<TX, V>(v10, base + ((int64_t)y1 * in_wp + x0) * c);
+        load_ch<TX, V>(v11, base + ((int64_t)y1 * in_wp + x1) * c);
+        xf(v00); xf(v01); xf(v10); xf(v11);
 #pragma unroll
-      for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
-    } else {
-      const int fh = in_h / out_h, fw = in_w / out_w;
+        for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
+      } else {
 #pragma unroll
-      for (int e = 0; e < V; ++e) y[e] = 0.f;
-      for (int dy = 0; dy < fh; ++dy)
-        for (int dx = 0; dx < fw; ++dx) {
-          float v[V];
-          load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_wp + (ox * fw + dx)) * c);
-          xf(v);
+        for (int e = 0; e < V; ++e) y[e] = 0.f;
+        for (int dy = 0; dy < fh; ++dy)
+          for (int dx = 0; dx < fw; ++dx) {
+            float v[V];
+            load_ch<TX, V>(v, base + ((int64_t)(oy * fh + dy) * in_wp + (ox * fw + dx)) * c);
+            xf(v);
 #pragma unroll
-          for (int e = 0; e < V; ++e) y[e] += v[e];
-        }
-      const float inv = 1.0f / (float)(fh * fw);
+            for (int e = 0; e < V; ++e) y[e] += v[e];
+          }
+        const float inv = 1.0f / (float)(fh * fw);
 #pragma unroll
-      for (int e = 0; e < V; ++e) y[e] *= inv;
+        for (int e = 0; e < V; ++e) y[e] *= inv;
+      }
+      store_ch<TO, V>(orow + (int64_t)ox * out_c_stride + ch, y);
     }
-    store_ch<TO, V>(out + ((ni * (out_h + 2 * ob) + oy + ob) * (out_w + 2 * ob) + ox + ob) * (int64_t)out_c_stride + out_c_off + ch, y);
   }
 }
 
@@ -823,8 +831,8 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
   PPST_REQUIRE(out_c_off >= 0 && out_c_off + c <= out_c_stride, PPST_ERR_ARG, "resample: channel slice");
   const bool vec = (c % 8 == 0) && (out_c_stride % 8 == 0) && (out_c_off % 8 == 0) &&
                    ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  const int64_t total = n * out_h * out_w * (vec ? c / 8 : c);
-  const int grid = grid_for(total);
+  PPST_REQUIRE(n <= 65535, PPST_ERR_ARG, "resample: batch too large");
+  const dim3 grid((unsigned)out_h, (unsigned)n);
   cudaStream_t st = (cudaStream_t)stream;
 #define PPST_RS(TX, TO)                                                                                        \
   do {                                                                                                         \

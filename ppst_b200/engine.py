@@ -116,6 +116,8 @@ class Engine:
                                      out_hw=lambda h, w: ((h - 5) // 2 + 1, (w - 5) // 2 + 1))
             blk["skip"] = make_spec(ws, dev, stride=2, off=(-1, -1),
                                     out_hw=lambda h, w: ((h - 2) // 2 + 1, (w - 2) // 2 + 1))
+            blk["conv2"].extra["alg_taps"] = 9          # the reference op is a 3x3 / 1x1 convolution after a Blur
+            blk["skip"].extra["alg_taps"] = 1
             blk["b1"] = b1.detach().to(dev, torch.float32).contiguous()
             blk["b2"] = b2.detach().to(dev, torch.float32).contiguous()
             P["res%d" % i] = blk
@@ -240,7 +242,8 @@ class Engine:
             if want_stats:
                 sbuf = torch.empty(ops.conv_tc_stats_elems(d), device=x.device, dtype=torch.float32)
             ops.conv_tc(out, x, spec.w16 if w_per_image is None else w_per_image,
-                        spec.bias if bias_per_image is None else bias_per_image, noise, sbuf, d)
+                        spec.bias if bias_per_image is None else bias_per_image, noise, sbuf, d,
+                        alg_taps=spec.extra.get("alg_taps"))
             if want_stats:
                 half = sbuf.numel() // 2
                 stats = {"sum": sbuf[:half], "sumsq": sbuf[half:], "n_partials": half // (n * spec.cout),

@@ -27,10 +27,11 @@ PROFILE_DETAIL = False        # file launches under "name|tag" (tag = shape stri
 
 
 class _Prof:
-    def __init__(self, name, work, tag=None, aux=0.0):
+    def __init__(self, name, work, tag=None, aux=0.0, alg=None):
         self.name = name if not (PROFILE_DETAIL and tag) else "%s|%s" % (name, tag)
-        self.work = work
+        self.work = work            # EXECUTED work (FLOPs for GEMM-shaped kernels, bytes for HBM-bound ones)
         self.aux = aux              # secondary work figure (conv_tc: algorithmic bytes next to the FLOPs)
+        self.alg = work if alg is None else alg     # ALGORITHMIC work of the reference op this launch stands for
 
     def __enter__(self):
         global _prof_count
@@ -48,7 +49,7 @@ class _Prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.setdefault(self.name, []).append((self.work, self.e0, self.e1, self.aux))
+            PROFILE.setdefault(self.name, []).append((self.work, self.e0, self.e1, self.aux, self.alg))
         return False
 
 
@@ -58,7 +59,7 @@ def profile_summary():
     for name, recs in (PROFILE or {}).items():
         ms = sum(r[1].elapsed_time(r[2]) for r in recs)
         out[name] = {"launches": len(recs), "work": float(sum(r[0] for r in recs)), "ms": ms,
-                     "aux": float(sum(r[3] for r in recs))}
+                     "aux": float(sum(r[3] for r in recs)), "alg": float(sum(r[4] for r in recs))}
     return out
 
 
@@ -199,11 +200,15 @@ def conv_tc_stats_elems(d):
     return int(_L().ppst_conv_tc_stats_elems(ctypes.byref(d)))
 
 
-def conv_tc(out, x, weight_bf16, bias, noise, stats, d):
+def conv_tc(out, x, weight_bf16, bias, noise, stats, d, alg_taps=None):
+    """alg_taps: taps of the reference convolution this launch stands for when they differ from kh*kw (a Blur folded
+    into a stride-2 convolution executes 5x5 / 3x3 taps for an algorithmic 3x3 / 1x1, SURVEY.md 8(d) counts the latter)."""
     require_cuda(out, x, weight_bf16, bias, noise, stats)
     nbytes = (d.n * d.in_h * d.in_w * d.cin * 2 + d.n * d.full_h * d.full_w * d.cout * (2 if d.out_dtype == BF16 else 4)
               + weight_bf16.numel() * 2)
-    with _Prof("conv_tc", _conv_flops(d), "n%d %dx%d ci%d co%d k%dx%d s%d ph%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride, d.phases_y * d.phases_x), aux=nbytes):
+    flops = _conv_flops(d)
+    alg = flops if alg_taps is None else flops * alg_taps / float(d.kh * d.kw)
+    with _Prof("conv_tc", flops, "n%d %dx%d ci%d co%d k%dx%d s%d ph%d" % (d.n, d.out_h, d.out_w, d.cin, d.cout, d.kh, d.kw, d.stride, d.phases_y * d.phases_x), aux=nbytes, alg=alg):
         check(_L().ppst_conv_tc(ptr(out), ptr(x), ptr(weight_bf16), ptr(bias), ptr(noise), ptr(stats), ctypes.byref(d),
                                 stream()))
     return out
@@ -541,6 +546,7 @@ def gemm_split_tc(a_split, b_split, m_hw, out=None):
         out = torch.empty((bt, M, N), device=a_split.device, dtype=torch.float32)
     d = conv_desc((bt, m_hw[0], m_hw[1], k2), N, 1, 1, out_hw=m_hw, in_dtype=BF16, out_dtype=F32, w_img_rows=N,
                   split_terms=3)
-    with _Prof("gemm_split_tc", 2.0 * bt * M * N * (k2 // 2) * 3, "b%d m%d n%d k%d" % (bt, M, N, k2 // 2)):
+    with _Prof("gemm_split_tc", 2.0 * bt * M * N * (k2 // 2) * 3, "b%d m%d n%d k%d" % (bt, M, N, k2 // 2),
+               alg=2.0 * bt * M * N * (k2 // 2)):      # 3 bf16 products executed per algorithmic fp32 product
         check(_L().ppst_conv_tc(ptr(out), ptr(a_split), ptr(b_split), None, None, None, ctypes.byref(d), stream()))
     return out
