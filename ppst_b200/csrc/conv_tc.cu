@@ -146,6 +146,63 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// ---- cta_group::2 (CTA pair) variants.  kPeerMask clears the bit that distinguishes the two CTAs of a pair in the
+// shared::cluster window, so the address names the EVEN CTA's copy of a barrier from either CTA.
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of each CTA: its 128 rows] * B[smem: each CTA holds half of the N rows]
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the EVEN CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_even_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -779,6 +836,238 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+
+// =====================================================================================================================
+// CTA-pair (cta_group::2) form of the halo kernel for the layers whose 1-CTA form is bound by shared-memory bandwidth
+// (cout = 128: every M128 x N128 x K16 MMA reads 8 KB of operands in 64 clocks = the SM's whole 128 B/clk, while TMA writes
+// the next stages into the same memory).  Two CTAs on the two SMs of a TPC work on horizontally adjacent pixel tiles
+// (tx = 2*txp + rank) of the same image / phase / cout tile:
+//   * each CTA loads its own A boxes and only HALF of every B tile (its BN/2 weight rows); tcgen05.mma.cta_group::2,
+//     issued by the even CTA alone, multiplies both CTAs' A tiles with the B tile gathered from both halves -- per CTA the
+//     operand reads drop to 6 KB per MMA and the B fills halve;
+//   * accumulators stay per CTA (its 128 pixel rows x BN columns per sub-tile), so the epilogue is the 1-CTA one and every
+//     output element sees the same K order: results are bit-identical to conv_tc_halo_kernel.
+// Barriers: "full" barriers live in the even CTA and collect the transaction bytes of BOTH CTAs' TMA loads (the odd CTA's
+// loads name them through the peer-bit-masked address); tcgen05.commit multicasts the "empty" / "accumulator ready"
+// arrivals to both CTAs; the odd CTA's epilogue warps release an accumulator stage by a remote arrive on the even CTA.
+// =====================================================================================================================
+template <int BN, int BKC, int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ noise,
+                     float* __restrict__ stats_sum, float* __restrict__ stats_sq, const Params p) {
+  using S = HaloSmem<BN, MT>;
+  constexpr int BNH = BN / 2;                        // weight rows this CTA holds of every B tile
+  constexpr int kBBytes = BNH * BKC * 2;
+  constexpr int kSubBytes = BM * BKC * 2;
+  constexpr int kAccCols = MT * BN;
+  constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                 : (2 * kAccCols <= 256) ? 256 : 512;
+  static_assert(2 * kAccCols <= 512, "accumulators exceed tensor memory");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_slot_bytes = p.bps * kBBytes;
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + p.na * p.a_slot_bytes;
+  uint8_t* fixed = b_ring + p.nb * b_slot_bytes;
+  float* s_stats = reinterpret_cast<float*>(fixed);
+  float* s_bias = reinterpret_cast<float*>(fixed + S::kStatsBytes);
+  uint8_t* s_epi = fixed + S::kStatsBytes + S::kBiasBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_epi + S::kEpiBytes);
+  uint64_t* a_empty = a_full + kMaxA;
+  uint64_t* b_full = a_empty + kMaxA;
+  uint64_t* b_empty = b_full + kMaxB;
+  uint64_t* tmem_full = b_empty + kMaxB;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2] (the even CTA's copy is the one in use)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  for (int i = threadIdx.x; i < p.cout; i += kThreads) s_bias[i] = s_bias[kBiasSmem + i] = bias ? bias[i] : 0.0f;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.na; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.nb; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }   // 4 warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();                     // barriers of both CTAs are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_phases = p.phases_y * p.phases_x;
+  const int tiles_xp = p.tiles_x >> 1;    // tile-column pairs (tiles_x is even, host-checked)
+
+  // cluster work item -> (n-tile, phase, tile-column pair, super-tile row, image)
+  auto decode = [&](int tile, int& nt, int& ph, int& tx, int& tys, int& img) {
+    nt = tile % p.n_tiles_n; tile /= p.n_tiles_n;
+    ph = tile % n_phases; tile /= n_phases;
+    tx = 2 * (tile % tiles_xp) + rank; tile /= tiles_xp;
+    tys = tile % p.tiles_ys; img = tile / p.tiles_ys;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      const uint32_t a_box_bytes = (uint32_t)(p.a_rows * p.tw * BKC * 2);
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        int nt, ph, tx, tys, img;
+        decode(tile, nt, ph, tx, tys, img);
+        const int py = ph / p.phases_x, px = ph % p.phases_x;
+        const int iy0 = tys * MT * p.th + p.off_y + py * p.phase_off_dy;
+        const int ix0 = tx * p.tw + p.off_x + px * p.phase_off_dx;
+        const int brow = img * p.w_img_rows + ph * p.cout + nt * BN + rank * BNH;
+        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+          for (int kx = 0; kx < p.kw; ++kx) {
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2u * a_box_bytes);        // both CTAs' boxes
+            tma_load_4d_2sm(a_ring + sa * p.a_slot_bytes, &map_a, &a_full[sa], cb * BKC, ix0 + kx, iy0, img);
+            if (++sa == p.na) { sa = 0; pha ^= 1; }
+            for (int ky0 = 0; ky0 < p.kh; ky0 += p.bps) {
+              mbar_wait(&b_empty[sb], phb ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2u * (uint32_t)b_slot_bytes);
+              for (int j = 0; j < p.bps; ++j)
+                tma_load_2d_2sm(b_ring + sb * b_slot_bytes + j * kBBytes, &map_b, &b_full[sb],
+                                ((ky0 + j) * p.kw + kx) * p.cin + cb * BKC, brow);
+              if (++sb == p.nb) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (even CTA only) =====================
+    if (rank == 0 && elect_one()) {
+      // kind::f16: D=f32, A=B=bf16, K-major; N>>3 at bit 17, M>>4 at bit 24 with M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t dy_bytes = (uint32_t)(p.tw * BKC * 2);
+      int sa = 0, sb = 0, it = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);            // both CTAs' epilogues have drained this stage
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccCols);
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
+          for (int kx = 0; kx < p.kw; ++kx) {
+            mbar_wait(&a_full[sa], pha);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(a_ring + sa * p.a_slot_bytes);
+            for (int ky0 = 0; ky0 < p.kh; ky0 += p.bps) {
+              mbar_wait(&b_full[sb], phb);
+              tc_fence_after();
+              const uint32_t b_base = smem_u32(b_ring + sb * b_slot_bytes);
+              for (int j = 0; j < p.bps; ++j) {
+                const uint64_t db = make_smem_desc<BKC>(b_base + (uint32_t)(j * kBBytes));
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                  const uint64_t da = make_smem_desc<BKC>(a_base + (uint32_t)(ky0 + j) * dy_bytes + (uint32_t)(m * kSubBytes));
+#pragma unroll
+                  for (int k = 0; k < BKC / 16; ++k)
+                    umma_bf16_2sm(tmem_d + (uint32_t)(m * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                  (accumulate | (uint32_t)k) != 0 ? 1u : 0u);
+                }
+                accumulate = 1;
+              }
+              umma_commit_2sm(&b_empty[sb]);
+              if (++sb == p.nb) { sb = 0; phb ^= 1; }
+            }
+            umma_commit_2sm(&a_empty[sa]);
+            if (++sa == p.na) { sa = 0; pha ^= 1; }
+          }
+        }
+        umma_commit_2sm(&tmem_full[as]);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===================== epilogue (both CTAs, each on its own pixels) =====================
+    const int q = warp & 3;
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int row = q * 32 + lane;
+    const int ety = row / p.tw, etx = row - ety * p.tw;
+    float* s_bias_g = s_bias + group * kBiasSmem;
+    const int fh_pad = p.full_h + 2 * p.out_pad - p.out_pad_trim, fw_pad = p.full_w + 2 * p.out_pad - p.out_pad_trim;
+    int it = 0, cur_img = -1;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, ++it) {
+      if ((it & 1) != group) continue;
+      int nt, ph, tx, tys, img;
+      decode(tile, nt, ph, tx, tys, img);
+      if (p.bias_img_stride > 0 && img != cur_img) {
+        reload_group_bias(s_bias_g, bias, img, p.bias_img_stride, p.cout, group, (threadIdx.x - kEpiWarp0 * 32) & 127);
+        cur_img = img;
+      }
+      const int py = ph / p.phases_x, px = ph % p.phases_x;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int m = 0; m < MT; ++m) {
+        const int ty = tys * MT + m;
+        const int oy = ty * p.th + ety, ox = tx * p.tw + etx;
+        const bool valid = (oy < p.out_h) && (ox < p.out_w);
+        const int64_t pix = ((int64_t)img * p.full_h + (oy * p.phases_y + py)) * p.full_w + (ox * p.phases_x + px);
+        const float nz = (noise != nullptr && valid) ? p.noise_w * noise[pix] : 0.0f;
+        float* b_sum = s_stats + (size_t)((as * MT + m) * 2 + 0) * 4 * BN;
+        float* b_sq = s_stats + (size_t)((as * MT + m) * 2 + 1) * 4 * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols + m * BN);
+        int64_t soff[4];
+        uint32_t svalid = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int srow = q * 32 + 8 * i + (lane >> 2);
+          const int sy = srow / p.tw, sx = srow - sy * p.tw;
+          const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
+          if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
+          const int64_t spix = ((int64_t)img * fh_pad + (soy * p.phases_y + py) + p.out_pad) * fw_pad + (sox * p.phases_x + px) + p.out_pad;
+          soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
+        }
+        epilogue_rows_bf16<BN>(taddr, smem_u32(s_bias_g + nt * BN), smem_u32(s_epi + (warp - kEpiWarp0) * kEpiStageBytes),
+                               stats_sum ? b_sum + q * BN : nullptr, b_sq + q * BN, out, soff, svalid, nz, valid, p.gain,
+                               p.has_act ? p.slope : 1.0f, lane);
+        if (m == MT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_even_cta(&tmem_empty[as]);
+        }
+        if (stats_sum != nullptr) {
+          if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (ty < p.tiles_y) {
+            const int e = (threadIdx.x - kEpiWarp0 * 32) & 127;
+            const int slot = ((ty * p.tiles_x + tx) * n_phases + ph);
+            for (int c = e; c < BN; c += 128) {
+              const float s = (b_sum[c] + b_sum[BN + c]) + (b_sum[2 * BN + c] + b_sum[3 * BN + c]);
+              const float qv = (b_sq[c] + b_sq[BN + c]) + (b_sq[2 * BN + c] + b_sq[3 * BN + c]);
+              const int64_t o = ((int64_t)img * p.stats_partials + slot) * p.cout + nt * BN + c;
+              stats_sum[o] = s;
+              stats_sq[o] = qv;
+            }
+          }
+          if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                     // no CTA leaves while its pair still reads its shared memory / signals its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, kTmemCols);
+  }
+}
+
 // =====================================================================================================================
 // Weight-gradient kernel with MN-major operands (entry point in wgrad.cu): dw[co][tap][ci] = sum_pixels dy[pix][co] * x[pix + tap][ci].
 // The contraction runs over pixels, and NHWC tensors are pixel-major with the channels contiguous -- exactly the
@@ -1176,6 +1465,83 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   return 0;
 }
 
+
+// CTA-pair launch of the halo kernel (see conv_tc_halo2_kernel).  Same geometry / rings as launch_halo, half-size B tiles.
+template <int BN, int BKC, int MT>
+static int launch_halo2(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
+                        const float* noise, float* stats, cudaStream_t st) {
+  using S = HaloSmem<BN, MT>;
+  Params p;
+  std::memset(&p, 0, sizeof(p));
+  p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
+  p.kh = d.kh; p.kw = d.kw; p.stride = 1;
+  p.off_y = d.off_y; p.off_x = d.off_x; p.phases_y = d.phases_y; p.phases_x = d.phases_x;
+  p.phase_off_dy = d.phase_off_dy; p.phase_off_dx = d.phase_off_dx;
+  p.full_h = d.full_h; p.full_w = d.full_w; p.cout_stride = d.cout_stride; p.c_off = d.c_off;
+  pick_tile(d.out_h, d.out_w, p.th, p.tw);
+  p.tiles_y = ceil_div(d.out_h, p.th); p.tiles_x = ceil_div(d.out_w, p.tw);
+  PPST_REQUIRE(p.tiles_x % 2 == 0, PPST_ERR_ARG, "conv_tc(halo2): odd number of tile columns");
+  p.tiles_ys = ceil_div(p.tiles_y, MT);
+  p.n_tiles_n = d.cout / BN;
+  const int n_phases = d.phases_y * d.phases_x;
+  const int64_t tiles = (int64_t)d.n * p.tiles_ys * (p.tiles_x / 2) * n_phases * p.n_tiles_n;     // cluster work items
+  PPST_REQUIRE(tiles < (1LL << 31), PPST_ERR_ARG, "conv_tc: too many tiles");
+  p.num_tiles = (int)tiles;
+  p.kblocks_per_tap = d.cin / BKC;
+  p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
+  p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
+  p.a_rows = MT * p.th + d.kh - 1;
+  p.a_slot_bytes = (p.a_rows * p.tw * BKC * 2 + 1023) / 1024 * 1024;
+  constexpr int kBBytes = (BN / 2) * BKC * 2;
+  p.bps = (d.kh * kBBytes <= 24576) ? d.kh : 1;
+  const int b_slot = p.bps * kBBytes;
+  const int avail = S::kMaxDynamic - S::kFixedBytes;
+  p.na = p.a_slot_bytes <= 24576 ? 4 : 3;
+  while (p.na > 2 && avail - p.na * p.a_slot_bytes < 3 * b_slot) --p.na;
+  p.nb = (avail - p.na * p.a_slot_bytes) / b_slot;
+  if (p.nb > kMaxB) p.nb = kMaxB;
+  PPST_REQUIRE(p.nb >= 2 && p.na >= 2, PPST_ERR_UNSUPPORTED, "conv_tc(halo2): rings do not fit in shared memory");
+  const int smem_total = p.na * p.a_slot_bytes + p.nb * b_slot + S::kFixedBytes;
+
+  CUtensorMap map_a, map_b;
+  {
+    const uint64_t dims[4] = {(uint64_t)d.cin, (uint64_t)d.in_w, (uint64_t)d.in_h, (uint64_t)d.n};
+    const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
+    const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
+    const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
+    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)p.tw, (uint32_t)p.a_rows, 1};
+    const uint32_t est[4] = {1, 1, 1, 1};
+    int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t K = (uint64_t)d.kh * d.kw * d.cin;
+    const uint64_t dims[2] = {K, d.w_img_rows ? (uint64_t)d.w_img_rows * d.n : (uint64_t)d.cout * n_phases};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {(uint32_t)BKC, (uint32_t)(BN / 2)};
+    const uint32_t est[2] = {1, 1};
+    int rc = encode_map(&map_b, weight, 2, dims, strides, box, est, BKC);
+    if (rc) return rc;
+  }
+  p.w_img_rows = d.w_img_rows;
+  p.out_pad = d.out_pad; p.out_pad_trim = d.out_pad_trim; p.bias_img_stride = d.bias_img_stride;
+  auto kern = conv_tc_halo2_kernel<BN, BKC, MT>;
+  static bool attr_set[kMaxDevices] = {false};
+  if (!attr_set[cur_device()]) {
+    int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kMaxDynamic),
+                        "cudaFuncSetAttribute(conv_tc_halo2)");
+    if (rc) return rc;
+    attr_set[cur_device()] = true;
+  }
+  const int pairs = num_sms() / 2;
+  const int clusters = p.num_tiles < pairs ? p.num_tiles : pairs;
+  float* ssum = stats;
+  float* ssq = stats ? stats + (int64_t)d.n * p.stats_partials * d.cout : nullptr;
+  kern<<<2 * clusters, kThreads, smem_total, st>>>(map_a, map_b, reinterpret_cast<__nv_bfloat16*>(out), bias, noise, ssum, ssq, p);
+  PPST_LAUNCH_CHECK("conv_tc_halo2_kernel");
+  return 0;
+}
+
 // 0: plain kernel; else MT (1 or 2) of the halo kernel for this layer
 static int halo_mode(const ppst_conv_desc& d, int bn) {
   static const int env_halo = [] { const char* e = getenv("PPST_CONV_TC_HALO"); return e ? atoi(e) : 1; }();
@@ -1189,6 +1555,19 @@ static int halo_mode(const ppst_conv_desc& d, int bn) {
   if (env_mt == 1 || env_mt == 2) return env_mt;
   const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * ceil_div(d.out_w, tw) * d.phases_y * d.phases_x * (d.cout / bn);
   return (ceil_div(d.out_h, th) >= 2 && tiles >= 4LL * num_sms()) ? 2 : 1;
+}
+
+// CTA-pair (cta_group::2) form of the halo kernel?  PPST_CONV_TC_2CTA: 0 never, 1 cout-128 layers only, 2 (default) also the
+// cout % 256 == 0 layers (measured on B200, 8 x 256^2 x 256 -> 256: 1348 -> 1551 TF/s; 8 x 128^2 x 512 -> 512: 1436 -> 1644).
+static bool pair_mode(const ppst_conv_desc& d, int bn) {
+  const char* e = getenv("PPST_CONV_TC_2CTA");        // read per call: tests toggle it
+  const int env = e ? atoi(e) : 2;
+  if (env == 0 || (bn != 128 && bn != 256) || (bn == 256 && env < 2)) return false;
+  int th, tw;
+  pick_tile(d.out_h, d.out_w, th, tw);
+  const int tiles_x = ceil_div(d.out_w, tw);
+  const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * tiles_x * d.phases_y * d.phases_x * (d.cout / bn);
+  return tiles_x % 2 == 0 && tiles >= 2LL * num_sms();
 }
 
 }  // namespace tc
@@ -1300,6 +1679,11 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
 #define PPST_TC(BN_, BKC_)                                                                   \
   do {                                                                                       \
     const int hm = tc::halo_mode(d, BN_);                                                    \
+    if (hm >= 1 && BKC_ == 64 && tc::pair_mode(d, BN_)) {                                    \
+      if (hm == 2 && BN_ == 128)                                                             \
+        return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, (BN_ == 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
+      return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, 1>(d, out, in, weight, bias, noise, stats, st); \
+    }                                                                                        \
     if (hm == 2 && BN_ <= 128)                                                               \
       return tc::launch_halo<BN_, BKC_, (BN_ <= 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
     if (hm >= 1) return tc::launch_halo<BN_, BKC_, 1>(d, out, in, weight, bias, noise, stats, st);         \

@@ -102,26 +102,31 @@ class Engine:
         P["from_rgb"] = make_spec(sd["FromRGB.Conv.weight"], dev, scale=1 / math.sqrt(3), bias=sd["FromRGB.Act.bias"],
                                   act=True)
         for i, (ci, co) in zip((1, 2, 4), E_CH):
-            p = "%s.ResBlockDownBy%d." % (down, i)
-            k = sd[p + "conv2.Blur.kernel"].to(torch.float32)
-            w1 = sd[p + "conv1.Conv.weight"]
-            w2 = packing.fold_fir(sd[p + "conv2.Conv.weight"].to(torch.float32) / math.sqrt(ci * 9), k)
-            ws = packing.fold_fir(sd[p + "skip.Conv.weight"].to(torch.float32) / math.sqrt(ci),
-                                  sd[p + "skip.Blur.kernel"].to(torch.float32))
-            b1, b2 = sd[p + "conv1.Act.bias"], sd[p + "conv2.Act.bias"]
-            blk = {}
-            # norm=True: IN sits between conv and activation, so bias+act move to the apply pass
-            blk["conv1"] = make_spec(w1, dev, scale=1 / math.sqrt(ci * 9), bias=None if norm else b1, act=not norm)
-            blk["conv2"] = make_spec(w2, dev, stride=2, off=(0, 0), bias=None if norm else b2, act=not norm,
-                                     out_hw=lambda h, w: ((h - 5) // 2 + 1, (w - 5) // 2 + 1))
-            blk["skip"] = make_spec(ws, dev, stride=2, off=(-1, -1),
-                                    out_hw=lambda h, w: ((h - 2) // 2 + 1, (w - 2) // 2 + 1))
-            blk["conv2"].extra["alg_taps"] = 9          # the reference op is a 3x3 / 1x1 convolution after a Blur
-            blk["skip"].extra["alg_taps"] = 1
-            blk["b1"] = b1.detach().to(dev, torch.float32).contiguous()
-            blk["b2"] = b2.detach().to(dev, torch.float32).contiguous()
-            P["res%d" % i] = blk
+            P["res%d" % i] = self._pack_res_block(sd, "%s.ResBlockDownBy%d." % (down, i), norm)
         return P
+
+    def _pack_res_block(self, sd, p, norm):
+        """One ResBlock (stylegan2_layers.py:559-579) with reflection padding and a [1,2,1] blur, keys under prefix p."""
+        dev = self.device
+        ci = sd[p + "conv1.Conv.weight"].shape[1]
+        k = sd[p + "conv2.Blur.kernel"].to(torch.float32)
+        w1 = sd[p + "conv1.Conv.weight"]
+        w2 = packing.fold_fir(sd[p + "conv2.Conv.weight"].to(torch.float32) / math.sqrt(ci * 9), k)
+        ws = packing.fold_fir(sd[p + "skip.Conv.weight"].to(torch.float32) / math.sqrt(ci),
+                              sd[p + "skip.Blur.kernel"].to(torch.float32))
+        b1, b2 = sd[p + "conv1.Act.bias"], sd[p + "conv2.Act.bias"]
+        blk = {}
+        # norm=True: IN sits between conv and activation, so bias+act move to the apply pass
+        blk["conv1"] = make_spec(w1, dev, scale=1 / math.sqrt(ci * 9), bias=None if norm else b1, act=not norm)
+        blk["conv2"] = make_spec(w2, dev, stride=2, off=(0, 0), bias=None if norm else b2, act=not norm,
+                                 out_hw=lambda h, w: ((h - 5) // 2 + 1, (w - 5) // 2 + 1))
+        blk["skip"] = make_spec(ws, dev, stride=2, off=(-1, -1),
+                                out_hw=lambda h, w: ((h - 2) // 2 + 1, (w - 2) // 2 + 1))
+        blk["conv2"].extra["alg_taps"] = 9          # the reference op is a 3x3 / 1x1 convolution after a Blur
+        blk["skip"].extra["alg_taps"] = 1
+        blk["b1"] = b1.detach().to(dev, torch.float32).contiguous()
+        blk["b2"] = b2.detach().to(dev, torch.float32).contiguous()
+        return blk
 
     def _pack_styled(self, sd, p, upsample_fused_ok=True):
         """StyledConv (stylegan2_layers.py:439-475): all three additive per-channel terms (conv.bias, .bias,

@@ -731,3 +731,59 @@ def test_guided_smooth_matches_oracle():
         assert (lv > 0).mean() <= 1e-4, (n, h, w, float((lv > 0).mean()))
     with pytest.raises(RuntimeError):
         ops.guided_smooth(torch.zeros(1, 3, 20, 20, device=DEV), torch.zeros(1, 3, 20, 20, device=DEV), radius=30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [
+    # (n, h, w, cin, cout, mode)  mode: "3x3" zero-padded, "up" = fused 2x2-phase transposed conv, "lazy" = per-sample weights
+    (4, 128, 128, 128, 128, "3x3"), (2, 64, 96, 256, 128, "3x3"), (3, 64, 64, 256, 384, "3x3"),
+    (2, 128, 128, 256, 128, "up"), (2, 96, 64, 128, 128, "lazy"), (2, 128, 128, 256, 256, "3x3"), (2, 64, 64, 512, 512, "up"),
+])
+def test_conv_tc_cta_pair_kernel_is_bit_identical_to_single_cta(shape):
+    """conv_tc_halo2_kernel (tcgen05.mma.cta_group::2, B tiles split over the two CTAs of a pair) against the 1-CTA halo
+    kernel: same K order per output element, so outputs AND instance-norm partials must agree bit for bit."""
+    import math
+    import os
+    from ppst_b200 import ops, packing
+    from ppst_b200._lib import BF16
+    from ppst_b200.engine import Engine
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    n, h, w, ci, co, mode = shape
+    eng = Engine.__new__(Engine)
+    eng.use_tc, eng.adt, eng.device, eng.mode, eng.acode = True, torch.bfloat16, torch.device("cuda"), "bf16", BF16
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, h, w, ci, generator=g).to(torch.bfloat16).cuda()
+    wt = torch.randn(co, ci, 3, 3, generator=g) / math.sqrt(ci * 9)
+    bias = torch.randn(co, generator=g)
+    kw = {}
+    if mode == "up":
+        spec = packing.make_upscale_spec(wt, "cuda", bias=bias, act=True, noise_w=0.3)
+        noise = torch.randn(n, 1, 2 * h, 2 * w, generator=g).cuda()
+    else:
+        spec = packing.make_spec(wt, "cuda", bias=bias, act=True, pad=1, noise_w=0.3)
+        noise = torch.randn(n, 1, h, w, generator=g).cuda()
+        if mode == "lazy":
+            a = (torch.rand(n, ci, generator=g) + 0.5).cuda()
+            b = torch.randn(n, ci, generator=g).cuda()
+            wn, bn = ops.modulate_weights(spec.w32, a, b, 9, ci, base_bias=spec.bias)
+            kw = dict(w_per_image=wn, bias_per_image=bn)
+    res = {}
+    old = os.environ.get("PPST_CONV_TC_2CTA")
+    try:
+        for flag in ("0", "2"):
+            os.environ["PPST_CONV_TC_2CTA"] = flag
+            y, st = eng.conv(x, spec, noise=noise, want_stats=True, out_pad=1 if mode == "up" else 0, **kw)
+            torch.cuda.synchronize()
+            res[flag] = (y.clone(), st["sum"].clone(), st["sumsq"].clone())
+    finally:
+        if old is None:
+            os.environ.pop("PPST_CONV_TC_2CTA", None)
+        else:
+            os.environ["PPST_CONV_TC_2CTA"] = old
+    if mode == "up":
+        i0, i2 = res["0"][0][:, 1:-1, 1:-1], res["2"][0][:, 1:-1, 1:-1]        # the border belongs to the caller
+    else:
+        i0, i2 = res["0"][0], res["2"][0]
+    assert torch.equal(i0, i2)
+    assert torch.equal(res["0"][1], res["2"][1]) and torch.equal(res["0"][2], res["2"][2])

@@ -1,0 +1,145 @@
+"""Parity cases the round-1 review asked for:
+  * the reference-run MODULE fixtures (tests/golden/layers.npz: ResBlock, StyledConv x3 paths, ResidualBlock, made by
+    oracle/gen_golden.py from the unmodified reference modules) loaded into the engine's own layer functions on the GPU
+    (fp32 mode, max-abs <= 1e-4);
+  * the BENCHED batch: a row of an 8-pair swap_graph step is bit-identical to the same pair run alone and >= 45 dB against
+    the CPU restatement;
+  * BASELINE configs[3] at full size: plain swap at 1024^2, batch 16 -- a row bit-identical to the same pair alone, and
+    >= 45 dB against the CPU restatement of that pair."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fp32_engine():
+    from ppst_b200 import ops  # noqa: F401  (loads the library)
+    from ppst_b200._lib import F32
+    from ppst_b200.engine import Engine
+    e = Engine.__new__(Engine)
+    e.device, e.mode, e.adt, e.acode, e.use_tc, e.padded = torch.device("cuda"), "fp32", torch.float32, F32, False, False
+    e._keep, e._side, e._side_live = [], {}, set()
+    return e
+
+
+def _fixture(name):
+    z = np.load(os.path.join(GOLD, "layers.npz"))
+    sd = {k[len(name) + 4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + "/sd/")}
+    ins = []
+    while "%s/in%d" % (name, len(ins)) in z.files:
+        ins.append(torch.from_numpy(z["%s/in%d" % (name, len(ins))]))
+    return sd, ins, torch.from_numpy(z[name + "/out"])
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous().cuda()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+@pytest.mark.parametrize("name,norm", [("resblock_in", True), ("resblock_none", False)])
+def test_reference_resblock_fixture_through_engine_res_block(name, norm):
+    e = _fp32_engine()
+    sd, (x,), ref = _fixture(name)
+    blk = e._pack_res_block(sd, "", norm)
+    y = _nchw(e._res_block(blk, _nhwc(x), norm))
+    assert y.shape == ref.shape
+    assert float((y - ref).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("name,ups", [("styled_plain", False), ("styled_up_small", True), ("styled_up_fused", True)])
+def test_reference_styledconv_fixture_through_engine_styled(name, ups):
+    from ppst_b200 import ops
+    from ppst_b200.packing import make_upscale_spec
+    e = _fp32_engine()
+    sd, (x, style, noise), ref = _fixture(name)
+    P = e._pack_styled(sd, "")
+    if ups:
+        P["fused_up"] = make_upscale_spec(sd["conv.weight"], e.device, bias=P["plain"].bias, act=True, noise_w=P["noise_w"])
+    lw, lb = P["lin_w"], P["lin_b"]
+    s = ops.linear(style.cuda(), lw, lb, w_scale=lw.shape[1] ** -0.5)          # EqualizedLinear(use_wscale) of StyleMod
+    y, a, b = e._styled(P, _nhwc(x), s, noise.cuda().contiguous(), upsample=ups)
+    out = _nchw(e.apply(y, a, b))
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-4
+
+
+def test_reference_residual_block_fixture_through_engine():
+    from ppst_b200.packing import make_spec
+    e = _fp32_engine()
+    sd, (x,), ref = _fixture("residual_block")
+    P = {"c1": make_spec(sd["conv1.weight"], e.device, bias=sd["conv1.bias"]),
+         "c2": make_spec(sd["conv2.weight"], e.device, bias=sd["conv2.bias"]),
+         "a": float(sd["prelu.weight"].reshape(-1)[0])}
+    for border in (0, 1):                      # plain, and inside a replicated border (what the padded path feeds it)
+        xin = _nhwc(x)
+        if border:
+            xin = torch.nn.functional.pad(x, (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1).contiguous().cuda()
+        y = _nchw(e._residual_block(P, xin, border=border))
+        assert float((y - ref).abs().max()) <= 1e-4
+
+
+def _psnr(a, b):
+    peak = float(b.max() - b.min())
+    return 10 * math.log10(peak * peak / max(float(((a - b) ** 2).mean()), 1e-30))
+
+
+def test_row_of_the_benched_8_pair_graph_step_matches_single_pair_and_oracle():
+    import ppst_b200
+    from oracle import ppst_oracle as O
+    from ppst_b200 import synthetic as S
+    sds = S.make_networks(0)
+    m = ppst_b200.SwapModel(*sds, mode="bf16")
+    if not m.engine.use_tc:
+        pytest.skip("tcgen05 path unavailable")
+    noises1 = S.make_noises(1, 512, 512)
+    m.noises = {k: v.expand(8, -1, -1, -1).contiguous() for k, v in noises1.items()}     # as bench.py sets them
+    c = S.make_portraits(8, 512, 512, seed=1234)
+    s = S.make_portraits(8, 512, 512, seed=4321, smooth=True)
+    out8 = m.swap_graph(c.cuda(), s.cuda()).clone()
+    out8_again = m.swap_graph(c.cuda(), s.cuda()).clone()
+    assert torch.equal(out8, out8_again)
+    row = 5
+    m.noises = noises1
+    out1 = m.swap(c[row:row + 1].cuda(), s[row:row + 1].cuda())
+    assert torch.equal(out8[row:row + 1], out1)          # MT = 2 kernels at batch 16 / 8, MT = 1 at batch 2 / 1: same bits
+    with torch.no_grad():
+        ref = O.swap_pair(*sds, c[row:row + 1], s[row:row + 1], noises=noises1)
+    p = _psnr(out1.cpu(), ref)
+    print("8-pair graph step, row %d vs oracle: %.1f dB" % (row, p))
+    assert p >= 45.0, p
+
+
+def test_plain_swap_1024_batch16_rows_match_single_pair_and_oracle():
+    import ppst_b200
+    from oracle import ppst_oracle as O
+    from ppst_b200 import synthetic as S
+    sds = S.make_networks(0)
+    m = ppst_b200.SwapModel(*sds, mode="bf16")
+    if not m.engine.use_tc:
+        pytest.skip("tcgen05 path unavailable")
+    n, size = 16, 1024
+    noises1 = S.make_noises(1, size, size, seed=21)
+    m.noises = {k: v.expand(n, -1, -1, -1).contiguous() for k, v in noises1.items()}
+    c = S.make_portraits(n, size, size, seed=31, smooth=True)
+    s = S.make_portraits(n, size, size, seed=32, smooth=True)
+    with torch.no_grad():
+        out = m.plain_swap(c.cuda(), s.cuda())
+    assert out.shape == (n, 3, size, size) and bool(torch.isfinite(out).all())
+    row = 11
+    m.noises = noises1
+    one = m.plain_swap(c[row:row + 1].cuda(), s[row:row + 1].cuda())
+    assert torch.equal(out[row:row + 1], one)
+    with torch.no_grad():
+        ref = O.generator(sds[2], O.encoder_con(sds[0], c[row:row + 1]), O.encoder_col(sds[1], s[row:row + 1])[0],
+                          noises=noises1)
+    p = _psnr(one.cpu(), ref)
+    print("plain swap 1024^2 batch 16, row %d vs oracle: %.1f dB" % (row, p))
+    assert p >= 45.0, p

@@ -80,7 +80,7 @@ def test_reference_layers_run_on_the_plugin(ref_layers, case):
         "conv_down_reflect": lambda L: L.ConvLayer(16, 32, 3, downsample=True, blur_kernel=[1, 2, 1], reflection_pad=True),
         "conv_down_zero": lambda L: L.ConvLayer(16, 32, 3, downsample=True),
         "conv_act": lambda L: L.ConvLayer(3, 32, 1),
-        "resblock_reflect": lambda L: L.ResBlock(32, 64, [1, 2, 1], reflection_pad=True, pad=1, downsample=True),
+        "resblock_reflect": lambda L: L.ResBlock(32, 64, [1, 2, 1], reflection_pad=True, norm="in"),      # encoder_con.py:38
         "resblock_d": lambda L: L.ResBlock(32, 64, [1, 3, 3, 1]),
     }[case]
     cin = 3 if case == "conv_act" else (16 if case.startswith("conv") else 32)
@@ -89,7 +89,7 @@ def test_reference_layers_run_on_the_plugin(ref_layers, case):
     torch.backends.cuda.matmul.allow_tf32 = False
 
     def run(m, dev):
-        xin = x.to(dev).requires_grad_(True)
+        xin = x.detach().clone().to(dev).requires_grad_(True)
         y = m(xin)
         go = torch.randn(y.shape, generator=torch.Generator().manual_seed(2)).to(dev)
         y.backward(go)
@@ -112,15 +112,16 @@ def test_reference_discriminator_with_r1_double_backward_on_the_plugin(ref_layer
     x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(3))
 
     def run(m, dev):
-        xin = x.to(dev).requires_grad_(True)
+        xin = x.detach().clone().to(dev).requires_grad_(True)
         pred = m(xin)
         (g,) = torch.autograd.grad(pred.sum(), [xin], create_graph=True, retain_graph=True)
         r1 = g.pow(2).reshape(2, -1).sum(1).mean()
         r1.backward()
-        return pred.detach().cpu(), float(r1), {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+        return pred.detach().cpu(), float(r1.detach()), {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
     (p0, r0, g0), (p1, r1v, g1) = _both(L, plugin, lambda L: L.Discriminator(64, 2.0), run)
     assert _rel(p1, p0) <= 1e-4
     assert abs(r1v - r0) <= 1e-3 * abs(r0)
+    assert set(g0) == set(g1)
     worst = max(_rel(g1[k], g0[k]) for k in g0 if float(g0[k].norm()) > 0)
     assert worst <= 5e-3, worst
 
