@@ -408,12 +408,88 @@ def gen_rscl():
     print("rscl.npz", [float(store["loss/%d" % i]) for i in range(4)])
 
 
+def gen_stage2():
+    """Training stage 2 (the reference's default, ppst_model.py:24): PPSTModel.compute_generator_losses /
+    compute_discriminator_losses (ppst_model.py:105-137,158-236) of the UNMODIFIED reference on CPU at 512^2, batch 2 (the
+    only size its correlation path accepts), with lpips stubbed by mean |a - b| (oracle/ref_harness.py): every loss term, the
+    L2 norm of every parameter gradient of the G step (E1 / E2 / G) and of the D step, subsamples of a few of them, and the
+    region-contrast queues after the step."""
+    RH.install()
+    from models.ppst_model import PPSTModel
+    opt = RH.default_opt(isTrain=True, continue_train=False, num_gpus=0, lambda_R1=10.0, lambda_L1=3.0, lambda_GAN=1.0,
+                         training_stage=2, lambda_StyleCon=1.0, lambda_Maskwarp=10.0, lambda_Cycwarp=5.0, match_kernel=1,
+                         nce_T=0.07, netE1="StyleGAN2Resnet", netE2="StyleGAN2Resnet", netG="StyleGAN2Resnet",
+                         netD="StyleGAN2", crop_size=512, netD_scale_capacity=1.0, checkpoints_dir="/tmp", name="x")
+    m = PPSTModel(opt)
+    m.initialize()
+    sdE1, sdE2, sdG, sdD, real, mask, queues = O.stage2_inputs()
+    m.E1.load_state_dict(sdE1)
+    m.E2.load_state_dict(sdE2)
+    m.G.load_state_dict(sdG)
+    m.D.stylegan2_D.load_state_dict(sdD)
+    for i, q in enumerate(queues):
+        getattr(m.criterionNCE, "queue_data_A%d" % i).copy_(q)
+    store = {}
+    # ---- generator step
+    for p_ in m.D.parameters():
+        p_.requires_grad_(False)
+    losses, metrics = m.compute_generator_losses(real, None, None, mask)
+    total = sum(v.mean() for v in losses.values())
+    total.backward()
+    for k, v in losses.items():
+        store["G/" + k] = np.float64(v.mean().item())
+    store["G/total"] = np.float64(total.item())
+    for tag, net in (("E1", m.E1), ("E2", m.E2), ("G", m.G)):
+        names, norms = [], []
+        for k, p_ in net.named_parameters():
+            names.append(k)
+            norms.append(0.0 if p_.grad is None else float(p_.grad.double().norm()))
+        store["Ggrad/%s/names" % tag] = np.array(names)
+        store["Ggrad/%s/norms" % tag] = np.array(norms, dtype=np.float64)
+    pick = {"E1": ["FromRGB.Conv.weight", "DownToSpatialCode.ResBlockDownBy4.conv2.Conv.weight", "ToSpatialCode.1.Conv.weight"],
+            "E2": ["FromRGB.Conv.weight", "DownToGlobalCode1.ResBlockDownBy1.conv1.Conv.weight", "conv1x1_9.weight",
+                   "projector2.5.weight"],
+            "G": ["HeadResnetBlock0.conv1.conv.weight", "UpsamplingResBlock64.conv2.conv.weight", "layer32.2.weight",
+                  "layer256.6.weight", "layert.2.conv2.weight", "layert1.1.weight", "ToRGB.conv.weight",
+                  "UpsamplingResBlock16.conv1.epi1.style_mod.lin.weight"]}
+    for tag, net in (("E1", m.E1), ("E2", m.E2), ("G", m.G)):
+        params = dict(net.named_parameters())
+        for k in pick[tag]:
+            summarize(store, "Ggrad/%s/sample/%s" % (tag, k), params[k].grad)
+    for i in range(4):
+        qd = getattr(m.criterionNCE, "queue_data_A%d" % i)
+        store["queue_head/%d" % i] = qd[:, :8].numpy().copy()
+        store["queue_ptr/%d" % i] = np.int64(int(getattr(m.criterionNCE, "queue_ptr_A%d" % i)))
+    # ---- discriminator step (fresh queues do not matter here)
+    for net in (m.E1, m.E2, m.G):
+        net.zero_grad()
+        for p_ in net.parameters():
+            p_.requires_grad_(False)
+    for p_ in m.D.parameters():
+        p_.requires_grad_(True)
+    d_losses, _, _, _ = m.compute_discriminator_losses(real, mask)
+    d_total = sum(v.mean() for v in d_losses.values())
+    d_total.backward()
+    for k, v in d_losses.items():
+        store["D/" + k] = np.float64(v.mean().item())
+    names, norms = [], []
+    for k, p_ in m.D.stylegan2_D.named_parameters():
+        names.append(k)
+        norms.append(0.0 if p_.grad is None else float(p_.grad.double().norm()))
+    store["Dgrad/names"] = np.array(names)
+    store["Dgrad/norms"] = np.array(norms, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "stage2.npz"), **store)
+    print("stage2.npz", {k: float(v) for k, v in store.items() if k.startswith(("G/", "D/"))})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["ops", "layers", "function", "nets", "discriminator", "rscl"]
     if "rscl" in which:
         gen_rscl()
+    if "stage2" in which:
+        gen_stage2()
     if "discriminator" in which:
         gen_discriminator()
     if "ops" in which:

@@ -272,7 +272,8 @@ def encoder_col(sd, x, corrmatrix=None, mask=None, taps=None):
         vectors.append(_gap_gmp_head(sd, level, x))
         if corrmatrix is not None:
             sf = 2 ** (3 - li)                      # 8, 4, 2, (1: resize=False)
-            xx = e2_warp(x, corrmatrix, resize=(li < 3), scale_factor=sf)
+            # encoder_col.py:168 warps the first level with the live matrix, :196 the others with corrmatrix.detach()
+            xx = e2_warp(x, corrmatrix if li == 0 else corrmatrix.detach(), resize=(li < 3), scale_factor=sf)
             vectors_w.append(_gap_gmp_head(sd, level, xx))
         if mask is not None:
             if li > 0:
@@ -344,7 +345,7 @@ def generator(sd, sp, codes, extract_features=False, noises=None, taps=None):
     feas = []
     if extract_features:
         pool_hw = x.shape[2:]
-        feas.append(feature_head(sd, "layer32.", x, 3))
+        feas.append(feature_head(sd, "layer32.", x.detach(), 3))          # generator.py:257: the heads see x.detach()
     for j, (res, cin, cout) in enumerate(UP_CH):
         p = "UpsamplingResBlock%d." % res
         g = codes[-2 - j]
@@ -356,7 +357,7 @@ def generator(sd, sp, codes, extract_features=False, noises=None, taps=None):
         if taps is not None:
             taps[p[:-1]] = x
         if extract_features:
-            feas.append(feature_head(sd, "layer%d." % (2 ** (j + 6)), x, 3 if j < 2 else 1))
+            feas.append(feature_head(sd, "layer%d." % (2 ** (j + 6)), x.detach(), 3 if j < 2 else 1))
     rgb = to_rgb(sd, "ToRGB.", x, codes[0])
     if not extract_features:
         return rgb
@@ -571,6 +572,102 @@ def r1_loss(sd, real, lambda_r1=10.0):
     pred = discriminator(sd, real).sum()
     grad_real, = torch.autograd.grad(outputs=pred, inputs=[real], create_graph=True, retain_graph=True)
     return grad_real.pow(2).sum(dim=(1, 2, 3)) * (lambda_r1 * 0.5)
+
+
+# training stage 2 (the reference's default, models/ppst_model.py:24): correlation-warped mix, cycle warp, mask warp, region
+# style contrast.  LPIPS (lpips.LPIPS(net='alex'), ppst_model.py:48,178) needs downloaded weights: like the reference-run
+# fixture (oracle/ref_harness.py's stub) it is replaced by mean |a - b| on BOTH sides.
+def _lpips_stub(a, b):
+    return (a - b).abs().mean()
+
+
+def stage2_inputs():
+    """Seeded inputs of the stage-2 fixture (tests/golden/stage2.npz): networks with the NoiseInjection weights zeroed (the
+    reference draws fresh noise per call; zero weights make the step deterministic), D at 512 (un-prefixed keys), two
+    smooth portraits, blocky label maps -> one-hot masks, deterministic rscl queues."""
+    from oracle import rscl_oracle as R
+    sdE1, sdE2, sdG = make_networks(0)
+    for k in sdG:
+        if k.endswith("noise.weight"):
+            sdG[k] = torch.zeros_like(sdG[k])
+    sdD = make_discriminator(512, seed=0, prefix="")
+    real = make_portraits(2, 512, 512, seed=77, smooth=True)
+    lab = make_label_map(2, 512, 512, seed=78)
+    mask = torch.stack([torch.tensor(mask_labels(lab[b].numpy()), dtype=torch.float) for b in range(2)])
+    queues = [R.make_queue(i) for i in range(4)]
+    return sdE1, sdE2, sdG, sdD, real, mask, queues
+
+
+def stage2_features(sdG, sp, gl, noises=None):
+    """ppst_model.py:164-166 / 118-120: sps = cat(feas, Rselfcorr(feas1)) of G(sp, gl, extract_features=True)."""
+    _, feas, feas1 = generator(sdG, sp, gl, extract_features=True, noises=noises)
+    return torch.cat((feas, rselfcorr(feas1)), dim=1)
+
+
+def stage2_generator_losses(sdE1, sdE2, sdG, sdD, real, mask, queues, lam=None, nce_T=0.07, noises=None):
+    """PPSTModel.compute_generator_losses with training_stage == 2 (ppst_model.py:158-236).  mask: one-hot f32 [B,3,H,W];
+    queues: the four rscl memories [2048, 128] (networks/rscl.py:26-40).  Returns (losses dict, enqueue list): the keys the
+    reference then pushes into the queues, in its order (ppst_model.py:213-218)."""
+    from oracle import rscl_oracle as R
+    lam = dict({"L1": 3.0, "GAN": 1.0, "StyleCon": 1.0, "Maskwarp": 10.0, "Cycwarp": 5.0}, **(lam or {}))
+    losses = {}
+    B = real.shape[0]
+    sp = encoder_con(sdE1, real)
+    gl, _ = encoder_col(sdE2, real)
+    sps = stage2_features(sdG, sp, gl, noises)
+    corr = corrm(sps, _swap_pairs(sps))
+    corr_self = corrm(sps, sps)
+    _, gl = encoder_col(sdE2, real, corrmatrix=corr_self)
+    _, pro_ms, gl_w, pro_mw = encoder_col(sdE2, real, corrmatrix=corr, mask=mask)
+    image_warp = model_warp(real, corr)
+    image_rec = model_warp(image_warp, _swap_pairs(corr))
+    losses["image_warp_reg"] = _lpips_stub(image_rec, real) * lam["Cycwarp"]
+    losses["Mask_warp"] = (model_warp(mask, corr) - _swap_pairs(mask)).abs().mean() * lam["Maskwarp"]
+    rec = generator(sdG, sp, gl, noises=noises)
+    losses["G_L1"] = (rec - real).abs().mean() * lam["L1"]
+    mix = generator(sdG, _swap_pairs(sp), gl_w, noises=noises)
+    _, pro_3m, _, _ = encoder_col(sdE2, mix, mask=_swap_pairs(mask))
+    _, pro_2m, _, _ = encoder_col(sdE2, rec, mask=mask)
+    sp_3 = encoder_con(sdE1, mix)
+    half_noises = None if noises is None else {k: v[:B // 2] for k, v in noises.items()}
+    cyc = generator(sdG, _swap_pairs(sp_3)[:B // 2], [g[:B // 2] for g in gl], noises=half_noises)
+    losses["G_L1_cyc"] = (cyc - real[:B // 2]).abs().mean() * 3
+    style1 = style2 = 0.0
+    pushes = []
+    for lvl in range(4):
+        key0 = torch.cat(pro_ms[3 * lvl:3 * lvl + 3], dim=0)
+        keyw = torch.cat(pro_mw[3 * lvl:3 * lvl + 3], dim=0)
+        query = torch.cat(pro_3m[3 * lvl:3 * lvl + 3], dim=0)
+        query_r = torch.cat(pro_2m[3 * lvl:3 * lvl + 3], dim=0)
+        # the queue of level `lvl` is read BEFORE this level's keys are pushed (ppst_model.py:211-218)
+        style1 = style1 + R.rscl_loss(query, keyw.detach(), queues[lvl], key0.detach(), nce_T)
+        style2 = style2 + R.rscl_loss(query_r, key0.detach(), queues[lvl], keyw.detach(), nce_T)
+        pushes.append((lvl, [key0[i:i + 1].detach() for i in range(3)] + [keyw[i:i + 1].detach() for i in range(3)]))
+    losses["G_styleContmix"] = style1 * lam["StyleCon"]
+    losses["G_styleContrec"] = style2 * lam["StyleCon"]
+    losses["G_GAN_rec"] = gan_loss(discriminator(sdD, rec), True) * (lam["GAN"] * 0.5)
+    losses["G_GAN_mix"] = gan_loss(discriminator(sdD, mix), True) * (lam["GAN"] * 1.0)
+    return losses, pushes
+
+
+def stage2_discriminator_losses(sdE1, sdE2, sdG, sdD, real, lam_gan=1.0, noises=None):
+    """PPSTModel.compute_discriminator_losses with training_stage == 2 (ppst_model.py:105-137, 68-92); the caller runs it
+    under torch.no_grad() for E1 / E2 / G exactly like the reference's optimizer does (the fakes are detached here)."""
+    B = real.shape[0]
+    with torch.no_grad():
+        sp = encoder_con(sdE1, real)
+        gl, _ = encoder_col(sdE2, real)
+        sps = stage2_features(sdG, sp, gl, noises)
+        corr = corrm(sps, _swap_pairs(sps))
+        corr_self = corrm(sps, sps)
+        _, gl_w = encoder_col(sdE2, real, corrmatrix=corr)
+        mix = generator(sdG, _swap_pairs(sp), gl_w, noises=noises)
+        _, gl = encoder_col(sdE2, real, corrmatrix=corr_self)
+        half_noises = None if noises is None else {k: v[:B // 2] for k, v in noises.items()}
+        rec = generator(sdG, sp[:B // 2], [g[:B // 2] for g in gl], noises=half_noises)
+    return {"D_real": gan_loss(discriminator(sdD, real), True) * lam_gan,
+            "D_rec": gan_loss(discriminator(sdD, rec), False) * (0.5 * lam_gan),
+            "D_mix": gan_loss(discriminator(sdD, mix), False) * (0.5 * lam_gan)}
 
 
 def _q(t):

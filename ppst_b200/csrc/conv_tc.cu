@@ -611,7 +611,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // A and B travel through separate rings (A slots live for kh taps, B slots for one tap or one kernel column).
 // K order: channel block, kernel column, kernel row -- fixed, so results do not depend on batch or grid.
 // =====================================================================================================================
-constexpr int kMaxA = 4, kMaxB = 8;
+constexpr int kMaxA = 8, kMaxB = 8;
 
 template <int BN, int MT>
 struct HaloSmem {
@@ -763,6 +763,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int ety = row / p.tw, etx = row - ety * p.tw;
     float* s_bias_g = s_bias + group * kBiasSmem;
     const int fh_pad = p.full_h + 2 * p.out_pad - p.out_pad_trim, fw_pad = p.full_w + 2 * p.out_pad - p.out_pad_trim;
+    // store-side rows of this lane (rows 8i + lane/4 of the warp's 32): tile-invariant, so the divisions happen once
+    int s_y[4], s_x[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int srow = q * 32 + 8 * i + (lane >> 2);
+      s_y[i] = srow / p.tw;
+      s_x[i] = srow - s_y[i] * p.tw;
+    }
     int it = 0, cur_img = -1;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != group) continue;
@@ -791,9 +799,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t svalid = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int srow = q * 32 + 8 * i + (lane >> 2);
-          const int sy = srow / p.tw, sx = srow - sy * p.tw;
-          const int soy = ty * p.th + sy, sox = tx * p.tw + sx;
+          const int soy = ty * p.th + s_y[i], sox = tx * p.tw + s_x[i];
           if (soy < p.out_h && sox < p.out_w) svalid |= 1u << i;
           const int64_t spix = ((int64_t)img * fh_pad + (soy * p.phases_y + py) + p.out_pad) * fw_pad + (sox * p.phases_x + px) + p.out_pad;
           soff[i] = spix * p.cout_stride + p.c_off + nt * BN + 8 * (lane & 3);
@@ -1421,6 +1427,13 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   const int b_slot = p.bps * kBBytes;
   const int avail = S::kMaxDynamic - S::kFixedBytes;
   p.na = p.a_slot_bytes <= 24576 ? 4 : 3;
+  if (BN <= 64) {
+    // thin layers are bound by the latency of the A loads, not by bandwidth (ncu: DRAM 22 %, L2 27 %, tensor 15 % at
+    // 8 x 512^2 x 32 -> 32): give the A ring most of the shared memory, several tiles' worth of boxes in flight
+    static const int env_na = [] { const char* e = getenv("PPST_CONV_TC_NA"); return e ? atoi(e) : 8; }();
+    p.na = env_na < 2 ? 2 : (env_na > kMaxA ? kMaxA : env_na);
+    while (p.na > 2 && p.na * p.a_slot_bytes > (avail * 3) / 4) --p.na;
+  }
   while (p.na > 2 && avail - p.na * p.a_slot_bytes < 3 * b_slot) --p.na;
   p.nb = (avail - p.na * p.a_slot_bytes) / b_slot;
   if (p.nb > kMaxB) p.nb = kMaxB;
@@ -1552,8 +1565,10 @@ static int halo_mode(const ppst_conv_desc& d, int bn) {
   pick_tile(d.out_h, d.out_w, th, tw);
   if (tw < 8 || tw * th != BM) return 0;       // tap row offsets must be whole swizzle atoms
   if (bn > 128) return 1;
-  if (env_mt == 1 || env_mt == 2) return env_mt;
+  if (env_mt == 1 || env_mt == 2 || (env_mt == 4 && bn <= 64)) return env_mt;
   const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * ceil_div(d.out_w, tw) * d.phases_y * d.phases_x * (d.cout / bn);
+  static const int env_mt4 = [] { const char* e = getenv("PPST_CONV_TC_MT4"); return e ? atoi(e) : 1; }();
+  if (env_mt4 && bn <= 64 && ceil_div(d.out_h, th) >= 4 && tiles >= 16LL * num_sms()) return 4;   // 512-pixel super-tiles
   return (ceil_div(d.out_h, th) >= 2 && tiles >= 4LL * num_sms()) ? 2 : 1;
 }
 
@@ -1684,7 +1699,9 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
         return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, (BN_ == 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
       return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, 1>(d, out, in, weight, bias, noise, stats, st); \
     }                                                                                        \
-    if (hm == 2 && BN_ <= 128)                                                               \
+    if (hm == 4 && BN_ <= 64)                                                                \
+      return tc::launch_halo<BN_, BKC_, (BN_ <= 64 ? 4 : 1)>(d, out, in, weight, bias, noise, stats, st); \
+    if (hm >= 2 && BN_ <= 128)                                                               \
       return tc::launch_halo<BN_, BKC_, (BN_ <= 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
     if (hm >= 1) return tc::launch_halo<BN_, BKC_, 1>(d, out, in, weight, bias, noise, stats, st);         \
     if (d.out_dtype == PPST_F32)                                                             \

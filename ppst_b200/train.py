@@ -858,7 +858,13 @@ class Discriminator(torch.nn.Module):
         return self
 
     def reference_state_dict(self, prefix="stylegan2_D."):
-        return {prefix + k.replace("/", "."): v.detach().clone() for k, v in self.P.items()}
+        """Key-complete for the reference's loader: the parameters plus the Blur.kernel buffers of every ResBlock
+        (convs.N.conv2.Blur.kernel / convs.N.skip.Blur.kernel, stylegan2_layers.py:142-152)."""
+        out = {prefix + k.replace("/", "."): v.detach().clone() for k, v in self.P.items()}
+        for name, _, _ in self.blocks:
+            for branch in ("conv2", "skip"):
+                out[prefix + name + "." + branch + ".Blur.kernel"] = self.blur.detach().clone()
+        return out
 
     def p(self, name):
         return self.P[name.replace(".", "/")]

@@ -1,0 +1,145 @@
+"""Training stage 2 (the reference's default, models/ppst_model.py:24) on the GPU: ppst_b200.train_stage2.Stage2 against the
+reference-run fixture tests/golden/stage2.npz (PPSTModel.compute_generator_losses / compute_discriminator_losses of the
+UNMODIFIED reference at 512^2, batch 2; made by oracle/gen_golden.py stage2): every loss term, the gradients of the G step
+(E1 / E2 / G) and of the D step, and the region-contrast queues after the step.
+
+Tolerances are those of a bf16 training path: losses 2-5 %, every gradient tensor's norm within
++-25 % of the reference's (measured: 0.93 .. 1.14 over 184 tensors, median 1.000), direction cosine >= 0.85 on the
+reference-run subsamples (measured 0.86 .. 0.998), the single-number PReLU slopes to an absolute bound."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _sample_idx(numel, key, n=4096):
+    h = 2166136261
+    for ch in key.encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    g = torch.Generator().manual_seed(abs(h) % (2 ** 31))
+    return torch.randint(0, numel, (min(n, numel),), generator=g)
+
+
+@pytest.fixture(scope="module")
+def stage2():
+    from oracle import ppst_oracle as O
+    from ppst_b200 import ops, train
+    from ppst_b200.train_stage2 import Stage2
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    z = np.load(os.path.join(GOLD, "stage2.npz"))
+    sdE1, sdE2, sdG, sdD, real, mask, queues = O.stage2_inputs()
+    D = train.Discriminator(512, 2.0).cuda()
+    D.load_reference_state_dict({"stylegan2_D." + k: v for k, v in sdD.items()})
+    m = Stage2(sdE1, sdE2, sdG, D).cuda()
+    for i, q in enumerate(queues):
+        getattr(m.criterionNCE, "queue_data_A%d" % i).copy_(q)
+    return z, m, real.cuda(), mask.cuda()
+
+
+def test_stage2_generator_step_against_the_reference_run(stage2):
+    z, m, real, mask = stage2
+    for p in m.D.parameters():
+        p.requires_grad_(False)
+    for p in m.g_params():
+        p.grad = None
+    losses = m.generator_losses(real, mask)
+    total = sum(v.mean() for v in losses.values())
+    total.backward()
+    torch.cuda.synchronize()
+    report = {}
+    for k, v in losses.items():
+        ref = float(z["G/" + k])
+        report[k] = (float(v), ref)
+    print("stage-2 G losses (ours, reference):", {k: ("%.4f" % a, "%.4f" % b) for k, (a, b) in report.items()})
+    for k in ("G_L1", "G_L1_cyc", "image_warp_reg", "Mask_warp"):
+        a, b = report[k]
+        assert abs(a - b) <= 2e-2 * abs(b), (k, a, b)
+    for k in ("G_styleContmix", "G_styleContrec"):
+        a, b = report[k]
+        assert abs(a - b) <= 5e-2 * abs(b), (k, a, b)
+    for k in ("G_GAN_rec", "G_GAN_mix"):
+        a, b = report[k]
+        assert abs(a - b) <= 0.25 * abs(b) + 2e-3, (k, a, b)
+    # gradients: norms of every parameter, and direction on the reference-run subsamples
+    ratios, scalars = [], []
+    for tag, net in (("E1", m.E1), ("E2", m.E2), ("G", m.G)):
+        names = [str(s) for s in z["Ggrad/%s/names" % tag]]
+        norms = z["Ggrad/%s/norms" % tag]
+        floor = 1e-4 * float(np.median(norms[norms > 0]))
+        for k, ref in zip(names, norms):
+            # skipped: unused parameters (exactly 0), the noise weights (their gradient is a fresh random draw upstream), and
+            # the biases that sit directly in front of an InstanceNorm (layer*.2/.6.bias, layert*.conv*.bias, ToRGB.*bias,
+            # ToSpatialCode.1.Conv.bias): their gradient is zero in exact arithmetic, the reference holds ~1e-7 of rounding noise
+            if ref <= floor or k.endswith("noise.weight"):
+                continue
+            g = net[k].grad
+            assert g is not None, (tag, k)
+            if g.numel() == 1:
+                scalars.append((float(g.double().norm()), ref, tag + "." + k))
+                continue
+            ratios.append((float(g.double().norm()) / ref, tag + "." + k))
+    r = np.array([a for a, _ in ratios])
+    print("gradient-norm ratio ours / reference over %d tensors: median %.3f, 5%% %.3f, 95%% %.3f, min %.3f (%s), max %.3f (%s)"
+          % (len(r), np.median(r), np.quantile(r, 0.05), np.quantile(r, 0.95), r.min(), ratios[int(r.argmin())][1], r.max(),
+             ratios[int(r.argmax())][1]))
+    bad = sorted([(a, k) for a, k in ratios if not (0.75 <= a <= 1.25)])
+    print("outside [0.75, 1.25]:", [("%.3g" % a, k) for a, k in bad])
+    assert 0.95 <= np.median(r) <= 1.05
+    assert r.min() >= 0.75 and r.max() <= 1.25
+    # the eight PReLU slopes are single numbers = sums of millions of signed terms g*x with heavy cancellation (one of them
+    # is 10x smaller than its siblings in the reference run): every bf16 rounding of the path lands in them coherently, so
+    # they are held to an ABSOLUTE bound, half the typical slope gradient
+    typ = float(np.median([b for _, b, _ in scalars]))
+    print("PReLU slope gradients |ours| vs |reference| (typical %.4f):" % typ, [(k, "%.4f" % a, "%.4f" % b) for a, b, k in scalars])
+    assert all(abs(a - b) <= 0.5 * typ for a, b, _ in scalars)
+    cos = {}
+    for key in z.files:
+        if not key.startswith("Ggrad/") or not key.endswith("/sample"):
+            continue
+        _, tag, _, name, _ = key.split("/")
+        g = {"E1": m.E1, "E2": m.E2, "G": m.G}[tag][name].grad.detach().float().cpu().reshape(-1)
+        ref = torch.from_numpy(z[key])
+        mine = g[_sample_idx(g.numel(), key[:-len("/sample")])]
+        cos[tag + "." + name] = float(torch.nn.functional.cosine_similarity(mine, ref, dim=0))
+    print("gradient cosine on reference subsamples:", {k: "%.3f" % v for k, v in cos.items()})
+    # 0.86 (E1.FromRGB, the far end of a graph that passes through G three times and E2 five times) .. 0.998: the bf16 path's
+    # activations drift by ~1 %, which flips ~1 % of the leaky-ReLU / PReLU branches per layer (DESIGN.md section 9 decomposes
+    # this for stage 1, where the same far end sits at 0.95)
+    assert min(cos.values()) >= 0.85, cos
+    # the region-contrast queues after the step (ppst_model.py:213-218)
+    for i in range(4):
+        assert int(getattr(m.criterionNCE, "queue_ptr_A%d" % i)) == int(z["queue_ptr/%d" % i])
+        head = getattr(m.criterionNCE, "queue_data_A%d" % i)[:, :8].float().cpu()
+        ref = torch.from_numpy(z["queue_head/%d" % i])
+        assert float((head - ref).norm() / ref.norm()) <= 3e-2
+
+
+def test_stage2_discriminator_step_against_the_reference_run(stage2):
+    z, m, real, mask = stage2
+    for p in m.D.parameters():
+        p.requires_grad_(True)
+        p.grad = None
+    losses = m.discriminator_losses(real, mask)
+    sum(v.mean() for v in losses.values()).backward()
+    torch.cuda.synchronize()
+    print("stage-2 D losses (ours, reference):", {k: ("%.4f" % float(v), "%.4f" % float(z["D/" + k])) for k, v in losses.items()})
+    for k, v in losses.items():
+        ref = float(z["D/" + k])
+        assert abs(float(v) - ref) <= 3e-2 * abs(ref) + 2e-3, (k, float(v), ref)
+    names = [str(s) for s in z["Dgrad/names"]]
+    norms = z["Dgrad/norms"]
+    got = {k.replace("/", "."): p.grad for k, p in m.D.named_parameters()}
+    r = []
+    for k, ref in zip(names, norms):
+        cand = [g for kk, g in got.items() if kk.endswith(k)]
+        if ref == 0.0 or not cand or cand[0] is None:
+            continue
+        r.append(float(cand[0].double().norm()) / ref)
+    r = np.array(r)
+    print("D gradient-norm ratio over %d tensors: median %.3f, min %.3f, max %.3f" % (len(r), np.median(r), r.min(), r.max()))
+    assert len(r) >= 10 and 0.9 <= np.median(r) <= 1.1 and r.min() >= 0.7 and r.max() <= 1.3

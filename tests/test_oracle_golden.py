@@ -271,3 +271,29 @@ def test_discriminator_forward_losses_and_gradients(golden):
             continue
         scale = float(g["r1_grad/%s/stats" % k][2])
         check_summary(g, "r1_grad/" + k, grad, atol=1e-3 * scale + 1e-12)
+
+
+def test_stage2_losses_match_the_reference_run(golden):
+    """Training stage 2 (ppst_model.py:105-137,158-236): every term of the generator and discriminator losses of the
+    oracle's restatement against tests/golden/stage2.npz (PPSTModel.compute_generator_losses / compute_discriminator_losses
+    of the unmodified reference at 512^2, batch 2, lpips stubbed on both sides).  Forward only (about 80 s of CPU)."""
+    z = golden("stage2")
+    sdE1, sdE2, sdG, sdD, real, mask, queues = O.stage2_inputs()
+    sdDp = {"stylegan2_D." + k: v for k, v in sdD.items()}
+    with torch.no_grad():
+        losses, pushes = O.stage2_generator_losses(sdE1, sdE2, sdG, sdDp, real, mask, queues)
+        d = O.stage2_discriminator_losses(sdE1, sdE2, sdG, sdDp, real)
+    for k, v in losses.items():
+        ref = float(z["G/" + k])
+        assert abs(float(v) - ref) <= 1e-4 * max(abs(ref), 1e-2), (k, float(v), ref)
+    for k, v in d.items():
+        ref = float(z["D/" + k])
+        assert abs(float(v) - ref) <= 1e-4 * max(abs(ref), 1e-2), (k, float(v), ref)
+    # the keys pushed into the region-contrast queues: level l's first key lands in column 0 of queue l
+    from oracle import rscl_oracle as R
+    for lvl, keys in pushes:
+        q, ptr = queues[lvl], 0
+        for kk in keys:
+            q, ptr = R.enqueue(q, ptr, kk)
+        assert ptr == int(z["queue_ptr/%d" % lvl])
+        assert float((q[:, :8] - torch.from_numpy(z["queue_head/%d" % lvl])).abs().max()) <= 1e-5
