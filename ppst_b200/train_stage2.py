@@ -15,7 +15,7 @@ train.py; replicate padding, PReLU, the bilinear / average resamplings of the 64
 of the 3-channel image warp and the [n, c]-sized arithmetic are ATen glue (activation-sized ones on channels-last views).
 
 LPIPS (lpips.LPIPS(net='alex'), ppst_model.py:48,178) needs weights that are not available offline: `lpips_fn` defaults to the
-same mean |a - b| stand-in the reference-run fixture uses (oracle/ref_harness.py), and can be replaced by the real module.
+same mean |a - b| stand-in the reference-run fixture was made with, and can be replaced by the real module.
 """
 import sys
 

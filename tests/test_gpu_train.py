@@ -235,8 +235,9 @@ def test_discriminator_r1_penalty_matches_reference_fixture(golden):
 def test_discriminator_state_dict_round_trip_and_determinism():
     D, sd = _make_d(256)
     out = D.reference_state_dict()
+    assert set(out) == set(sd)
     for k, v in out.items():
-        assert torch.equal(v.cpu(), sd[k]), k
+        assert torch.allclose(v.cpu(), sd[k], atol=1e-7) if "Blur" in k else torch.equal(v.cpu(), sd[k]), k
     x = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
     with torch.no_grad():
         a, b = D(x), D(x)
