@@ -142,6 +142,8 @@ def gen_layers():
     from models.networks import generator as GM
     store = {}
     g = torch.Generator().manual_seed(777)
+    torch.manual_seed(777)          # module constructors draw their initial weights from the global RNG (randomize_ scales
+                                    # by the initial std): seeded, so that regenerating the fixture is bit-reproducible
 
     def put(name, module, inputs, out):
         for k, v in module.state_dict().items():

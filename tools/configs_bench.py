@@ -10,6 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons during the timed regions)
 from ppst_b200 import synthetic as O  # noqa: E402  (seeded weights / inputs)
 import ppst_b200  # noqa: E402
 
@@ -29,6 +30,8 @@ def timed(fn, reps):
 
 m = ppst_b200.SwapModel(*O.make_networks(0), mode="bf16")
 which = sys.argv[1:] or ["c3", "c4"]
+sampler = ClockSampler(0)
+sampler.start()
 if "c3" in which:
     m.noises = O.make_noises(1, 512, 512)
     contents = O.make_portraits(16, 512, 512, seed=11).cuda()
@@ -45,7 +48,10 @@ if "c3" in which:
                       "ms_grid": ms_grid, "cells_per_s": 256 / ms_grid * 1e3,
                       "ms_grid_with_guided_filter": ms_smooth, "cells_per_s_with_guided_filter": 256 / ms_smooth * 1e3,
                       "ms_same_cells_as_independent_swaps": ms_pairs, "encoder_reuse_speedup": ms_pairs / ms_grid,
-                      "guided_filter_ms_per_16_images": gf, "dtype": "bf16", "n_gpus": 1}), flush=True)
+                      "guided_filter_ms_per_16_images": gf, "dtype": "bf16", "n_gpus": 1, "clocks": sampler.stop()}),
+          flush=True)
+    sampler = ClockSampler(0)
+    sampler.start()
 if "c4" in which:
     n = 16
     m.noises = O.make_noises(1, 1024, 1024)
@@ -55,7 +61,7 @@ if "c4" in which:
     flop = 2.130e12                                   # plain swap @1024^2, conv + GEMM 2*MAC per image
     print(json.dumps({"config": "C4 plain swap @1024^2, batch 16 (BASELINE configs[3]); eager launches", "batch": n,
                       "ms_per_batch": ms, "images_per_s": n / ms * 1e3, "tflops": n * flop / ms / 1e9,
-                      "dtype": "bf16", "n_gpus": 1}), flush=True)
+                      "dtype": "bf16", "n_gpus": 1, "clocks": sampler.stop()}), flush=True)
     from ppst_b200 import ops
     ops.PROFILE = {}
     m.plain_swap(c, s)

@@ -16,7 +16,13 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active" ,
+        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        # tcgen05 (UTC*MMA) tensor-pipe activity: the counters north_star asks for
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_uhmma.sum", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_bytes.sum", "launch__cluster_size",
         "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__cycles_active.avg",
         "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
