@@ -258,7 +258,10 @@ def run_train(args):
     tb = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(tb)
     a = types.SimpleNamespace(size=256, batch=8, steps=max(4, min(args.steps, 10)), no_torch=True, stage1=True, return_dict=True)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
     out = tb.stage1(a)
+    clocks = sampler.stop()
     if out is None:
         return
     line = {"metric": "training images/s @256^2 (stage 1: G step + D step + R1/16)", "value": out["images_per_s"],
@@ -270,7 +273,7 @@ def run_train(args):
             "e2e": {"value": out["e2e_images_per_s"], "unit": "images/s", "h2d_bytes_per_step": out["h2d_bytes_per_iteration"],
                     "d2h_bytes_per_step": out["d2h_bytes_per_iteration"], "ms_per_step": out["iteration_e2e_ms"]},
             "gpu_launches": out["launches_g_d_r1"] * a.steps, "step_ms": out["graph_ms"], "eager_step_ms": out["ms"],
-            "kernels": out["kernels_g_plus_d"]}
+            "clocks": clocks, "kernels": out["kernels_g_plus_d"]}
     # roofline of the dominant kernels: every tcgen05 launch of a G step + D step (forward / input-gradient convolutions =
     # ppst_conv_tc, weight gradients = ppst_conv_wgrad), CUDA events per launch in the eager profiling pass
     peaks = load_peaks()

@@ -84,11 +84,12 @@ def allreduce_grads_(params, world=None):
     if not grads:
         return 0
     flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
-    dist.all_reduce(flat)
-    flat.div_(world)
-    off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
-        off += n
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)          # the division rides in the collective
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world)
+    # scatter back with ONE multi-tensor copy instead of a launch per parameter (~250 per step)
+    pieces = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
+    torch._foreach_copy_(grads, pieces)
     return flat.numel() * 4

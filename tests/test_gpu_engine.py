@@ -373,3 +373,52 @@ def test_grid_evaluator_sequence_with_guided_filter_target(world, model_fp32):
     assert lv.max() <= 3.0 and lv.mean() <= 0.05, (float(lv.max()), float(lv.mean()))
     # every value is an exact uint8 level mapped back to [-1, 1]
     assert np.abs(np.rint((out.cpu().numpy() + 1) * 127.5) - (out.cpu().numpy() + 1) * 127.5).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_random_noise_mode_and_noise_routing_for_other_batch_sizes():
+    """(a) noises="random" draws fresh N(0,1) NoiseInjection maps per generator pass like the reference
+    (stylegan2_layers.py:376-399), reproducibly from noise_seed; (b) a noise dict set for batch B is repeated for passes over
+    another batch size in extract_feat / extract_feat_from_image as well (they used to pass the dict through unchanged)."""
+    import ppst_b200
+    from ppst_b200 import synthetic as S
+    sds = S.make_networks(0)                     # synthetic networks have non-zero noise weights
+    c = S.make_portraits(2, 256, 256, seed=3).cuda()
+    m1 = ppst_b200.SwapModel(*sds, mode="bf16", noise_seed=7)
+    m2 = ppst_b200.SwapModel(*sds, mode="bf16", noise_seed=7)
+    sp, gl = m1.encode(c)
+    a1, a2 = m1.decode(sp, gl), m1.decode(sp, gl)
+    b1 = m2.decode(*m2.encode(c))
+    assert not torch.equal(a1, a2)               # fresh noise on every pass
+    assert torch.equal(a1, b1)                   # same seed, same stream of draws
+    m1.noises = None
+    off = m1.decode(sp, gl)
+    assert not torch.equal(off, a1)
+    m3 = ppst_b200.SwapModel(*sds, mode="bf16")
+    m3.noises = S.make_noises(1, 256, 256, seed=5)          # batch-1 maps, passes over batch 2
+    f_a = m3.extract_feat_from_image(c)
+    f_b = [torch.cat([m3.extract_feat_from_image(c[i:i + 1])[k] for i in range(2)]) for k in range(2)]
+    assert all(torch.equal(x, y) for x, y in zip(f_a, f_b))
+
+
+@pytest.mark.gpu
+def test_model_on_a_non_current_device():
+    """SwapModel(device="cuda:1") while cuda:0 is current must run on cuda:1 (launches used to go to the current
+    device's stream with the other device's pointers); the raw operators refuse tensors of a non-current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import ppst_b200
+    from ppst_b200 import ops, synthetic as S
+    torch.cuda.set_device(0)
+    sds = S.make_networks(0)
+    c = S.make_portraits(1, 256, 256, seed=3)
+    s = S.make_portraits(1, 256, 256, seed=4, smooth=True)
+    m0 = ppst_b200.SwapModel(*sds, device="cuda:0", mode="bf16")
+    m1 = ppst_b200.SwapModel(*sds, device="cuda:1", mode="bf16")
+    assert torch.cuda.current_device() == 0
+    out0 = m0.plain_swap(c, s)
+    out1 = m1.plain_swap(c, s)
+    assert out1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(out0.cpu(), out1.cpu())
+    with pytest.raises(RuntimeError):
+        ops.l2_normalize(torch.randn(2, 8, device="cuda:1"), 1e-8, 0)
