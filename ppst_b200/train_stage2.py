@@ -371,7 +371,8 @@ class Stage2(torch.nn.Module):
             style1 = style1 + self.criterionNCE(query, keyw.detach(), key0.detach(), lvl)
             style2 = style2 + self.criterionNCE(query_r, key0.detach(), keyw.detach(), lvl)
             pushes += [(key0[i:i + 1].detach(), lvl) for i in range(3)] + [(keyw[i:i + 1].detach(), lvl) for i in range(3)]
-        if enqueue:
+        self.last_pushes = pushes                    # with enqueue=False (CUDA-graph capture: the queue pointers live on the
+        if enqueue:                                  # host) the caller runs criterionNCE.dequeue_and_enqueue_many(last_pushes)
             # the reference pushes level l's keys right after level l's losses (ppst_model.py:211-218); the levels' queues are
             # independent, so pushing all 24 keys afterwards in one collective leaves the same queues
             self.criterionNCE.dequeue_and_enqueue_many(pushes)
