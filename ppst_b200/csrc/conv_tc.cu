@@ -1582,7 +1582,8 @@ static bool pair_mode(const ppst_conv_desc& d, int bn) {
   pick_tile(d.out_h, d.out_w, th, tw);
   const int tiles_x = ceil_div(d.out_w, tw);
   const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * tiles_x * d.phases_y * d.phases_x * (d.cout / bn);
-  return tiles_x % 2 == 0 && tiles >= 2LL * num_sms();
+  static const int env_min = [] { const char* e = getenv("PPST_CONV_TC_PAIR_MIN"); return e ? atoi(e) : 2; }();
+  return tiles_x % 2 == 0 && tiles >= (int64_t)env_min * num_sms();
 }
 
 }  // namespace tc
