@@ -68,8 +68,7 @@ class SwapModel:
           dict      -- '<block>.conv{1,2}' -> [B,1,H,W] explicit maps (parity tests, reproducible outputs);
           "random"  -- what the reference does (its evaluators leave fix_noise commented out): fresh N(0,1) maps on every
                        generator pass, drawn on the device from a generator seeded by `noise_seed` (SwapModel(...,
-                       noise_seed=s)).  swap_graph / swap_pipelined capture the draws, so a replay re-uses the maps
-                       drawn at capture time's generator offsets (torch's graph-safe Philox state advances per replay)."""
+                       noise_seed=s)).  Eager API only: swap_graph / swap_pipelined replay a captured step and refuse it."""
         return self._noises
 
     @noises.setter
@@ -307,6 +306,9 @@ class SwapModel:
         key = (tuple(content.shape), tuple(style.shape), float(alpha))
         entry = self._graphs.get(key)
         if entry is None:
+            if isinstance(self._noises, str):
+                raise RuntimeError("swap_graph / swap_pipelined replay a captured step: use explicit noise maps or noises=None "
+                                   "(noises='random' draws fresh maps per call and belongs to the eager API)")
             c_static = torch.empty(tuple(content.shape), device=self.device, dtype=torch.float32)
             s_static = torch.empty(tuple(style.shape), device=self.device, dtype=torch.float32)
             c_static.copy_(content)
