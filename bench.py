@@ -373,6 +373,20 @@ def main():
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
+    # one replay at a time with the GPU idle in between: what a step costs before the 1 kW power cap pulls the SM clock
+    # down (the gap between the sum of kernel times of a single replay and the back-to-back step time is clocks, not idle gaps)
+    cool = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        time.sleep(0.3)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        step_device()
+        c1.record()
+        torch.cuda.synchronize()
+        cool.append(c0.elapsed_time(c1))
+    ms_single_replay = min(cool)
+
     # per-kernel roofline leg: the same steps with every launch bracketed by CUDA events
     ops.PROFILE = {}
     torch.cuda.synchronize()
@@ -454,6 +468,7 @@ def main():
                 "d2h_bytes_per_step": int(out_pin.numel() * 4), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "launch_mode": "CUDA graph replay of %d kernels per step (captured from the eager path)" % launches_per_step,
+        "ms_single_replay_after_idle": ms_single_replay,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "ppst_conv_tc (tcgen05 implicit-GEMM convolutions + the two split GEMMs: every "
                                                  "launch of one step)",
