@@ -202,10 +202,14 @@ __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
   }
 }
 
+// One WARP per output (n, region, channel): lane l sums chunks l, l + 32, ... left to right, then a fixed shuffle tree --
+// deterministic and independent of the batch; a single thread walking 128 chunks cost 16 us of pure latency.
 template <int R>
-__global__ void plane_reduce_nhwc_final(float* __restrict__ sum, float* __restrict__ sumsq, float* __restrict__ vmax,
-                                        const float* __restrict__ scratch, int64_t n, int64_t c, int chunks) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over n*R*c
+__global__ void __launch_bounds__(256) plane_reduce_nhwc_final(float* __restrict__ sum, float* __restrict__ sumsq,
+                                                               float* __restrict__ vmax, const float* __restrict__ scratch,
+                                                               int64_t n, int64_t c, int chunks) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // over n*R*c
   if (t >= n * R * c) return;
   const int64_t ch = t % c;
   const int r = (int)((t / c) % R);
@@ -213,18 +217,20 @@ __global__ void plane_reduce_nhwc_final(float* __restrict__ sum, float* __restri
   float a = 0.f, b = 0.f, mm = -FLT_MAX;
   const int64_t kstride = (int64_t)R * c * 3;
   const float* o = scratch + ((((int64_t)nidx * chunks) * R + r) * c + ch) * 3;
-  int k = 0;
-  for (; k + 4 <= chunks; k += 4) {                     // 12 independent loads in flight; same left-to-right sum order
-    float v[4][3];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { v[u][0] = o[(k + u) * kstride]; v[u][1] = o[(k + u) * kstride + 1]; v[u][2] = o[(k + u) * kstride + 2]; }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { a += v[u][0]; b += v[u][1]; mm = fmaxf(mm, v[u][2]); }
+  for (int k = lane; k < chunks; k += 32) {
+    a += o[k * kstride]; b += o[k * kstride + 1]; mm = fmaxf(mm, o[k * kstride + 2]);
   }
-  for (; k < chunks; ++k) { a += o[k * kstride]; b += o[k * kstride + 1]; mm = fmaxf(mm, o[k * kstride + 2]); }
-  if (sum) sum[t] = a;
-  if (sumsq) sumsq[t] = b;
-  if (vmax) vmax[t] = mm;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, off);
+    b += __shfl_xor_sync(0xffffffffu, b, off);
+    mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, off));
+  }
+  if (lane == 0) {
+    if (sum) sum[t] = a;
+    if (sumsq) sumsq[t] = b;
+    if (vmax) vmax[t] = mm;
+  }
 }
 
 template <typename T, int R>
@@ -280,7 +286,7 @@ static int launch_reduce(float* sum, float* sumsq, float* vmax, const T* x, cons
   }
   PPST_LAUNCH_CHECK("plane_reduce_nhwc_kernel");
   const int64_t tot = n * c * R;
-  plane_reduce_nhwc_final<R><<<ceil_div(tot, 256), 256, 0, st>>>(sum, sumsq, vmax, scratch, n, c, pl.chunks);
+  plane_reduce_nhwc_final<R><<<ceil_div(tot, 8), 256, 0, st>>>(sum, sumsq, vmax, scratch, n, c, pl.chunks);
   PPST_LAUNCH_CHECK("plane_reduce_nhwc_final");
   return 0;
 }
@@ -465,7 +471,7 @@ extern "C" int ppst_upsample_reduce(float* sum, float* vmax, const float* x, int
   const size_t smem = sizeof(float) * 2 * (size_t)lanes * c;
   upsample_reduce_kernel<<<dim3(rows, (unsigned)n), 256, smem, st>>>(scratch, x, lh, lw, c_stride, c_off, c, scale, rows);
   PPST_LAUNCH_CHECK("upsample_reduce_kernel");
-  plane_reduce_nhwc_final<1><<<ceil_div(n * c, 256), 256, 0, st>>>(sum, nullptr, vmax, scratch, n, c, rows);
+  plane_reduce_nhwc_final<1><<<ceil_div(n * c, 8), 256, 0, st>>>(sum, nullptr, vmax, scratch, n, c, rows);
   PPST_LAUNCH_CHECK("plane_reduce_nhwc_final");
   return 0;
 }
