@@ -143,3 +143,25 @@ def test_plain_swap_1024_batch16_rows_match_single_pair_and_oracle():
     p = _psnr(one.cpu(), ref)
     print("plain swap 1024^2 batch 16, row %d vs oracle: %.1f dB" % (row, p))
     assert p >= 45.0, p
+
+
+def test_swap_grid_5x6_with_guided_filter_matches_pairwise_swaps():
+    """BASELINE configs[2] beyond the 2 x 3 case of test_gpu_engine.py: a 5 x 6 grid with the evaluator's cell batching
+    (two full chunks of 12 and a ragged one of 6), with and without decode(target=content)'s guided-filter post-process; every
+    cell bit-identical to the pairwise call sequence of evaluation/content_style_grid_generation_evaluator.py:57-91."""
+    import ppst_b200
+    from ppst_b200 import ops, synthetic as S
+    sds = S.make_networks(0)
+    m = ppst_b200.SwapModel(*sds, mode="bf16")
+    if not m.engine.use_tc:
+        pytest.skip("tcgen05 path unavailable")
+    m.noises = S.make_noises(1, 512, 512, seed=4)
+    contents = S.make_portraits(5, 512, 512, seed=41, smooth=True).cuda()
+    styles = S.make_portraits(6, 512, 512, seed=42, smooth=True).cuda()
+    grid = m.swap_grid(contents, styles, cell_batch=12)
+    smooth = m.swap_grid(contents, styles, cell_batch=12, smooth=True)
+    assert grid.shape == smooth.shape == (5, 6, 3, 512, 512)
+    for i, j in ((0, 0), (1, 5), (2, 3), (4, 0), (4, 5), (3, 2)):
+        one = m.swap(contents[i:i + 1], styles[j:j + 1])
+        assert torch.equal(grid[i, j], one[0]), (i, j)
+        assert torch.equal(smooth[i, j], ops.guided_smooth(one, contents[i:i + 1])[0]), (i, j)
