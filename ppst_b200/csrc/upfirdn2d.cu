@@ -162,6 +162,212 @@ __global__ void __launch_bounds__(256, 5) upfirdn2d_bulk_kernel(T* __restrict__ 
   }
 }
 
+// ---- the same strip kernel for 16-bit element types (bf16 / fp16).  The fp32 form above issues one 16-bit LDS, one
+//      conversion and KS x KS FFMA per tap row and output: at half the bytes per element it is issue-bound at the same
+//      element rate as fp32 (0.34-0.50 of HBM).  Here one thread owns TWO adjacent columns x RR rows: a tap row of the
+//      window is KS + 1 elements = three aligned 32-bit shared-memory words (funnel-shifted by 16 bits when the row
+//      starts on an odd element: 2^n+3-wide rows alternate), the two columns' accumulators are one float2 and every tap is
+//      one packed FFMA2 (sm_100: fma.rn.f32x2), and the two results leave as one 32-bit store.  Per-column arithmetic and
+//      its order are those of the scalar kernel, so the results are bit-identical to it.
+template <typename T> struct Pack16;
+template <> struct Pack16<__nv_bfloat16> {
+  __device__ __forceinline__ static float2 unpack(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+  }
+  __device__ __forceinline__ static uint32_t pack(float2 v) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <> struct Pack16<__half> {
+  __device__ __forceinline__ static float2 unpack(uint32_t w) { return __half22float2(*reinterpret_cast<__half2*>(&w)); }
+  __device__ __forceinline__ static uint32_t pack(float2 v) {
+    __half2 h = __floats2half2_rn(v.x, v.y);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+// One column x RR rows with every tap predicated (window touches the image border / the strip's staged rows).
+template <typename T, int KS, int RR>
+__device__ __forceinline__ void upfirdn2d_border_item(T* __restrict__ q, const T* sp, const float (&k)[KS ? KS : 4][KS ? KS : 4],
+                                                      int kh, int kw, int xb, int yb, int iyA, int iyB, int in_w, int out_w,
+                                                      int nvalid) {
+  constexpr int KM = KS ? KS : 4;
+  float acc[RR];
+#pragma unroll
+  for (int o = 0; o < RR; ++o) acc[o] = 0.0f;
+  bool cok[KM];
+#pragma unroll
+  for (int kx = 0; kx < KM; ++kx) cok[kx] = kx < kw && xb + kx >= 0 && xb + kx < in_w;
+#pragma unroll
+  for (int r = 0; r < RR + KM - 1; ++r) {
+    const int y = yb + r;
+    const bool rok = r < RR + kh - 1 && y >= iyA && y < iyB;
+    float v[KM];
+#pragma unroll
+    for (int kx = 0; kx < KM; ++kx) v[kx] = (rok && cok[kx]) ? Cvt<T>::to_f(sp[r * in_w + kx]) : 0.0f;
+#pragma unroll
+    for (int o = 0; o < RR; ++o) {
+      const int ky = r - o;
+      if (ky >= 0 && ky < KM && (KS != 0 || ky < kh)) {
+#pragma unroll
+        for (int kx = 0; kx < KM; ++kx)
+          if (KS != 0 || kx < kw) acc[o] = fmaf(v[kx], k[ky][kx], acc[o]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < RR; ++o) {
+    if (o < nvalid) *q = Cvt<T>::from_f(acc[o]);
+    q += out_w;
+  }
+}
+
+template <typename T, int KS>
+__global__ void __launch_bounds__(256, 4) upfirdn2d_bulk16_kernel(T* __restrict__ out, const T* __restrict__ in,
+                                                                  const float* __restrict__ kernel, UpfirdnParams p,
+                                                                  int R, int nstrips) {
+  static_assert(sizeof(T) == 2, "16-bit element types only");
+  constexpr int RR = 8;                              // output rows per thread (vertical sliding window)
+  constexpr int KM = KS ? KS : 4;
+  constexpr int VEC = 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  T* sm = reinterpret_cast<T*>(smem_raw + 16);
+  const uint32_t* smw = reinterpret_cast<const uint32_t*>(smem_raw + 16);
+  const int tid = threadIdx.x;
+  const int strip = blockIdx.x % nstrips;
+  const int64_t plane = blockIdx.x / nstrips;
+  const int oy0 = strip * R;
+  const int rows = min(R, p.out_h - oy0);
+  const int kh = KS ? KS : p.kh, kw = KS ? KS : p.kw;
+  const int iyA = max(0, oy0 - p.py0), iyB = min(p.in_h, oy0 - p.py0 + rows + kh - 1);
+  const int64_t n = iyB > iyA ? (int64_t)(iyB - iyA) * p.in_w : 0;
+  const T* g = in + (plane * p.in_h + iyA) * (int64_t)p.in_w;
+  const int mis = (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) & (VEC - 1));
+  const int64_t head = n < ((VEC - mis) & (VEC - 1)) ? n : ((VEC - mis) & (VEC - 1));
+  const int64_t body = (n - head) / VEC * VEC;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (uint32_t)(body * sizeof(T)));
+    if (body) bulk_g2s(sm + mis + head, g + head, (uint32_t)(body * sizeof(T)), bar);
+  } else if (tid >= 32 && tid < 32 + 2 * VEC) {
+    const int j = tid - 32;
+    const int64_t i = j < VEC ? j : head + body + (j - VEC);
+    if (j < VEC ? i < head : i < n) sm[mis + i] = g[i];
+  }
+  float k[KM][KM];
+#pragma unroll
+  for (int ky = 0; ky < KM; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < KM; ++kx)
+      k[ky][kx] = (ky < kh && kx < kw) ? __ldg(kernel + (kh - 1 - ky) * kw + (kw - 1 - kx)) : 0.0f;
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  // Columns whose window stays inside the image horizontally form the pair loop: [cl, cl + 2 * cols2).  The few columns
+  // left of / right of it (zero padding, and the odd last column) are done one by one afterwards, so that no warp of the
+  // pair loop runs both the packed and the predicated code and the items divide evenly over the 256 threads.
+  const int cl = min(max(p.px0, 0), p.out_w);
+  const int cr = max(cl, min(p.out_w, p.in_w - kw + p.px0 + 1));
+  const int cols2 = (cr - cl) >> 1;                  // column pairs
+  const int nrg = (rows + RR - 1) / RR;
+  const int nitems = nrg * cols2;
+  T* dst = out + plane * (int64_t)p.out_h * p.out_w;
+  const bool rows_aligned = (reinterpret_cast<uintptr_t>(dst) & 3) == 0 && ((p.out_w | cl) & 1) == 0;
+  int rg = cols2 ? tid / cols2 : 0, cp = tid - rg * cols2;
+  for (int idx = tid; idx < nitems; idx += 256) {
+    const int c = cl + cp * 2;
+    const int oyb = oy0 + rg * RR;
+    const int xb = c - p.px0, yb = oyb - p.py0;
+    const int e = mis + (yb - iyA) * p.in_w + xb;    // element index of tap (0, 0) of the first output in sm
+    const int nvalid = p.out_h - oyb;
+    T* q = dst + (int64_t)oyb * p.out_w + c;
+    const bool interior = yb >= iyA && yb + RR + kh - 1 <= iyB;    // per row group: (almost) warp-uniform
+    if (interior) {
+      float2 acc[RR];
+#pragma unroll
+      for (int o = 0; o < RR; ++o) acc[o] = make_float2(0.0f, 0.0f);
+      // Row r of the window starts at element e + r * in_w: byte 2 * that, rounded down to a word, plus a 16-bit funnel
+      // shift when the element is odd.  With in_w odd the parity alternates, so even and odd rows are two address
+      // streams that both advance by 2 rows = 4 * in_w bytes (a whole number of words): one add per row.
+      const uint32_t par0 = e & 1, par1 = (e + p.in_w) & 1;
+      const uint32_t shv[2] = {par0 << 4, par1 << 4};
+      const unsigned char* rowp[2] = {reinterpret_cast<const unsigned char*>(sm) + 2 * (e - (int)par0),
+                                      reinterpret_cast<const unsigned char*>(sm) + 2 * (e + p.in_w - (int)par1)};
+      const int pitch2 = 4 * p.in_w;
+#pragma unroll
+      for (int r = 0; r < RR + KM - 1; ++r) {
+        if (KS == 0 && r >= RR + kh - 1) break;
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp[r & 1]);
+        rowp[r & 1] += pitch2;
+        const uint32_t sh = shv[r & 1];
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const float2 a = Pack16<T>::unpack(__funnelshift_r(w0, w1, sh));    // elements 0, 1 of the row's window
+        const float2 b = Pack16<T>::unpack(__funnelshift_r(w1, w2, sh));    // 2, 3
+        float2 v[4];
+        v[0] = a;
+        v[1] = make_float2(a.y, b.x);
+        v[2] = b;
+        if (KM == 4) v[3] = make_float2(b.y, Pack16<T>::unpack(w2 >> sh).x);  // 3, 4
+#pragma unroll
+        for (int o = 0; o < RR; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < KM && (KS != 0 || ky < kh)) {
+#pragma unroll
+            for (int kx = 0; kx < KM; ++kx)
+              if (KS != 0 || kx < kw) acc[o] = __ffma2_rn(v[kx], make_float2(k[ky][kx], k[ky][kx]), acc[o]);
+          }
+        }
+      }
+      if (nvalid >= RR) {
+        if (rows_aligned) {                          // every row starts on a 4-byte boundary: one store per pair
+#pragma unroll
+          for (int o = 0; o < RR; ++o) {
+            *reinterpret_cast<uint32_t*>(q) = Pack16<T>::pack(acc[o]);
+            q += p.out_w;
+          }
+        } else {                                     // odd widths (the 2^n+1 hot case): the alignment alternates
+#pragma unroll
+          for (int o = 0; o < RR; ++o) {
+            const uint32_t w = Pack16<T>::pack(acc[o]);
+            reinterpret_cast<unsigned short*>(q)[0] = (unsigned short)(w & 0xffffu);
+            reinterpret_cast<unsigned short*>(q)[1] = (unsigned short)(w >> 16);
+            q += p.out_w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int o = 0; o < RR; ++o) {
+          if (o < nvalid) {
+            const uint32_t w = Pack16<T>::pack(acc[o]);
+            reinterpret_cast<unsigned short*>(q)[0] = (unsigned short)(w & 0xffffu);
+            reinterpret_cast<unsigned short*>(q)[1] = (unsigned short)(w >> 16);
+          }
+          q += p.out_w;
+        }
+      }
+    } else {
+      const T* sp = sm + e;                          // only dereferenced where the predicates hold
+      upfirdn2d_border_item<T, KS, RR>(q, sp, k, kh, kw, xb, yb, iyA, iyB, p.in_w, p.out_w, nvalid);
+      upfirdn2d_border_item<T, KS, RR>(q + 1, sp + 1, k, kh, kw, xb + 1, yb, iyA, iyB, p.in_w, p.out_w, nvalid);
+    }
+    cp += 256;
+    while (cp >= cols2) { cp -= cols2; ++rg; }
+  }
+  // the columns outside the pair loop
+  const int cend = cl + 2 * cols2;
+  const int nleft = cl + (p.out_w - cend);
+  for (int idx = tid; idx < nleft * nrg; idx += 256) {
+    const int g2 = idx / nleft, j = idx - g2 * nleft;
+    const int c = j < cl ? j : cend + (j - cl);
+    const int oyb = oy0 + g2 * RR;
+    const int xb = c - p.px0, yb = oyb - p.py0;
+    upfirdn2d_border_item<T, KS, RR>(dst + (int64_t)oyb * p.out_w + c, sm + mis + (yb - iyA) * p.in_w + xb, k, kh, kw, xb, yb,
+                                     iyA, iyB, p.in_w, p.out_w, p.out_h - oyb);
+  }
+}
+
 // ---- register-staged variant of the up = down = 1 path for rows too long for the bulk-copy kernel above
 //      (strip x column-chunk tiles, fp32 tile in shared memory with the zero padding materialised).
 template <typename T, int KMAX>
@@ -363,10 +569,22 @@ static int launch_upfirdn2d(T* y, const T* x, const float* k, const UpfirdnParam
       rows = rows / 8 * 8;
       rows = rows < 8 ? 8 : (rows > 128 ? 128 : rows);
       rows = (ceil_div(p.out_h, ceil_div(p.out_h, rows)) + 7) / 8 * 8;   // balance the strips of a plane
-      const size_t smem = 16 + 16 + row_bytes * (size_t)(rows + p.kh - 1);
+      const size_t smem = 16 + 32 + row_bytes * (size_t)(rows + p.kh - 1);
       const int nstrips = ceil_div(p.out_h, rows);
       const int64_t blocks = p.major * nstrips;
       if (smem <= 100 * 1024 && blocks < (1LL << 31) && (int64_t)p.in_w * (rows + 8) < (1 << 24)) {
+        if constexpr (sizeof(T) == 2) {
+          if (p.in_w >= 8) {
+            auto kern16 = ks == 3 ? upfirdn2d_bulk16_kernel<T, 3> : ks == 4 ? upfirdn2d_bulk16_kernel<T, 4>
+                                                                          : upfirdn2d_bulk16_kernel<T, 0>;
+            int rc = cuda_check(cudaFuncSetAttribute(kern16, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+                                "upfirdn2d_bulk16_kernel attribute");
+            if (rc) return rc;
+            kern16<<<(unsigned)blocks, 256, smem, st>>>(y, x, k, p, rows, nstrips);
+            PPST_LAUNCH_CHECK("upfirdn2d_bulk16_kernel");
+            return 0;
+          }
+        }
         auto kern = ks == 3 ? upfirdn2d_bulk_kernel<T, 3> : ks == 4 ? upfirdn2d_bulk_kernel<T, 4>
                                                                   : upfirdn2d_bulk_kernel<T, 0>;
         int rc = cuda_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),

@@ -150,6 +150,38 @@ def test_upfirdn2d_strip_path_edge_cases():
         assert (got[fin] - want[fin]).abs().max() <= 1e-5
 
 
+def test_upfirdn2d_16bit_pair_kernel_is_bit_identical_to_the_fp32_kernel():
+    """bf16 / fp16 strips run two columns per thread on packed FFMA2 (upfirdn2d_bulk16_kernel); per column the fp32
+    arithmetic and its order are those of the fp32 kernel, so y16 == round16(fp32 kernel on the same 16-bit values),
+    exactly -- over odd / even widths, every tap shape up to 4x4, zero / cropping pads, ragged strips, tiny planes, Inf."""
+    from ppst_b200.stylegan2_op import upfirdn2d
+    cases = [((8, 4, 515, 515), (3, 3), (0, 0)), ((2, 8, 512, 512), (4, 4), (2, 2)), ((2, 3, 256, 256), (3, 3), (1, 0)),
+             ((2, 3, 259, 259), (4, 4), (2, 1)), ((1, 2, 131, 130), (4, 4), (1, 1)), ((1, 2, 37, 41), (3, 3), (-1, -2)),
+             ((1, 2, 37, 41), (2, 2), (5, 6)), ((1, 1, 70, 1027), (1, 4), (1, 2)), ((3, 1, 9, 9), (4, 3), (3, 3)),
+             ((1, 2, 8, 8), (3, 3), (0, 0)), ((1, 2, 5, 12), (1, 1), (0, 0)), ((1, 1, 40, 64), (2, 4), (0, 3)),
+             ((1, 2, 300, 24), (4, 4), (2, 2)), ((2, 2, 16, 2050), (3, 3), (1, 1))]
+    for shape, ks, pad in cases:
+        k = torch.randn(*ks, generator=gen(ks[0] * 7 + ks[1])).to(DEV)
+        x = torch.randn(*shape, generator=gen(shape[2] + shape[3])).to(DEV)
+        for dt in (torch.bfloat16, torch.float16):
+            x16 = x.to(dt)
+            got = upfirdn2d(x16, k, pad=pad)
+            want = upfirdn2d(x16.float(), k, pad=pad).to(dt)
+            assert got.dtype == dt and got.shape == want.shape
+            assert torch.equal(got, want), (shape, ks, pad, dt, float((got.float() - want.float()).abs().max()))
+    # a view at an odd element offset (2-byte aligned planes: 16-bit stores) and Inf next to the border
+    k = torch.randn(4, 4, generator=gen(3)).to(DEV)
+    flat = torch.randn(2 * 3 * 66 * 130 + 1, generator=gen(4)).to(DEV, torch.bfloat16)
+    x = flat[1:].view(2, 3, 66, 130)
+    x[0, 0, 0, 0] = float("inf")
+    x[1, 2, -1, -2] = float("-inf")
+    got = upfirdn2d(x, k.abs(), pad=(2, 2))
+    want = upfirdn2d(x.float(), k.abs(), pad=(2, 2)).to(torch.bfloat16)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    ok = ~torch.isnan(want)
+    assert torch.equal(got[ok], want[ok])
+
+
 def test_upfirdn2d_backward_and_double_backward():
     from ppst_b200.stylegan2_op import upfirdn2d
     k = O.make_kernel([1, 3, 3, 1])
