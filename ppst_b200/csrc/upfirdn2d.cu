@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256, 5) upfirdn2d_bulk_kernel(T* __restrict__ 
 //      starts on an odd element: 2^n+3-wide rows alternate), the two columns' accumulators are one float2 and every tap is
 //      one packed FFMA2 (sm_100: fma.rn.f32x2), and the two results leave as one 32-bit store.  Per-column arithmetic and
 //      its order are those of the scalar kernel, so the results are bit-identical to it.
+constexpr int kRows16 = 8;
 template <typename T> struct Pack16;
 template <> struct Pack16<__nv_bfloat16> {
   __device__ __forceinline__ static float2 unpack(uint32_t w) {
@@ -228,13 +229,12 @@ __global__ void __launch_bounds__(256, 4) upfirdn2d_bulk16_kernel(T* __restrict_
                                                                   const float* __restrict__ kernel, UpfirdnParams p,
                                                                   int R, int nstrips) {
   static_assert(sizeof(T) == 2, "16-bit element types only");
-  constexpr int RR = 8;                              // output rows per thread (vertical sliding window)
+  constexpr int RR = kRows16;                        // output rows per thread (vertical sliding window)
   constexpr int KM = KS ? KS : 4;
   constexpr int VEC = 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   T* sm = reinterpret_cast<T*>(smem_raw + 16);
-  const uint32_t* smw = reinterpret_cast<const uint32_t*>(smem_raw + 16);
   const int tid = threadIdx.x;
   const int strip = blockIdx.x % nstrips;
   const int64_t plane = blockIdx.x / nstrips;
@@ -669,7 +669,7 @@ namespace ppst {
 // vectors it needs are loaded once and shared by the rows (7 loads per output instead of 16 for the 4x4 kernel).
 constexpr int kBlurRows = 4;
 template <typename T, int KH, int KW>
-__global__ void __launch_bounds__(256) blur_nhwc_kernel(T* __restrict__ out, const T* __restrict__ in,
+__global__ void __launch_bounds__(256, 4) blur_nhwc_kernel(T* __restrict__ out, const T* __restrict__ in,
                                                         const float* __restrict__ k, int64_t n, int in_h, int in_w, int c,
                                                         int py0, int px0, int out_h, int out_w, int flip) {
   constexpr int VEC = Vec16<T>::N;
@@ -679,15 +679,13 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(T* __restrict__ out, con
     sk[threadIdx.x] = flip ? k[(KH - 1 - ky) * KW + (KW - 1 - kx)] : k[threadIdx.x];
   }
   __syncthreads();
+  // grid = (chunks of 256 (column, channel vector) items of a row strip, strips, images): 32-bit index math only
   const int cv = c / VEC;
-  const int strips = (out_h + kBlurRows - 1) / kBlurRows;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * strips * out_w * cv) return;
-  const int v = (int)(idx % cv);
-  int64_t r = idx / cv;
-  const int ox = (int)(r % out_w); r /= out_w;
-  const int oy0 = (int)(r % strips) * kBlurRows;
-  const int64_t ni = r / strips;
+  const int item = blockIdx.x * 256 + threadIdx.x;
+  if (item >= out_w * cv) return;
+  const int ox = item / cv, v = item - ox * cv;
+  const int oy0 = blockIdx.y * kBlurRows;
+  const int64_t ni = blockIdx.z;
   float acc[kBlurRows][VEC];
 #pragma unroll
   for (int j = 0; j < kBlurRows; ++j)
@@ -714,17 +712,36 @@ __global__ void __launch_bounds__(256) blur_nhwc_kernel(T* __restrict__ out, con
     for (int kx = 0; kx < KW; ++kx) xv[kx] = ld_vec16(row + (int64_t)cx[kx] * c);
 #pragma unroll
     for (int kx = 0; kx < KW; ++kx) {
-      float xf[VEC];
       const bool valid = (vy * vx[kx]) != 0.0f;
+      if constexpr (sizeof(T) == 2) {
+        // adjacent channels are the two halves of one 32-bit word: unpack to a float2 and use packed FFMA2 with the tap
+        // broadcast -- half the FMA issue slots of the scalar form, same per-channel arithmetic and order
+        const uint32_t* wv = reinterpret_cast<const uint32_t*>(&xv[kx].raw);
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) xf[e] = valid ? Cvt<T>::to_f(xv[kx].v[e]) : 0.0f;
+        for (int e2 = 0; e2 < VEC / 2; ++e2) {
+          const float2 xf = Pack16<T>::unpack(valid ? wv[e2] : 0u);
 #pragma unroll
-      for (int j = 0; j < kBlurRows; ++j) {
-        const int ky = rr - j;                       // input row rr is tap ky of output row j (compile-time after unrolling)
-        if (ky < 0 || ky >= KH) continue;
-        const float w = sk[ky * KW + kx];
+          for (int j = 0; j < kBlurRows; ++j) {
+            const int ky = rr - j;
+            if (ky < 0 || ky >= KH) continue;
+            const float w = sk[ky * KW + kx];
+            const float2 a = __ffma2_rn(make_float2(w, w), xf, make_float2(acc[j][2 * e2], acc[j][2 * e2 + 1]));
+            acc[j][2 * e2] = a.x;
+            acc[j][2 * e2 + 1] = a.y;
+          }
+        }
+      } else {
+        float xf[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc[j][e] = fmaf(w, xf[e], acc[j][e]);
+        for (int e = 0; e < VEC; ++e) xf[e] = valid ? Cvt<T>::to_f(xv[kx].v[e]) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < kBlurRows; ++j) {
+          const int ky = rr - j;                     // input row rr is tap ky of output row j (compile-time after unrolling)
+          if (ky < 0 || ky >= KH) continue;
+          const float w = sk[ky * KW + kx];
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[j][e] = fmaf(w, xf[e], acc[j][e]);
+        }
       }
     }
   }
@@ -750,9 +767,11 @@ extern "C" int ppst_blur_nhwc(void* out, const void* in, const float* kernel, in
   const int out_h = in_h + py0 + py1 - kh + 1, out_w = in_w + px0 + px1 - kw + 1;
   PPST_REQUIRE(out_h > 0 && out_w > 0, PPST_ERR_ARG, "blur_nhwc: empty output");
   PPST_REQUIRE(kh == kw && kh >= 1 && kh <= 4, PPST_ERR_UNSUPPORTED, "blur_nhwc: kernel %dx%d (square, 1..4 taps per axis)", kh, kw);
-  const int64_t total = n * ((out_h + kBlurRows - 1) / kBlurRows) * out_w * (c / vec);
+  const int strips = (out_h + kBlurRows - 1) / kBlurRows;
+  PPST_REQUIRE(n <= 65535 && strips <= 65535 && (int64_t)out_w * (c / vec) < (1LL << 31), PPST_ERR_UNSUPPORTED,
+               "blur_nhwc: n=%lld / %d row strips exceed the grid limits", (long long)n, strips);
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const dim3 blocks((unsigned)(((int64_t)out_w * (c / vec) + 255) / 256), (unsigned)strips, (unsigned)n);
 #define PPST_BLUR(T, K) \
   blur_nhwc_kernel<T, K, K><<<blocks, 256, 0, st>>>((T*)out, (const T*)in, kernel, n, in_h, in_w, c, py0, px0, out_h, out_w, flip)
   if (dtype == PPST_BF16) {
