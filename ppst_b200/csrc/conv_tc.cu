@@ -58,6 +58,7 @@ struct Params {
   // halo kernel only
   int tiles_ys;                         // super-tile rows per image = ceil(tiles_y / MT)
   int a_rows, a_slot_bytes;             // rows of one A box (MT*th + kh - 1) and its 1024-aligned slot size
+  int a_box_bytes;                      // bytes of one A box; row stride 2: a slot holds the even-row box, then the odd-row box
   int na, nb, bps;                      // A slots, B slots, taps per B slot (1 or kh)
 };
 
@@ -684,19 +685,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (elect_one()) {
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      const uint32_t a_box_bytes = (uint32_t)(p.a_rows * p.tw * BKC * 2);
+      const uint32_t a_box_bytes = (uint32_t)p.a_box_bytes;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int nt, ph, tx, tys, img;
         decode(tile, nt, ph, tx, tys, img);
         const int py = ph / p.phases_x, px = ph % p.phases_x;
-        const int iy0 = tys * MT * p.th + p.off_y + py * p.phase_off_dy;
-        const int ix0 = tx * p.tw + p.off_x + px * p.phase_off_dx;
+        const int iy0 = tys * MT * p.th * p.stride + p.off_y + py * p.phase_off_dy;
+        const int ix0 = tx * p.tw * p.stride + p.off_x + px * p.phase_off_dx;
         const int brow = img * p.w_img_rows + ph * p.cout + nt * BN;
         for (int cb = 0; cb < p.kblocks_per_tap; ++cb) {
           for (int kx = 0; kx < p.kw; ++kx) {
             mbar_wait(&a_empty[sa], pha ^ 1);
-            mbar_arrive_expect_tx(&a_full[sa], a_box_bytes);
+            mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * (uint32_t)p.stride);
             tma_load_4d(a_ring + sa * p.a_slot_bytes, &map_a, &a_full[sa], cb * BKC, ix0 + kx, iy0, img);
+            if (p.stride == 2)     // the map skips every other row: second box = the odd rows (taps ky = 1, 3, ...)
+              tma_load_4d(a_ring + sa * p.a_slot_bytes + a_box_bytes, &map_a, &a_full[sa], cb * BKC, ix0 + kx, iy0 + 1, img);
             if (++sa == p.na) { sa = 0; pha ^= 1; }
             for (int ky0 = 0; ky0 < p.kh; ky0 += p.bps) {
               mbar_wait(&b_empty[sb], phb ^ 1);
@@ -736,8 +739,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               for (int j = 0; j < p.bps; ++j) {
                 const uint64_t db = make_smem_desc<BKC>(b_base + (uint32_t)(j * kBBytes));
 #pragma unroll
+                // tap row ky starts ky rows into the box; row stride 2: ky / 2 rows into the box of its parity
+                const int ky = ky0 + j;
+                const uint32_t a_tap = p.stride == 2 ? (uint32_t)(ky & 1) * (uint32_t)p.a_box_bytes + (uint32_t)(ky >> 1) * dy_bytes
+                                                     : (uint32_t)ky * dy_bytes;
+#pragma unroll
                 for (int m = 0; m < MT; ++m) {
-                  const uint64_t da = make_smem_desc<BKC>(a_base + (uint32_t)(ky0 + j) * dy_bytes + (uint32_t)(m * kSubBytes));
+                  const uint64_t da = make_smem_desc<BKC>(a_base + a_tap + (uint32_t)(m * kSubBytes));
 #pragma unroll
                   for (int k = 0; k < BKC / 16; ++k)
                     umma_bf16(tmem_d + (uint32_t)(m * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
@@ -1367,8 +1375,8 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
     const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
     const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
     const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
-    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)(p.tw * d.stride), (uint32_t)(p.th * d.stride), 1};
-    const uint32_t est[4] = {1, (uint32_t)d.stride, (uint32_t)d.stride, 1};
+    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)(p.tw * p.stride), (uint32_t)(p.th * d.stride), 1};
+    const uint32_t est[4] = {1, (uint32_t)p.stride, (uint32_t)d.stride, 1};
     int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
     if (rc) return rc;
   }
@@ -1405,7 +1413,7 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   Params p;
   std::memset(&p, 0, sizeof(p));
   p.n = d.n; p.out_h = d.out_h; p.out_w = d.out_w; p.cout = d.cout; p.cin = d.cin;
-  p.kh = d.kh; p.kw = d.kw; p.stride = 1;
+  p.kh = d.kh; p.kw = d.kw; p.stride = d.stride;
   p.off_y = d.off_y; p.off_x = d.off_x; p.phases_y = d.phases_y; p.phases_x = d.phases_x;
   p.phase_off_dy = d.phase_off_dy; p.phase_off_dx = d.phase_off_dx;
   p.full_h = d.full_h; p.full_w = d.full_w; p.cout_stride = d.cout_stride; p.c_off = d.c_off;
@@ -1420,8 +1428,10 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   p.kblocks_per_tap = d.cin / BKC;
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
   p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
-  p.a_rows = MT * p.th + d.kh - 1;
-  p.a_slot_bytes = (p.a_rows * p.tw * BKC * 2 + 1023) / 1024 * 1024;
+  // row stride 2: the tensor map skips every other row, a slot holds the even-row box (taps 0, 2, ..) then the odd-row box
+  p.a_rows = MT * p.th + (d.kh - 1) / d.stride;
+  p.a_box_bytes = p.a_rows * p.tw * BKC * 2;                         // a whole number of swizzle atoms (tw >= 8)
+  p.a_slot_bytes = (d.stride * p.a_box_bytes + 1023) / 1024 * 1024;
   constexpr int kBBytes = BN * BKC * 2;
   p.bps = (d.kh * kBBytes <= 24576) ? d.kh : 1;
   const int b_slot = p.bps * kBBytes;
@@ -1446,8 +1456,8 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
     const uint64_t rowp = d.in_row_pitch ? (uint64_t)d.in_row_pitch : (uint64_t)d.in_w * d.cin;
     const uint64_t imgp = d.in_img_pitch ? (uint64_t)d.in_img_pitch : (uint64_t)d.in_h * d.in_w * d.cin;
     const uint64_t strides[3] = {(uint64_t)d.cin * 2, rowp * 2, imgp * 2};
-    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)p.tw, (uint32_t)p.a_rows, 1};
-    const uint32_t est[4] = {1, 1, 1, 1};
+    const uint32_t box[4] = {(uint32_t)BKC, (uint32_t)(p.tw * p.stride), (uint32_t)(p.a_rows * d.stride), 1};
+    const uint32_t est[4] = {1, (uint32_t)p.stride, (uint32_t)d.stride, 1};
     int rc = encode_map(&map_a, in, 4, dims, strides, box, est, BKC);
     if (rc) return rc;
   }
@@ -1504,7 +1514,8 @@ static int launch_halo2(const ppst_conv_desc& d, void* out, const void* in, cons
   p.has_act = d.has_act; p.slope = d.slope; p.gain = d.gain; p.noise_w = d.noise_w;
   p.stats_partials = p.tiles_y * p.tiles_x * n_phases;
   p.a_rows = MT * p.th + d.kh - 1;
-  p.a_slot_bytes = (p.a_rows * p.tw * BKC * 2 + 1023) / 1024 * 1024;
+  p.a_box_bytes = p.a_rows * p.tw * BKC * 2;
+  p.a_slot_bytes = (p.a_box_bytes + 1023) / 1024 * 1024;
   constexpr int kBBytes = (BN / 2) * BKC * 2;
   p.bps = (d.kh * kBBytes <= 24576) ? d.kh : 1;
   const int b_slot = p.bps * kBBytes;
@@ -1559,11 +1570,20 @@ static int launch_halo2(const ppst_conv_desc& d, void* out, const void* in, cons
 static int halo_mode(const ppst_conv_desc& d, int bn) {
   static const int env_halo = [] { const char* e = getenv("PPST_CONV_TC_HALO"); return e ? atoi(e) : 1; }();
   static const int env_mt = [] { const char* e = getenv("PPST_CONV_TC_MT"); return e ? atoi(e) : 0; }();
-  if (!env_halo || d.stride != 1 || d.kh < 2 || d.kh > 4 || d.split_terms != 0 || d.out_dtype != PPST_BF16)
+  const char* e_s2 = getenv("PPST_CONV_TC_HALO_S2");   // read per call: tests toggle it.  0: plain kernel, 1: MT = 1, 2: MT <= 2, 3: MT <= 4
+  const int env_s2 = e_s2 ? atoi(e_s2) : 3;
+  const bool s2 = d.stride == 2 && env_s2 > 0 && d.phases_y * d.phases_x == 1 && d.kh >= 2 && d.kh <= 6;
+  if (!env_halo || !(s2 || (d.stride == 1 && d.kh >= 2 && d.kh <= 4)) || d.split_terms != 0 || d.out_dtype != PPST_BF16)
     return 0;
   int th, tw;
   pick_tile(d.out_h, d.out_w, th, tw);
   if (tw < 8 || tw * th != BM) return 0;       // tap row offsets must be whole swizzle atoms
+  if (s2) {
+    // a slot holds two boxes of MT*th + (kh-1)/2 rows; MT = 2 when two such slots and a B ring still fit
+    const int64_t tiles2 = (int64_t)d.n * ceil_div(d.out_h, th) * ceil_div(d.out_w, tw) * (d.cout / bn);
+    if (env_s2 >= 3 && bn <= 64 && ceil_div(d.out_h, th) >= 4 && tiles2 >= 16LL * num_sms()) return 4;
+    return (env_s2 >= 2 && bn <= 128 && ceil_div(d.out_h, th) >= 2 && tiles2 >= 4LL * num_sms()) ? 2 : 1;
+  }
   if (bn > 128) return 1;
   if (env_mt == 1 || env_mt == 2 || (env_mt == 4 && bn <= 64)) return env_mt;
   const int64_t tiles = (int64_t)d.n * ceil_div(d.out_h, th) * ceil_div(d.out_w, tw) * d.phases_y * d.phases_x * (d.cout / bn);
@@ -1577,7 +1597,7 @@ static int halo_mode(const ppst_conv_desc& d, int bn) {
 static bool pair_mode(const ppst_conv_desc& d, int bn) {
   const char* e = getenv("PPST_CONV_TC_2CTA");        // read per call: tests toggle it
   const int env = e ? atoi(e) : 2;
-  if (env == 0 || (bn != 128 && bn != 256) || (bn == 256 && env < 2)) return false;
+  if (env == 0 || (bn != 128 && bn != 256) || (bn == 256 && env < 2) || d.stride != 1) return false;
   int th, tw;
   pick_tile(d.out_h, d.out_w, th, tw);
   const int tiles_x = ceil_div(d.out_w, tw);

@@ -819,3 +819,56 @@ def test_conv_tc_cta_pair_kernel_is_bit_identical_to_single_cta(shape):
         i0, i2 = res["0"][0], res["2"][0]
     assert torch.equal(i0, i2)
     assert torch.equal(res["0"][1], res["2"][1]) and torch.equal(res["0"][2], res["2"][2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(2, 64, 64, 32, 64, 5, 0), (1, 128, 96, 32, 64, 3, -1), (2, 48, 80, 64, 128, 5, 0),
+                                  (1, 64, 64, 128, 256, 3, -1), (3, 32, 48, 32, 32, 6, -2), (16, 256, 256, 32, 64, 5, 0),
+                                  (8, 256, 192, 64, 128, 3, -1), (1, 70, 50, 32, 64, 4, -1)])
+def test_conv_tc_stride2_halo_boxes(case):
+    """The blurred stride-2 convolutions of ResBlock: plain kernel (one strided box per tap) and the halo kernel with row
+    stride 2 (one even-row + one odd-row box per kernel column, taps = row offsets inside the box of their parity, 1 / 2 /
+    4 sub-tiles per work item) against F.conv2d on the same bf16 operands; statistics partials must add up to the sums of
+    the stored outputs, and the super-tile heights must agree bit for bit (same K order)."""
+    import math
+    import os
+    import torch.nn.functional as F
+    from ppst_b200 import ops, packing
+    from ppst_b200._lib import BF16
+    if not ops.conv_tc_available():
+        pytest.skip("tcgen05 path unavailable")
+    n, h, w, ci, co, k, off = case
+    g = torch.Generator().manual_seed(k * 100 + ci)
+    pad = -off
+    ih, iw = (h, w) if off else (h + k - 1, w + k - 1)       # off = 0: the caller pre-padded
+    oh, ow = ((h - 2) // 2 + 1, (w - 2) // 2 + 1) if off else (h // 2, w // 2)
+    x = torch.randn(n, ih, iw, ci, generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn(co, ci, k, k, generator=g) / math.sqrt(ci * k * k)).to(torch.bfloat16)
+    bias = torch.randn(co, generator=g).cuda()
+    xr = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(F.pad(xr, [pad, pad + k, pad, pad + k]), wt.float().cuda(), stride=2)[:, :, :oh, :ow] + bias.view(1, -1, 1, 1)
+    ref = ref.permute(0, 2, 3, 1)
+    wq = packing.pack_taps(wt.float()).unsqueeze(0).to(torch.bfloat16).cuda()
+    d = ops.conv_desc((n, ih, iw, ci), co, k, k, stride=2, off=(off, off), out_hw=(oh, ow), in_dtype=BF16, out_dtype=BF16)
+    old = os.environ.get("PPST_CONV_TC_HALO_S2")
+    outs = {}
+    try:
+        for flag in ("0", "1", "2", "3"):
+            os.environ["PPST_CONV_TC_HALO_S2"] = flag
+            y = torch.full((n, oh, ow, co), float("nan"), device="cuda", dtype=torch.bfloat16)
+            st = torch.empty(ops.conv_tc_stats_elems(d), device="cuda")
+            ops.conv_tc(y, x, wq, bias, None, st, d)
+            torch.cuda.synchronize()
+            err = float((y.float() - ref).norm() / ref.norm())
+            assert err <= 4e-3, (case, flag, err)
+            half = st.numel() // 2
+            s1 = st[:half].view(n, -1, co).sum(1)
+            assert torch.allclose(s1, y.float().sum((1, 2)), rtol=1e-3, atol=2e-2), (case, flag)
+            outs[flag] = (y, st.clone())
+    finally:
+        if old is None:
+            os.environ.pop("PPST_CONV_TC_HALO_S2", None)
+        else:
+            os.environ["PPST_CONV_TC_HALO_S2"] = old
+    for flag in ("2", "3"):
+        assert torch.equal(outs["1"][0], outs[flag][0]), (case, flag)
