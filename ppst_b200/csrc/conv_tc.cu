@@ -738,7 +738,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const uint32_t b_base = smem_u32(b_ring + sb * b_slot_bytes);
               for (int j = 0; j < p.bps; ++j) {
                 const uint64_t db = make_smem_desc<BKC>(b_base + (uint32_t)(j * kBBytes));
-#pragma unroll
                 // tap row ky starts ky rows into the box; row stride 2: ky / 2 rows into the box of its parity
                 const int ky = ky0 + j;
                 const uint32_t a_tap = p.stride == 2 ? (uint32_t)(ky & 1) * (uint32_t)p.a_box_bytes + (uint32_t)(ky >> 1) * dy_bytes
