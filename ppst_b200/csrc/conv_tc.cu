@@ -1405,6 +1405,7 @@ static int launch(const ppst_conv_desc& d, void* out, const void* in, const void
 }
 
 
+constexpr int kHaloNoFit = -1000;                   // launch_halo only: not an error, never leaves this file
 template <int BN, int BKC, int MT>
 static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const void* weight, const float* bias,
                        const float* noise, float* stats, cudaStream_t st) {
@@ -1446,7 +1447,7 @@ static int launch_halo(const ppst_conv_desc& d, void* out, const void* in, const
   while (p.na > 2 && avail - p.na * p.a_slot_bytes < 3 * b_slot) --p.na;
   p.nb = (avail - p.na * p.a_slot_bytes) / b_slot;
   if (p.nb > kMaxB) p.nb = kMaxB;
-  PPST_REQUIRE(p.nb >= 2 && p.na >= 2, PPST_ERR_UNSUPPORTED, "conv_tc(halo): rings do not fit in shared memory");
+  if (p.nb < 2 || p.na < 2) return kHaloNoFit;      // rings do not fit: the dispatcher tries fewer sub-tiles, then the plain kernel
   const int smem_total = p.na * p.a_slot_bytes + p.nb * b_slot + S::kFixedBytes;
 
   CUtensorMap map_a, map_b;
@@ -1719,11 +1720,14 @@ extern "C" int ppst_conv_tc(void* out, const void* in, const void* weight, const
         return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, (BN_ == 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
       return tc::launch_halo2<(BN_ == 128 ? 128 : 256), 64, 1>(d, out, in, weight, bias, noise, stats, st); \
     }                                                                                        \
+    int hrc = tc::kHaloNoFit;                                                                \
     if (hm == 4 && BN_ <= 64)                                                                \
-      return tc::launch_halo<BN_, BKC_, (BN_ <= 64 ? 4 : 1)>(d, out, in, weight, bias, noise, stats, st); \
-    if (hm >= 2 && BN_ <= 128)                                                               \
-      return tc::launch_halo<BN_, BKC_, (BN_ <= 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
-    if (hm >= 1) return tc::launch_halo<BN_, BKC_, 1>(d, out, in, weight, bias, noise, stats, st);         \
+      hrc = tc::launch_halo<BN_, BKC_, (BN_ <= 64 ? 4 : 1)>(d, out, in, weight, bias, noise, stats, st); \
+    if (hrc == tc::kHaloNoFit && hm >= 2 && BN_ <= 128)                                      \
+      hrc = tc::launch_halo<BN_, BKC_, (BN_ <= 128 ? 2 : 1)>(d, out, in, weight, bias, noise, stats, st); \
+    if (hrc == tc::kHaloNoFit && hm >= 1)                                                    \
+      hrc = tc::launch_halo<BN_, BKC_, 1>(d, out, in, weight, bias, noise, stats, st);       \
+    if (hrc != tc::kHaloNoFit) return hrc;                                                   \
     if (d.out_dtype == PPST_F32)                                                             \
       return tc::launch<BN_, BKC_, true>(d, out, in, weight, bias, noise, stats, st);        \
     return tc::launch<BN_, BKC_, false>(d, out, in, weight, bias, noise, stats, st);         \

@@ -824,7 +824,8 @@ def test_conv_tc_cta_pair_kernel_is_bit_identical_to_single_cta(shape):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", [(2, 64, 64, 32, 64, 5, 0), (1, 128, 96, 32, 64, 3, -1), (2, 48, 80, 64, 128, 5, 0),
                                   (1, 64, 64, 128, 256, 3, -1), (3, 32, 48, 32, 32, 6, -2), (16, 256, 256, 32, 64, 5, 0),
-                                  (8, 256, 192, 64, 128, 3, -1), (1, 70, 50, 32, 64, 4, -1)])
+                                  (8, 256, 192, 64, 128, 3, -1), (1, 70, 50, 32, 64, 4, -1), (16, 256, 256, 64, 128, 5, 0),
+                                  (8, 128, 256, 128, 128, 6, -2), (16, 128, 128, 128, 256, 5, 0)])
 def test_conv_tc_stride2_halo_boxes(case):
     """The blurred stride-2 convolutions of ResBlock: plain kernel (one strided box per tap) and the halo kernel with row
     stride 2 (one even-row + one odd-row box per kernel column, taps = row offsets inside the box of their parity, 1 / 2 /
