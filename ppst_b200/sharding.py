@@ -93,3 +93,91 @@ def allreduce_grads_(params, world=None):
     pieces = [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)]
     torch._foreach_copy_(grads, pieces)
     return flat.numel() * 4
+
+
+def _reduce_bucket_(grads, world):
+    """Average one bucket of gradient tensors over the ranks, in place (one flat f32 buffer, one all-reduce)."""
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world)
+    torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
+    return flat.numel() * 4
+
+
+class OverlappedGradReducer:
+    """allreduce_grads_ with the exchange hidden behind the rest of the backward pass (what DistributedDataParallel's
+    bucketing does for the reference, models/__init__.py:88): every parameter reports the moment autograd has finished
+    its gradient (post-accumulate hook: once per backward() however often the parameter is used); parameters are
+    collected in that order and every `bucket_bytes` of them are averaged by one all-reduce on a SIDE stream that waits
+    for the main stream at that point only.  The networks here keep most of their parameters in the low-resolution,
+    512-channel layers, whose gradients come early in the backward pass of D, E1 and E2 (and, for G, before the whole
+    encoder backward), while the time goes into the high-resolution layers -- so all but the last bucket travel while
+    the tensor cores are busy.  Deterministic: the bucket sequence is the autograd order, identical on every rank.
+    Works inside CUDA-graph capture (the fork / join are event dependencies of the captured graph).
+
+        red = OverlappedGradReducer(params)       # once
+        with red:                                  # per step: arm, backward, flush the tail, join
+            loss.backward()
+        optimiser.step()
+    """
+
+    def __init__(self, params, world=None, bucket_bytes=32 << 20):
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.world = world
+        self.active = world > 1 and dist.is_initialized()
+        self.bucket_bytes = int(bucket_bytes)
+        self.params = [p for p in params]
+        self._armed = False
+        self._pending, self._pending_bytes = [], 0
+        self._side = None
+        self.bytes_reduced = 0
+        self.buckets = 0
+        self._hooks = [p.register_post_accumulate_grad_hook(self._ready) for p in self.params] if self.active else []
+
+    def _ready(self, p):
+        if not self._armed or p.grad is None:
+            return
+        self._pending.append(p.grad)
+        self._pending_bytes += p.grad.numel() * 4
+        if self._pending_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        grads, self._pending, self._pending_bytes = self._pending, [], 0
+        if not grads:
+            return
+        self.buckets += 1
+        if grads[0].is_cuda:
+            main = torch.cuda.current_stream(grads[0].device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(grads[0].device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self._side.wait_event(ready)                      # the side stream sees these gradients, nothing later
+            with torch.cuda.stream(self._side):
+                self.bytes_reduced += _reduce_bucket_(grads, self.world)
+        else:
+            self.bytes_reduced += _reduce_bucket_(grads, self.world)
+
+    def __enter__(self):
+        self._armed = self.active
+        self._pending, self._pending_bytes = [], 0
+        self.bytes_reduced, self.buckets = 0, 0
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if self._armed and exc_type is None:
+            self._flush()
+            if self._side is not None:
+                torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+        self._armed = False
+        return False
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

@@ -113,3 +113,70 @@ def test_two_rank_gradient_allreduce_is_one_averaged_flat_bucket():
         assert g1 == [1.5 * i for i in range(7)]
         assert g2 is None
     assert sharding.allreduce_grads_([torch.nn.Parameter(torch.zeros(1))]) == 0   # single process: no-op
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank),
+                      LOCAL_RANK=str(rank))
+    sharding.init(backend="gloo")
+
+    def make():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                                   torch.nn.Linear(16, 4)).double()
+    torch.manual_seed(100 + rank)
+    x = torch.randn(5, 6, dtype=torch.float64)
+
+    def loss_of(net):
+        # the first layer is used TWICE: its gradient must be reported once, after both uses are accumulated
+        return (net(x) ** 2).mean() + net[0](x).sum() * 0.1
+    ref = make()
+    loss_of(ref).backward()
+    sharding.allreduce_grads_(list(ref.parameters()))
+    net = make()
+    red = sharding.OverlappedGradReducer(list(net.parameters()), bucket_bytes=16 * 16 * 4)   # several small buckets
+    order = []
+    for i, p in enumerate(net.parameters()):
+        p.register_post_accumulate_grad_hook(lambda p_, i=i: order.append(i))
+    with red:
+        loss_of(net).backward()
+    same = all(torch.equal(a.grad, b.grad) for a, b in zip(net.parameters(), ref.parameters()))
+    # a second step reuses the reducer; a backward outside `with` is left alone
+    net.zero_grad(set_to_none=True)
+    loss_of(net).backward()
+    local = make()
+    loss_of(local).backward()                                   # this rank's own gradients, never exchanged
+    untouched = all(torch.equal(a.grad, b.grad) for a, b in zip(net.parameters(), local.parameters()))
+    with red:
+        net.zero_grad(set_to_none=True)
+        loss_of(net).backward()
+    same2 = all(torch.equal(a.grad, b.grad) for a, b in zip(net.parameters(), ref.parameters()))
+    dist.destroy_process_group()
+    q.put((rank, same, same2, untouched, red.buckets, red.bytes_reduced, order))
+
+
+def test_two_rank_overlapped_gradient_reducer_matches_the_flat_allreduce():
+    """OverlappedGradReducer: buckets in autograd order, each averaged as soon as it is full; the result equals the
+    one-bucket all-reduce bit for bit, parameters used twice are reported once, the bucket sequence is the same on both
+    ranks (or the collectives would not line up and this test would hang / mismatch)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_param_bytes = (6 * 16 + 16 + 16 * 16 + 16 + 16 * 4 + 4) * 4
+    for rank, same, same2, untouched, buckets, nbytes, order in results:
+        assert same and same2 and untouched
+        assert buckets >= 2 and nbytes == n_param_bytes
+        assert sorted(order[:6]) == list(range(6)) and order[0] in (4, 5)    # first backward; last layer first: autograd order
+    assert results[0][6] == results[1][6]
+    red = sharding.OverlappedGradReducer([torch.nn.Parameter(torch.zeros(1))])     # single process: inert
+    assert not red.active
+    with red:
+        pass

@@ -49,22 +49,36 @@ def stage1(args):
     opt_d = torch.optim.Adam(d_params, lr=2e-3, betas=(0.0, 0.99), fused=True)
     real = O.make_portraits(args.batch, args.size, args.size, seed=77 + rank, smooth=True).to(dev)
     bucket = {}
+    # gradient exchange: bucketed and overlapped with the rest of the backward pass (sharding.OverlappedGradReducer);
+    # PPST_TRAIN_OVERLAP=0: one flat all-reduce after the backward pass (round 1)
+    overlap = os.environ.get("PPST_TRAIN_OVERLAP", "1") != "0"
+    red_g = sharding.OverlappedGradReducer(g_params, world) if overlap else None
+    red_d = sharding.OverlappedGradReducer(d_params, world) if overlap else None
+
+    def backward_and_exchange(loss, params, red, key=None):
+        if red is not None and red.active:
+            with red:
+                loss.backward()
+            nbytes = red.bytes_reduced
+        else:
+            loss.backward()
+            nbytes = sharding.allreduce_grads_(params, world)
+        if key:
+            bucket[key] = nbytes
 
     def g_step():
         opt_g.zero_grad(set_to_none=True)
         for p in d_params:
             p.requires_grad_(False)
         losses, _ = m.generator_losses(real)
-        sum(losses.values()).backward()
+        backward_and_exchange(sum(losses.values()), g_params, red_g, "g")
         for p in d_params:
             p.requires_grad_(True)
-        bucket["g"] = sharding.allreduce_grads_(g_params, world)
         opt_g.step()
 
     def d_step():
         opt_d.zero_grad(set_to_none=True)
-        sum(m.discriminator_losses(real).values()).backward()
-        bucket["d"] = sharding.allreduce_grads_(d_params, world)
+        backward_and_exchange(sum(m.discriminator_losses(real).values()), d_params, red_d, "d")
         opt_d.step()
 
     def r1_step():
@@ -99,14 +113,12 @@ def stage1(args):
         def body_g():
             losses, _ = m.generator_losses(real)
             total = sum(losses.values())
-            total.backward()
+            backward_and_exchange(total, g_params, red_g)
             loss_buf.copy_(total.detach().reshape(1))
-            sharding.allreduce_grads_(g_params, world)
             cg.step()
 
         def body_d():
-            sum(m.discriminator_losses(real).values()).backward()
-            sharding.allreduce_grads_(d_params, world)
+            backward_and_exchange(sum(m.discriminator_losses(real).values()), d_params, red_d)
             cd.step()
 
         def body_r1():
