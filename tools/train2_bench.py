@@ -34,20 +34,32 @@ og = torch.optim.Adam(g_params, lr=2e-3, betas=(0.0, 0.99), fused=True, capturab
 od = torch.optim.Adam(d_params, lr=2e-3, betas=(0.0, 0.99), fused=True, capturable=True)
 loss_buf = torch.zeros(1, device=dev)
 bucket = {}
+# gradient exchange bucketed and overlapped with the backward pass (PPST_TRAIN_OVERLAP=0: one flat all-reduce after it)
+overlap = os.environ.get("PPST_TRAIN_OVERLAP", "1") != "0"
+red_g = sharding.OverlappedGradReducer(g_params, world) if overlap else None
+red_d = sharding.OverlappedGradReducer(d_params, world) if overlap else None
+
+
+def backward_and_exchange(loss, params, red, key):
+    if red is not None and red.active:
+        with red:
+            loss.backward()
+        bucket[key] = red.bytes_reduced
+    else:
+        loss.backward()
+        bucket[key] = sharding.allreduce_grads_(params, world)
 
 
 def body_g():
     losses = m.generator_losses(real, mask, enqueue=False)
     total = sum(v.mean() for v in losses.values())
-    total.backward()
+    backward_and_exchange(total, g_params, red_g, "g")
     loss_buf.copy_(total.detach().reshape(1))
-    bucket["g"] = sharding.allreduce_grads_(g_params, world)
     og.step()
 
 
 def body_d():
-    sum(v.mean() for v in m.discriminator_losses(real, mask).values()).backward()
-    bucket["d"] = sharding.allreduce_grads_(d_params, world)
+    backward_and_exchange(sum(v.mean() for v in m.discriminator_losses(real, mask).values()), d_params, red_d, "d")
     od.step()
 
 
