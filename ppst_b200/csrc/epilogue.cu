@@ -820,6 +820,93 @@ extern "C" int ppst_affine_apply_torgb(void* out, float* rgb_out, const void* x,
   return 0;
 }
 
+// Bilinear upsampling by an integer factor F in {1, 2, 4, 8} (mode 0, out = F x in: the feature heads' x4 / x2 / x1 maps,
+// generator.py:252-280, and the x8 / x4 / x2 maps of E2.warp).  The generic kernel above loads and transforms (affine +
+// PReLU) four neighbours for EVERY output element -- 31 instructions per element, issue-bound at 1.5-2.8 TB/s -- although
+// the F outputs between two input columns share them.  Here a work item is one input column PAIR (j-1, j) x one 16-byte
+// channel vector: the four neighbours are loaded and transformed once and the F outputs that lie between the two columns
+// (ox = F(j-1) + F/2 .. F(j-1) + F/2 + F - 1) are blended from registers; item j = 0 does the two clamped half segments at
+// the row ends.  Same expressions per element as the generic kernel (horizontal blend, then vertical).
+namespace ppst {
+template <typename TX, typename TO, int F>
+__global__ void __launch_bounds__(256) resample_up_kernel(TO* __restrict__ out, const TX* __restrict__ x, int in_h, int in_w,
+                                                          int c, int out_c_stride, int out_c_off,
+                                                          const float* __restrict__ a, const float* __restrict__ b,
+                                                          float slope, int ib, int ob) {
+  constexpr int V = 8;
+  const int cv = c / V;
+  const int out_h = in_h * F, out_w = in_w * F;
+  const int oy = blockIdx.x;
+  const int64_t ni = blockIdx.y;
+  const int in_wp = in_w + 2 * ib;
+  TO* orow = out + ((ni * (out_h + 2 * ob) + oy + ob) * (out_w + 2 * ob) + ob) * (int64_t)out_c_stride + out_c_off;
+  const TX* img = x + ((ni * (in_h + 2 * ib) + ib) * in_wp + ib) * (int64_t)c;
+  const bool tf = (a != nullptr);
+  const float sh = 1.0f / (float)F;                          // exact: F is a power of two
+  float sy = sh * ((float)oy + 0.5f) - 0.5f;
+  if (sy < 0.f) sy = 0.f;
+  const int y0 = min((int)sy, in_h - 1);
+  const int y1 = y0 + ((y0 < in_h - 1) ? 1 : 0);
+  const float ly1 = sy - (float)y0, ly0 = 1.f - ly1;
+  const TX* row0 = img + (int64_t)y0 * in_wp * c;
+  const TX* row1 = img + (int64_t)y1 * in_wp * c;
+  const int cvb = cv < 256 ? cv : 256;                      // channel groups served concurrently
+  const int lanes = 256 / cvb, lane = threadIdx.x / cvb;
+  if (lane >= lanes) return;
+  for (int cg = threadIdx.x % cvb; cg < cv; cg += cvb) {
+    const int ch = cg * V;
+    float av[V], bv[V];
+    if (tf) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) { av[e] = a[ni * c + ch + e]; bv[e] = b ? b[ni * c + ch + e] : 0.0f; }
+    }
+    auto ld = [&](const TX* rowp, int xx, float (&v)[V]) {
+      load_ch<TX, V>(v, rowp + (int64_t)xx * c + ch);
+      if (tf) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = lrelu_slope(fmaf(v[e], av[e], bv[e]), slope);
+      }
+    };
+    auto emit = [&](int ox, const float (&v00)[V], const float (&v01)[V], const float (&v10)[V], const float (&v11)[V], int x0) {
+      float sx = sh * ((float)ox + 0.5f) - 0.5f;
+      if (sx < 0.f) sx = 0.f;
+      const float lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+      float y[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[e] = ly0 * (lx0 * v00[e] + lx1 * v01[e]) + ly1 * (lx0 * v10[e] + lx1 * v11[e]);
+      store_ch<TO, V>(orow + (int64_t)ox * out_c_stride + ch, y);
+    };
+    if (F == 1) {
+      // the source sample itself (both blend weights of the other neighbours are exactly 0)
+      for (int j = lane; j < in_w; j += lanes) {
+        float v[V];
+        ld(row0, j, v);
+        store_ch<TO, V>(orow + (int64_t)j * out_c_stride + ch, v);
+      }
+      continue;
+    }
+    for (int j = lane; j < in_w; j += lanes) {
+      if (j > 0) {
+        float v00[V], v01[V], v10[V], v11[V];
+        ld(row0, j - 1, v00); ld(row0, j, v01); ld(row1, j - 1, v10); ld(row1, j, v11);
+        const int ox0 = F * (j - 1) + F / 2;
+#pragma unroll
+        for (int t = 0; t < F; ++t) emit(ox0 + t, v00, v01, v10, v11, j - 1);
+      } else {
+        // left end: source coordinate clamped to 0 (lx1 = 0); right end: x0 = x1 = in_w - 1
+        float l0[V], l1[V], r0[V], r1[V];
+        ld(row0, 0, l0); ld(row1, 0, l1); ld(row0, in_w - 1, r0); ld(row1, in_w - 1, r1);
+#pragma unroll
+        for (int t = 0; t < F / 2; ++t) {
+          emit(t, l0, l0, l1, l1, 0);
+          emit(F * (in_w - 1) + F / 2 + t, r0, r0, r1, r1, in_w - 1);
+        }
+      }
+    }
+  }
+}
+}  // namespace ppst
+
 extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int in_w, int out_h, int out_w, int c,
                              int out_c_stride, int out_c_off, int mode, int in_dtype, int out_dtype, const float* a,
                              const float* b, float slope, int in_border, int out_border, void* stream) {
@@ -834,6 +921,32 @@ extern "C" int ppst_resample(void* out, const void* x, int64_t n, int in_h, int 
   PPST_REQUIRE(n <= 65535, PPST_ERR_ARG, "resample: batch too large");
   const dim3 grid((unsigned)out_h, (unsigned)n);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // integer-factor bilinear upsampling (x1 = the transform alone): shared neighbours, see resample_up_kernel
+    const int f = out_h / in_h;
+    const char* e_up = getenv("PPST_RESAMPLE_UP");           // read per call: tests toggle it (0 = generic kernel)
+    const int env_up = e_up ? atoi(e_up) : 1;
+    if (env_up && mode == 0 && vec && out_h == f * in_h && out_w == f * in_w && (f == 1 || f == 2 || f == 4 || f == 8) &&
+        (int64_t)in_w * (c / 8) < (1 << 30)) {
+#define PPST_RU(TX, TO, F_)                                                                                          \
+  resample_up_kernel<TX, TO, F_><<<grid, 256, 0, st>>>((TO*)out, (const TX*)x, in_h, in_w, c, out_c_stride, out_c_off, \
+                                                       a, b, slope, in_border, out_border)
+#define PPST_RUF(TX, TO)                                                                       \
+  do {                                                                                         \
+    if (f == 1) PPST_RU(TX, TO, 1); else if (f == 2) PPST_RU(TX, TO, 2);                       \
+    else if (f == 4) PPST_RU(TX, TO, 4); else PPST_RU(TX, TO, 8);                              \
+  } while (0)
+      if (in_dtype == PPST_F32 && out_dtype == PPST_F32) PPST_RUF(float, float);
+      else if (in_dtype == PPST_BF16 && out_dtype == PPST_BF16) PPST_RUF(__nv_bfloat16, __nv_bfloat16);
+      else if (in_dtype == PPST_BF16 && out_dtype == PPST_F32) PPST_RUF(__nv_bfloat16, float);
+      else if (in_dtype == PPST_F32 && out_dtype == PPST_BF16) PPST_RUF(float, __nv_bfloat16);
+      else PPST_REQUIRE(false, PPST_ERR_DTYPE, "resample: dtype combination %d -> %d", in_dtype, out_dtype);
+#undef PPST_RUF
+#undef PPST_RU
+      PPST_LAUNCH_CHECK("resample_up_kernel");
+      return 0;
+    }
+  }
 #define PPST_RS(TX, TO)                                                                                        \
   do {                                                                                                         \
     if (vec)                                                                                                   \

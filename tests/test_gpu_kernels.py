@@ -647,6 +647,54 @@ def test_resample():
         assert (y.permute(0, 3, 1, 2).cpu() - F.adaptive_avg_pool2d(xr, 4)).abs().max() <= 1e-5
 
 
+def test_resample_integer_upsampling_kernel_matches_the_generic_one():
+    """resample_up_kernel (x1 / x2 / x4 / x8 bilinear, the four neighbours of a column pair loaded and transformed once for
+    the F outputs between them) against the generic per-output kernel (PPST_RESAMPLE_UP=0) and F.interpolate: every dtype
+    pair, affine + PReLU on load, bordered input and output buffers, a channel slice of a wider output, 1-pixel-wide maps."""
+    import os
+    from ppst_b200 import ops
+    g = gen(64)
+    cases = [(2, 16, 16, 64, 4, 0, 0), (1, 8, 24, 16, 8, 0, 0), (2, 32, 20, 64, 2, 1, 0), (1, 64, 64, 64, 1, 0, 1),
+             (2, 9, 1, 8, 4, 0, 0), (1, 1, 7, 8, 2, 0, 0), (3, 5, 6, 24, 8, 1, 1), (1, 3, 3, 8, 1, 1, 0)]
+    old = os.environ.get("PPST_RESAMPLE_UP")
+    try:
+        for n, h, w, c, f, ib, ob in cases:
+            x = torch.randn(n, c, h, w, generator=g)
+            a, b = torch.randn(n, c, generator=g).to(DEV), torch.randn(n, c, generator=g).to(DEV)
+            for dt_in, dt_out in ((torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
+                                  (torch.float32, torch.bfloat16)):
+                xin = ops.nchw_to_nhwc(x.to(DEV), dtype=dt_in)
+                if ib:
+                    xin = torch.nn.functional.pad(xin, (0, 0, ib, ib, ib, ib), value=float("nan")).contiguous()
+                for tf in (False, True):
+                    outs = {}
+                    for flag in ("0", "1"):
+                        os.environ["PPST_RESAMPLE_UP"] = flag
+                        dst = torch.full((n, h * f + 2 * ob, w * f + 2 * ob, c + 16), 7.0, device=DEV, dtype=dt_out)
+                        ops.resample(xin, (h * f, w * f), 0, out=dst, out_c_off=8, in_border=ib, out_border=ob,
+                                     **(dict(a=a, b=b, slope=0.25) if tf else {}))
+                        outs[flag] = dst
+                    tol = 0.0 if dt_out == torch.float32 else 0.0
+                    d = (outs["0"].float() - outs["1"].float()).abs().max()
+                    assert float(d) <= 1e-6 * (1 if dt_out == torch.float32 else 0) + (4e-2 if dt_out == torch.bfloat16 else 0), \
+                        (n, h, w, c, f, ib, ob, dt_in, dt_out, tf, float(d))
+                    inner = outs["1"][:, ob:ob + h * f, ob:ob + w * f]
+                    assert float((inner[..., :8].float() - 7.0).abs().max()) == 0 and float((inner[..., 8 + c:].float() - 7.0).abs().max()) == 0
+                    if ob:
+                        assert float((outs["1"][:, 0].float() - 7.0).abs().max()) == 0        # the border is the caller's
+                    xr = x.to(dt_in).float()
+                    if tf:
+                        xr = F.leaky_relu(xr * a.cpu()[:, :, None, None] + b.cpu()[:, :, None, None], 0.25)
+                    want = F.interpolate(xr, (h * f, w * f), mode="bilinear")
+                    got = inner[..., 8:8 + c].float().permute(0, 3, 1, 2).cpu()
+                    assert (got - want).abs().max() <= (1e-5 if dt_out == torch.float32 else 4e-2) * max(1.0, float(want.abs().max()))
+    finally:
+        if old is None:
+            os.environ.pop("PPST_RESAMPLE_UP", None)
+        else:
+            os.environ["PPST_RESAMPLE_UP"] = old
+
+
 # ------------------------------------------------------------------------------------------------ dense / corr
 def test_linear_l2norm_lerp():
     from ppst_b200 import ops
