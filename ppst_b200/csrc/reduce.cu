@@ -148,29 +148,46 @@ __global__ void __launch_bounds__(kReduceThreads) plane_reduce_nhwc_kernel(
     // BORDER: (yy, xx) of pixel p tracked incrementally -- one division per thread, none per pixel (hw < 2^31, host-checked)
     int yy = BORDER ? (int)(beg + lane_p) / w_row : 0;
     int xx = BORDER ? (int)(beg + lane_p) - yy * w_row : 0;
-    for (int64_t p = beg + lane_p; p < end; p += planes) {
-      float xv[VEC];
-      int64_t po = p;
-      if (BORDER) {
-        po = (int64_t)yy * wp + xx;
-        xx += planes;
-        while (xx >= w_row) { xx -= w_row; ++yy; }
+    // UNR pixels per trip: their loads are issued together (one 16-byte load in flight per thread left the stream at
+    // 2.5 TB/s), then accumulated in pixel order -- the same order, so the same sums, as one pixel per trip
+    constexpr int UNR = (VEC > 1 && R == 1) ? 4 : 1;
+    for (int64_t p = beg + lane_p; p < end; p += (int64_t)planes * UNR) {
+      Vec16<T> v[UNR];
+      T v1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t pu = p + (int64_t)u * planes;
+        int64_t po = pu;
+        if (BORDER) {
+          po = (int64_t)yy * wp + xx;
+          xx += planes;
+          while (xx >= w_row) { xx -= w_row; ++yy; }
+        }
+        if (pu < end) {
+          if (VEC > 1) v[u] = ld_vec16_stream(base + po * c);
+          else v1[u] = base[po * c];
+        }
       }
-      if (VEC > 1) {
-        Vec16<T> v = ld_vec16_stream(base + po * c);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) xv[e] = Cvt<T>::to_f(v.v[e]);
-      } else {
-        xv[0] = Cvt<T>::to_f(base[po * c]);
-      }
-      const int L = (R > 1) ? pl[p] : 0;
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t pu = p + (int64_t)u * planes;
+        if (pu >= end) break;
+        float xv[VEC];
+        if (VEC > 1) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const bool in = (R == 1) || (label_mode ? (((L >> r) & 1) != 0) : (L == r));
+          for (int e = 0; e < VEC; ++e) xv[e] = Cvt<T>::to_f(v[u].v[e]);
+        } else {
+          xv[0] = Cvt<T>::to_f(v1[u]);
+        }
+        const int L = (R > 1) ? pl[pu] : 0;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          const float d = in ? xv[e] - sh[e] : 0.0f;
-          s[r][e] += d; q[r][e] = fmaf(d, d, q[r][e]); m[r][e] = fmaxf(m[r][e], in ? xv[e] : 0.0f);
+        for (int r = 0; r < R; ++r) {
+          const bool in = (R == 1) || (label_mode ? (((L >> r) & 1) != 0) : (L == r));
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const float d = in ? xv[e] - sh[e] : 0.0f;
+            s[r][e] += d; q[r][e] = fmaf(d, d, q[r][e]); m[r][e] = fmaxf(m[r][e], in ? xv[e] : 0.0f);
+          }
         }
       }
     }
